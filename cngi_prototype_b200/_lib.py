@@ -1,0 +1,143 @@
+"""ctypes binding of libcngi_b200.so (include/cngi_b200.h).
+
+There is NO CPU fallback: if the library is missing or no sm_100 device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libcngi_b200.so")
+
+F32, F64 = 0, 1
+CHAN_GENERAL, CHAN_CUBE, CHAN_CONTINUUM = 0, 1, 2
+ALGO_AUTO, ALGO_NAIVE, ALGO_TRACK = 0, 1, 2
+
+i64, i32, f64, vp = C.c_int64, C.c_int32, C.c_double, C.c_void_p
+
+
+class StdGridArgs(C.Structure):
+    _fields_ = [
+        ("n_time", i64), ("n_baseline", i64), ("n_chan", i64), ("n_pol", i64),
+        ("n_imag_chan", i64), ("n_imag_pol", i64), ("n_u", i64), ("n_v", i64),
+        ("vis", vp), ("weight", vp), ("flag", vp), ("uvw", vp), ("freq_chan", vp),
+        ("chan_map", vp), ("pol_map", vp), ("cgk_1D", vp), ("grid", vp), ("sum_weight", vp),
+        ("delta_lm", f64 * 2),
+        ("support", i32), ("oversampling", i32), ("precision", i32), ("do_psf", i32),
+        ("complex_grid", i32), ("chan_mode", i32), ("algorithm", i32), ("chan_group", i32),
+        ("time_segment", i32), ("reserved", i32),
+    ]
+
+
+class IwGridArgs(C.Structure):
+    _fields_ = [
+        ("n_time", i64), ("n_baseline", i64), ("n_chan", i64), ("n_pol", i64),
+        ("n_imag_chan", i64), ("n_imag_pol", i64), ("n_u", i64), ("n_v", i64),
+        ("weight", vp), ("uvw", vp), ("freq_chan", vp), ("chan_map", vp), ("pol_map", vp),
+        ("density", vp), ("sum_weight", vp),
+        ("delta_lm", f64 * 2),
+        ("precision", i32), ("chan_mode", i32),
+    ]
+
+
+class IwDegridArgs(C.Structure):
+    _fields_ = [
+        ("n_time", i64), ("n_baseline", i64), ("n_chan", i64), ("n_pol", i64),
+        ("n_imag_chan", i64), ("n_imag_pol", i64), ("n_u", i64), ("n_v", i64),
+        ("natural_weight", vp), ("uvw", vp), ("freq_chan", vp), ("chan_map", vp), ("pol_map", vp),
+        ("density", vp), ("density_stride", i64 * 4), ("briggs_factors", vp), ("imaging_weight", vp),
+        ("delta_lm", f64 * 2),
+        ("precision", i32), ("chan_mode", i32),
+    ]
+
+
+class ApertureGridArgs(C.Structure):
+    _fields_ = [
+        ("n_time", i64), ("n_baseline", i64), ("n_chan", i64), ("n_pol", i64),
+        ("n_imag_chan", i64), ("n_imag_pol", i64), ("n_u", i64), ("n_v", i64),
+        ("vis", vp), ("weight", vp), ("flag", vp), ("uvw", vp), ("freq_chan", vp),
+        ("chan_map", vp), ("pol_map", vp), ("field", vp), ("field_id", vp),
+        ("cf_baseline_map", vp), ("cf_chan_map", vp), ("cf_pol_map", vp),
+        ("conv_kernel", vp), ("weight_support", vp), ("phase_gradient", vp),
+        ("grid", vp), ("sum_weight", vp),
+        ("delta_lm", f64 * 2),
+        ("n_field", i64), ("n_cfb", i64), ("n_cfc", i64), ("n_cfp", i64), ("n_cu", i64), ("n_cv", i64),
+        ("oversampling", i32 * 2), ("max_support", i32), ("precision", i32), ("do_psf", i32),
+        ("chan_mode", i32),
+    ]
+
+
+class StdDegridArgs(C.Structure):
+    _fields_ = [
+        ("n_time", i64), ("n_baseline", i64), ("n_chan", i64), ("n_pol", i64),
+        ("n_imag_chan", i64), ("n_imag_pol", i64), ("n_u", i64), ("n_v", i64),
+        ("model_grid", vp), ("uvw", vp), ("freq_chan", vp), ("chan_map", vp), ("pol_map", vp),
+        ("cgk_1D", vp), ("vis", vp),
+        ("delta_lm", f64 * 2),
+        ("support", i32), ("oversampling", i32), ("precision", i32), ("chan_mode", i32),
+    ]
+
+
+class GridToImageArgs(C.Structure):
+    _fields_ = [
+        ("n_planes", i64), ("n_u", i64), ("n_v", i64), ("image_size", i64 * 2),
+        ("grid", vp), ("grid_is_complex", i32), ("precision", i32),
+        ("sum_weight", vp), ("corr_u", vp), ("corr_v", vp),
+        ("norm_image", vp), ("norm_image_planes", i64),
+        ("pb_image", vp), ("pb_image_planes", i64),
+        ("pb_limit", f64),
+        ("divide_by_centre", i32), ("single_precision_roundtrip", i32),
+        ("image", vp),
+    ]
+
+
+# every symbol include/cngi_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "cngi_b200_abi_version", "cngi_b200_last_error", "cngi_b200_check_device",
+    "cngi_b200_standard_grid", "cngi_b200_imaging_weight_grid", "cngi_b200_briggs_factors",
+    "cngi_b200_imaging_weight_degrid", "cngi_b200_aperture_grid", "cngi_b200_aperture_weight_grid",
+    "cngi_b200_standard_degrid", "cngi_b200_fft_plan_create", "cngi_b200_fft_plan_destroy",
+    "cngi_b200_grid_to_image", "cngi_b200_standard_grid_host",
+]
+
+_lib = None
+
+
+class CngiError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libcngi_b200.so.  Raises if it has not been built -- there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CngiError("%s not found: run `python -m cngi_prototype_b200.build` (needs nvcc). "
+                            "cngi_prototype_b200 has no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.cngi_b200_last_error.restype = C.c_char_p
+        L.cngi_b200_abi_version.restype = C.c_int
+        for name in EXPORTS:
+            getattr(L, name)  # AttributeError here means header and library disagree
+        L.cngi_b200_briggs_factors.argtypes = [vp, vp, vp, i64, i64, f64, i32, vp]
+        L.cngi_b200_fft_plan_create.argtypes = [C.POINTER(vp), i64, i64, i64, i32]
+        L.cngi_b200_fft_plan_destroy.argtypes = [vp]
+        L.cngi_b200_grid_to_image.argtypes = [vp, C.POINTER(GridToImageArgs), vp]
+        L.cngi_b200_standard_grid.argtypes = [C.POINTER(StdGridArgs), vp]
+        L.cngi_b200_standard_grid_host.argtypes = [C.POINTER(StdGridArgs), i64]
+        L.cngi_b200_imaging_weight_grid.argtypes = [C.POINTER(IwGridArgs), vp]
+        L.cngi_b200_imaging_weight_degrid.argtypes = [C.POINTER(IwDegridArgs), vp]
+        L.cngi_b200_aperture_grid.argtypes = [C.POINTER(ApertureGridArgs), vp]
+        L.cngi_b200_aperture_weight_grid.argtypes = [C.POINTER(ApertureGridArgs), vp]
+        L.cngi_b200_standard_degrid.argtypes = [C.POINTER(StdDegridArgs), vp]
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().cngi_b200_last_error()
+        raise CngiError("%s failed (status %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def require_device():
+    check(lib().cngi_b200_check_device(), "cngi_b200_check_device")

@@ -1,0 +1,269 @@
+// aperture_grid.cu -- A5/A6 of SURVEY.md section 8: A-projection / mosaic gridders.
+//   A5  _aperture_grid_jit         (/root/reference/ngcasa/imaging/_imaging_utils/_aperture_grid.py:376-513)
+//   A6  _aperture_weight_grid_jit  (_aperture_grid.py:180-291)
+//
+// The reference multiplies the whole CF stack by the pointing's phase gradient whenever the field changes
+// (_aperture_grid.py:428-430, O(n_cf * 160^2) per change); here the product CF[cf] * PG[field] is formed
+// on the fly for exactly the taps a sample reads, so the CF stack (real, L2 resident) and the per-field
+// phase gradients are only ever read.
+//
+// A5: one thread per (time, baseline, chan) sample, S_u x S_v reductions per polarisation (REDG.F32x2 /
+//     2 x REDG.F64).
+// A6: every sample stamps the SAME Su x Sv cells at the grid centre, so weights are first summed per
+//     (field, cf_baseline, cf_chan, cf_pol, image plane) bucket (warp-aggregated REDG into a small table) and a
+//     second tiny kernel multiplies each bucket by its CF*PG taps -- O(n_samples) + O(n_buckets * S^2)
+//     instead of O(n_samples * S^2) colliding atomics.
+#include "common.cuh"
+
+namespace cngi {
+
+struct ApParams {
+    int n_time, n_baseline, n_chan, n_pol;
+    int n_ic, n_ip, n_u, n_v;
+    const void *vis;
+    const void *weight;
+    const uint8_t *flag;
+    const double *uvw;
+    const double *freq;
+    const int64_t *chan_map, *pol_map, *field, *field_id, *cf_b_map, *cf_c_map, *cf_p_map, *support;
+    const double *ck;
+    const double2 *pg;
+    void *grid;
+    double *sum_weight;
+    double dl, dm;
+    int n_field, n_cfb, n_cfc, n_cfp, n_cu, n_cv;
+    int os_u, os_v, max_support, do_psf, chan_mode;
+    double *buckets;       // A6: [n_field, n_cfb, n_cfc, n_cfp, n_ic, n_ip] weight sums
+};
+
+__device__ __forceinline__ int ap_chan_of(const ApParams &p, int c)
+{
+    if (p.chan_mode == CNGI_CHAN_CUBE) return c;
+    if (p.chan_mode == CNGI_CHAN_CONTINUUM) return 0;
+    return (int)p.chan_map[c];
+}
+
+__device__ __forceinline__ int ap_find_field(const ApParams &p, long long f)
+{
+    for (int i = 0; i < p.n_field; ++i)
+        if (p.field_id[i] == f) return i;
+    return -1;
+}
+
+// per-sample geometry shared by A5 and A6: row/field skip, centre cell, full-support bounds test (:397,447)
+__device__ __forceinline__ bool ap_locate(const ApParams &p, long long tb, int c, int &field_indx, CellPos &cp)
+{
+    const long long f = p.field[tb];
+    if (!(f > -1)) return false;
+    field_indx = ap_find_field(p, f);
+    if (field_indx < 0) return false;
+    const double fr = p.freq[c];
+    if (!locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], uv_scale_of(fr, p.dl, p.n_u), uv_scale_of(fr, p.dm, p.n_v), p.n_u,
+                       p.n_v, cp))
+        return false;
+    return stamp_inside(cp.uc, cp.vc, p.max_support, p.n_u, p.n_v);
+}
+
+template <typename T> __global__ void __launch_bounds__(256) aperture_grid_kernel(ApParams p)
+{
+    using CT = typename Cplx<T>::type;
+    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % p.n_chan);
+    const long long tb = idx / p.n_chan;
+    const int b = (int)(tb % p.n_baseline);
+    int field_indx;
+    CellPos cp;
+    if (!ap_locate(p, tb, c, field_indx, cp)) return;
+    const int u_off = oversample_offset(cp.uc, cp.u_pos, p.os_u) + p.n_cu / 2;   // :448-451
+    const int v_off = oversample_offset(cp.vc, cp.v_pos, p.os_v) + p.n_cv / 2;
+    const int cf_b = (int)p.cf_b_map[b], cf_c = (int)p.cf_c_map[c];
+    const int a_chan = ap_chan_of(p, c);
+    const double2 *pg = p.pg + (long long)field_indx * p.n_cu * p.n_cv;
+    for (int ip = 0; ip < p.n_pol; ++ip) {
+        const long long s = idx * p.n_pol + ip;
+        const double w = (double)((const T *)p.weight)[s];
+        double wre = w, wim = 0.0;
+        if (!p.do_psf) {
+            const CT d = ((const CT *)p.vis)[s];
+            weighted_vis((double)d.x, (double)d.y, w, wre, wim);
+            if (p.flag && p.flag[s]) wre = nan("");
+        }
+        if (masked(wre, wim)) continue;
+        const int cf_p = (int)p.cf_p_map[ip];
+        const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
+        const long long cf = ((long long)cf_b * p.n_cfc + cf_c) * p.n_cfp + cf_p;
+        const int su = (int)p.support[cf * 2], sv = (int)p.support[cf * 2 + 1];
+        const double *ck = p.ck + cf * p.n_cu * p.n_cv;
+        CT *plane = (CT *)p.grid + ((long long)a_chan * p.n_ip + a_pol) * p.n_u * (long long)p.n_v;
+        double nre = 0.0, nim = 0.0;
+        for (int iu = -(su / 2); iu < su - su / 2; ++iu) {          // u outer: consecutive iv are contiguous in CF and grid
+            const int cf_u = p.os_u * iu + u_off;
+            CT *rowp = plane + (long long)(cp.uc + iu) * p.n_v + cp.vc;
+            for (int iv = -(sv / 2); iv < sv - sv / 2; ++iv) {
+                const int cf_v = p.os_v * iv + v_off;
+                const double k = ck[(long long)cf_u * p.n_cv + cf_v];
+                const double2 g = pg[(long long)cf_u * p.n_cv + cf_v];
+                const double cr = k * g.x, ci = k * g.y;                     // (k + 0j) * pg
+                CT val;
+                val.x = (T)(cr * wre - ci * wim);
+                val.y = (T)(cr * wim + ci * wre);
+                red_add(rowp + iv, val);
+                nre += cr;
+                nim += ci;
+            }
+        }
+        // psf: w * Re(norm); image: w * Re(norm^2)   (:508-511)
+        const double sw = p.do_psf ? w * nre : w * (nre * nre - nim * nim);
+        atomicAdd(p.sum_weight + a_chan * p.n_ip + a_pol, sw);
+    }
+}
+
+// A6 pass 1: bucket the weights
+template <typename T> __global__ void __launch_bounds__(256) aperture_weight_bucket_kernel(ApParams p)
+{
+    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % p.n_chan);
+    const long long tb = idx / p.n_chan;
+    const int b = (int)(tb % p.n_baseline);
+    int field_indx;
+    CellPos cp;
+    if (!ap_locate(p, tb, c, field_indx, cp)) return;
+    const int cf_b = (int)p.cf_b_map[b], cf_c = (int)p.cf_c_map[c];
+    const int a_chan = ap_chan_of(p, c);
+    for (int ip = 0; ip < p.n_pol; ++ip) {
+        const double w = (double)((const T *)p.weight)[idx * p.n_pol + ip];
+        if (isnan(w) || w == 0.0) continue;
+        const int cf_p = (int)p.cf_p_map[ip];
+        const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
+        const long long cf = (((long long)field_indx * p.n_cfb + cf_b) * p.n_cfc + cf_c) * p.n_cfp + cf_p;
+        atomicAdd(p.buckets + (cf * p.n_ic + a_chan) * p.n_ip + a_pol, w);
+    }
+}
+
+// A6 pass 2: one block per bucket; stamp bucket_weight * CF * PG at the grid centre (:276-289)
+template <typename T> __global__ void __launch_bounds__(256) aperture_weight_stamp_kernel(ApParams p)
+{
+    using CT = typename Cplx<T>::type;
+    const long long bucket = blockIdx.x;
+    const double w = p.buckets[bucket];
+    if (w == 0.0) return;
+    long long r = bucket;
+    const int a_pol = (int)(r % p.n_ip);
+    r /= p.n_ip;
+    const int a_chan = (int)(r % p.n_ic);
+    r /= p.n_ic;
+    const long long cf = r % ((long long)p.n_cfb * p.n_cfc * p.n_cfp);
+    const int field_indx = (int)(r / ((long long)p.n_cfb * p.n_cfc * p.n_cfp));
+    const int su = (int)p.support[cf * 2], sv = (int)p.support[cf * 2 + 1];
+    const double *ck = p.ck + cf * p.n_cu * p.n_cv;
+    const double2 *pg = p.pg + (long long)field_indx * p.n_cu * p.n_cv;
+    CT *plane = (CT *)p.grid + ((long long)a_chan * p.n_ip + a_pol) * p.n_u * (long long)p.n_v;
+    double nre = 0.0;
+    for (int e = threadIdx.x; e < su * sv; e += blockDim.x) {
+        const int iu = e / sv - su / 2, iv = e % sv - sv / 2;
+        const int cf_u = p.os_u * iu + p.n_cu / 2, cf_v = p.os_v * iv + p.n_cv / 2;
+        const double k = ck[(long long)cf_u * p.n_cv + cf_v];
+        const double2 g = pg[(long long)cf_u * p.n_cv + cf_v];
+        const double cr = k * g.x, ci = k * g.y;
+        CT val;
+        val.x = (T)(cr * w);
+        val.y = (T)(ci * w);
+        red_add(plane + (long long)(p.n_u / 2 + iu) * p.n_v + p.n_v / 2 + iv, val);
+        nre += cr;
+    }
+    __shared__ double part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nre += __shfl_xor_sync(0xffffffffu, nre, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = nre;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += part[i];
+        atomicAdd(p.sum_weight + a_chan * p.n_ip + a_pol, w * s);   // sum over samples of w*Re(norm) == (sum w)*Re(norm)
+    }
+}
+
+static int fill(ApParams &p, const cngi_aperture_grid_args *a, const char *who, bool need_vis)
+{
+    CNGI_REQUIRE(a != nullptr, "%s: null args", who);
+    CNGI_REQUIRE(a->weight && a->uvw && a->freq_chan && a->field && a->field_id && a->cf_baseline_map && a->cf_chan_map &&
+                     a->cf_pol_map && a->conv_kernel && a->weight_support && a->phase_gradient && a->grid && a->sum_weight,
+                 "%s: null array pointer", who);
+    CNGI_REQUIRE(!need_vis || a->vis, "%s: vis is null in image mode", who);
+    CNGI_REQUIRE(a->precision == CNGI_F32 || a->precision == CNGI_F64, "%s: bad precision", who);
+    CNGI_REQUIRE(a->chan_mode != CNGI_CHAN_GENERAL || a->chan_map, "%s: chan_map is null", who);
+    CNGI_REQUIRE(a->n_u > 0 && a->n_v > 0 && a->n_u < (1 << 24) && a->n_v < (1 << 24), "%s: bad grid size", who);
+    CNGI_REQUIRE(a->n_field > 0 && a->n_cfb > 0 && a->n_cfc > 0 && a->n_cfp > 0 && a->n_cu > 0 && a->n_cv > 0, "%s: bad CF shape", who);
+    CNGI_REQUIRE(a->max_support >= 1, "%s: max_support must be >= 1", who);
+    CNGI_REQUIRE(a->n_time * a->n_baseline < (1LL << 31), "%s: too many rows", who);
+    // every tap index os*i + off + centre must stay inside the CF
+    CNGI_REQUIRE((int64_t)a->oversampling[0] * (a->max_support / 2) + a->oversampling[0] / 2 + 1 <= a->n_cu / 2 + (a->n_cu % 2) &&
+                     (int64_t)a->oversampling[1] * (a->max_support / 2) + a->oversampling[1] / 2 + 1 <= a->n_cv / 2 + (a->n_cv % 2),
+                 "%s: CF of %lld x %lld is too small for support %d at oversampling %d x %d", who, (long long)a->n_cu,
+                 (long long)a->n_cv, a->max_support, a->oversampling[0], a->oversampling[1]);
+    p.n_time = (int)a->n_time, p.n_baseline = (int)a->n_baseline, p.n_chan = (int)a->n_chan, p.n_pol = (int)a->n_pol;
+    p.n_ic = (int)a->n_imag_chan, p.n_ip = (int)a->n_imag_pol, p.n_u = (int)a->n_u, p.n_v = (int)a->n_v;
+    p.vis = a->vis, p.weight = a->weight, p.flag = a->flag, p.uvw = a->uvw, p.freq = a->freq_chan;
+    p.chan_map = a->chan_map, p.pol_map = a->pol_map, p.field = a->field, p.field_id = a->field_id;
+    p.cf_b_map = a->cf_baseline_map, p.cf_c_map = a->cf_chan_map, p.cf_p_map = a->cf_pol_map, p.support = a->weight_support;
+    p.ck = a->conv_kernel, p.pg = (const double2 *)a->phase_gradient, p.grid = a->grid, p.sum_weight = a->sum_weight;
+    p.dl = a->delta_lm[0], p.dm = a->delta_lm[1];
+    p.n_field = (int)a->n_field, p.n_cfb = (int)a->n_cfb, p.n_cfc = (int)a->n_cfc, p.n_cfp = (int)a->n_cfp;
+    p.n_cu = (int)a->n_cu, p.n_cv = (int)a->n_cv, p.os_u = a->oversampling[0], p.os_v = a->oversampling[1];
+    p.max_support = a->max_support, p.do_psf = a->do_psf, p.chan_mode = a->chan_mode;
+    p.buckets = nullptr;
+    return CNGI_OK;
+}
+
+}  // namespace cngi
+
+extern "C" int cngi_b200_aperture_grid(const cngi_aperture_grid_args *a, void *stream)
+{
+    using namespace cngi;
+    ApParams p{};
+    int rc = fill(p, a, "aperture_grid", a && !a->do_psf);
+    if (rc != CNGI_OK) return rc;
+    if (p.do_psf) p.flag = nullptr;
+    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
+    if (total == 0 || p.n_pol == 0) return CNGI_OK;
+    const long long blocks = ceil_div(total, 256);
+    CNGI_REQUIRE(blocks < (1LL << 31), "aperture_grid: too many samples");
+    if (a->precision == CNGI_F32)
+        aperture_grid_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else
+        aperture_grid_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    CNGI_CUDA_TRY(cudaGetLastError());
+    return CNGI_OK;
+}
+
+extern "C" int cngi_b200_aperture_weight_grid(const cngi_aperture_grid_args *a, void *stream)
+{
+    using namespace cngi;
+    ApParams p{};
+    int rc = fill(p, a, "aperture_weight_grid", false);
+    if (rc != CNGI_OK) return rc;
+    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
+    if (total == 0 || p.n_pol == 0) return CNGI_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_buckets = (long long)p.n_field * p.n_cfb * p.n_cfc * p.n_cfp * p.n_ic * p.n_ip;
+    CNGI_REQUIRE(n_buckets < (1LL << 31), "aperture_weight_grid: too many (field, cf, plane) buckets");
+    CNGI_CUDA_TRY(cudaMallocAsync((void **)&p.buckets, n_buckets * sizeof(double), st));
+    CNGI_CUDA_TRY(cudaMemsetAsync(p.buckets, 0, n_buckets * sizeof(double), st));
+    const long long blocks = ceil_div(total, 256);
+    CNGI_REQUIRE(blocks < (1LL << 31), "aperture_weight_grid: too many samples");
+    if (a->precision == CNGI_F32) {
+        aperture_weight_bucket_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(p);
+        aperture_weight_stamp_kernel<float><<<(unsigned)n_buckets, 256, 0, st>>>(p);
+    } else {
+        aperture_weight_bucket_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(p);
+        aperture_weight_stamp_kernel<double><<<(unsigned)n_buckets, 256, 0, st>>>(p);
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(p.buckets, st);
+    CNGI_CUDA_TRY(e);
+    return CNGI_OK;
+}

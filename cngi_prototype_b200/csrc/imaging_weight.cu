@@ -1,0 +1,254 @@
+// imaging_weight.cu -- A2/A3/A4 of SURVEY.md section 8: Briggs / uniform imaging weights.
+//   A2  density grid      _standard_grid_jit with do_imaging_weight, support 1   (_standard_grid.py:306-369,
+//                         called from make_imaging_weight.py:153-161)
+//   A3  briggs factors    calculate_briggs_parms                                 (make_imaging_weight.py:198-213)
+//   A4  weight degrid     _standard_imaging_weight_degrid_jit                    (_standard_grid.py:466-518)
+// All three are HBM / L2-reduction bound (one or two cells per sample).  A2 walks each (baseline, chan)
+// track through time and run-length accumulates while the (cell, conjugate cell) pair is unchanged, so a
+// slowly moving baseline issues one pair of REDG.F64 per cell crossing rather than per sample.
+#include "common.cuh"
+
+namespace cngi {
+
+struct IwParams {
+    int n_time, n_baseline, n_chan, n_pol;
+    int n_ic, n_ip, n_u, n_v;
+    const void *weight;
+    const double *uvw;
+    const double *freq;
+    const int64_t *chan_map;
+    const int64_t *pol_map;
+    double *density;
+    double *sum_weight;
+    double dl, dm;
+    int chan_mode;
+    int seg_len, n_seg;
+    // degrid
+    const double *bf;
+    long long ds_u, ds_v, ds_c, ds_p;
+    void *out;
+};
+
+__device__ __forceinline__ int iw_chan_of(const IwParams &p, int c)
+{
+    if (p.chan_mode == CNGI_CHAN_CUBE) return c;
+    if (p.chan_mode == CNGI_CHAN_CONTINUUM) return 0;
+    return (int)p.chan_map[c];
+}
+
+// thread <-> (time segment, baseline, chan); chan fastest so weight loads coalesce across the warp
+template <typename T> __global__ void __launch_bounds__(256) iw_grid_kernel(IwParams p)
+{
+    const long long n_items = (long long)p.n_seg * p.n_baseline * p.n_chan;
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_items) return;
+    const int c = (int)(item % p.n_chan);
+    const long long r = item / p.n_chan;
+    const int b = (int)(r % p.n_baseline);
+    const int seg = (int)(r / p.n_baseline);
+    const int t_lo = seg * p.seg_len, t_hi = min(p.n_time, t_lo + p.seg_len);
+    const double f = p.freq[c];
+    const double us = uv_scale_of(f, p.dl, p.n_u), vs = uv_scale_of(f, p.dm, p.n_v);
+    const int a_chan = iw_chan_of(p, c);
+    const bool average = p.n_pol >= 2;               // (n_pol >= 2) and do_imaging_weight, :328-330
+    const double mid_u = (double)(p.n_u / 2), mid_v = (double)(p.n_v / 2);
+
+    int cur_u = -1, cur_v = 0, cur_cu = 0, cur_cv = 0;
+    double acc = 0.0, sw = 0.0;
+
+    auto flush = [&]() {
+        if (cur_u < 0 || acc == 0.0) return;
+        const bool conj_ok = cur_cu >= 0 && cur_cu < p.n_u && cur_cv >= 0 && cur_cv < p.n_v;
+        for (int ip = 0; ip < p.n_pol; ++ip) {
+            const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
+            double *plane = p.density + ((long long)a_chan * p.n_ip + a_pol) * p.n_u * (long long)p.n_v;
+            atomicAdd(plane + (long long)cur_u * p.n_v + cur_v, acc);
+            if (conj_ok) atomicAdd(plane + (long long)cur_cu * p.n_v + cur_cv, acc);
+        }
+        acc = 0.0;
+    };
+
+    for (int t = t_lo; t < t_hi; ++t) {
+        const long long tb = (long long)t * p.n_baseline + b;
+        CellPos cp;
+        if (!locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], us, vs, p.n_u, p.n_v, cp)) continue;
+        if (!stamp_inside(cp.uc, cp.vc, 0, p.n_u, p.n_v)) continue;
+        const T *w = (const T *)p.weight + (tb * p.n_chan + c) * p.n_pol;
+        const double wd = average ? __ddiv_rn(__dadd_rn((double)w[0], (double)w[1]), 2.0) : (double)w[0];
+        if (isnan(wd) || wd == 0.0) continue;
+        // conjugate cell: int(-u + centre + 0.5)   (:309-318)
+        const double un = -__dmul_rn(p.uvw[tb * 3], us), vn = -__dmul_rn(p.uvw[tb * 3 + 1], vs);
+        const int cu = __double2int_rz(__dadd_rn(__dadd_rn(un, mid_u), 0.5));
+        const int cv = __double2int_rz(__dadd_rn(__dadd_rn(vn, mid_v), 0.5));
+        if (cp.uc != cur_u || cp.vc != cur_v || cu != cur_cu || cv != cur_cv) {
+            flush();
+            cur_u = cp.uc, cur_v = cp.vc, cur_cu = cu, cur_cv = cv;
+        }
+        acc += wd;
+        sw += wd + wd;   // sum_weight gets sel_weight*norm twice (:366-369), norm == cgk_1D[0] == 1
+    }
+    flush();
+    if (sw != 0.0) {
+        for (int ip = 0; ip < p.n_pol; ++ip) {
+            const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
+            atomicAdd(p.sum_weight + a_chan * p.n_ip + a_pol, sw);
+        }
+    }
+}
+
+// sum of squares per plane -> bf[0][plane] (used as the accumulator, finalised below)
+__global__ void __launch_bounds__(256) iw_sumsq_kernel(const double *density, double *acc, long long n_cells)
+{
+    const int plane = blockIdx.y;
+    const double *d = density + (long long)plane * n_cells;
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (long long)gridDim.x * blockDim.x) {
+        const double x = d[i];
+        s = fma(x, x, s);
+    }
+    __shared__ double part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < 8 ? part[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(acc + plane, s);
+    }
+}
+
+__global__ void iw_briggs_finalize_kernel(double *bf, const double *sum_weight, long long n_planes, double k2, int weighting)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_planes) return;
+    if (weighting == 0) {   // briggs: (5*10^-robust)^2 / (sum(rho^2)/sum_weight), f1 = 1
+        bf[i] = __ddiv_rn(k2, __ddiv_rn(bf[i], sum_weight[i]));
+        bf[n_planes + i] = 1.0;
+    } else {                // uniform: f0 = 1, f1 = 0
+        bf[i] = 1.0;
+        bf[n_planes + i] = 0.0;
+    }
+}
+
+template <typename T> __global__ void __launch_bounds__(256) iw_degrid_kernel(IwParams p)
+{
+    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % p.n_chan);
+    const long long tb = idx / p.n_chan;
+    T *out = (T *)p.out + idx * p.n_pol;
+    const T *nat = (const T *)p.weight + idx * p.n_pol;
+    const double f = p.freq[c];
+    CellPos cp;
+    bool ok = locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], uv_scale_of(f, p.dl, p.n_u), uv_scale_of(f, p.dm, p.n_v),
+                            p.n_u, p.n_v, cp);
+    if (ok) ok = stamp_inside(cp.uc, cp.vc, 0, p.n_u, p.n_v);
+    if (!ok) {   // off-grid or NaN uv: output stays 0 (:460,493,502)
+        for (int ip = 0; ip < p.n_pol; ++ip) out[ip] = (T)0;
+        return;
+    }
+    const int a_chan = iw_chan_of(p, c);
+    const double avg = p.n_pol == 2 ? __ddiv_rn(__dadd_rn((double)nat[0], (double)nat[1]), 2.0) : 0.0;
+    for (int ip = 0; ip < p.n_pol; ++ip) {
+        const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
+        double iw = p.n_pol == 2 ? avg : (double)nat[ip];   // :508-511
+        const double w = (double)nat[ip];
+        if (!isnan(w) && w != 0.0) {
+            const double rho = p.density[cp.uc * p.ds_u + cp.vc * p.ds_v + a_chan * p.ds_c + a_pol * p.ds_p];
+            if (!isnan(rho) && rho != 0.0) {
+                const double f0 = p.bf[a_chan * p.n_ip + a_pol];
+                const double f1 = p.bf[((long long)p.n_ic + a_chan) * p.n_ip + a_pol];
+                iw = __ddiv_rn(iw, __dadd_rn(__dmul_rn(f0, rho), f1));   // :515-516
+            }
+        }
+        out[ip] = (T)iw;
+    }
+}
+
+}  // namespace cngi
+
+extern "C" int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *a, void *stream)
+{
+    using namespace cngi;
+    CNGI_REQUIRE(a != nullptr, "imaging_weight_grid: null args");
+    CNGI_REQUIRE(a->weight && a->uvw && a->freq_chan && a->density && a->sum_weight, "imaging_weight_grid: null array pointer");
+    CNGI_REQUIRE(a->precision == CNGI_F32 || a->precision == CNGI_F64, "imaging_weight_grid: bad precision");
+    CNGI_REQUIRE(a->n_u > 0 && a->n_v > 0 && a->n_u < (1 << 24) && a->n_v < (1 << 24), "imaging_weight_grid: bad grid size");
+    CNGI_REQUIRE(a->chan_mode != CNGI_CHAN_GENERAL || a->chan_map, "imaging_weight_grid: chan_map is null");
+    CNGI_REQUIRE(a->n_time * a->n_baseline < (1LL << 31), "imaging_weight_grid: too many rows");
+    if (a->n_time == 0 || a->n_baseline == 0 || a->n_chan == 0 || a->n_pol == 0) return CNGI_OK;
+    IwParams p{};
+    p.n_time = (int)a->n_time, p.n_baseline = (int)a->n_baseline, p.n_chan = (int)a->n_chan, p.n_pol = (int)a->n_pol;
+    p.n_ic = (int)a->n_imag_chan, p.n_ip = (int)a->n_imag_pol, p.n_u = (int)a->n_u, p.n_v = (int)a->n_v;
+    p.weight = a->weight, p.uvw = a->uvw, p.freq = a->freq_chan, p.chan_map = a->chan_map, p.pol_map = a->pol_map;
+    p.density = a->density, p.sum_weight = a->sum_weight, p.dl = a->delta_lm[0], p.dm = a->delta_lm[1];
+    p.chan_mode = a->chan_mode;
+    const long long per_seg = (long long)p.n_baseline * p.n_chan;
+    long long n_seg = ceil_div((long long)sm_count() * 2048 * 4, per_seg);   // ~4 waves of full occupancy
+    if (n_seg < 1) n_seg = 1;
+    p.seg_len = (int)ceil_div(p.n_time, n_seg);
+    if (p.seg_len < 16) p.seg_len = 16;
+    p.n_seg = (int)ceil_div(p.n_time, p.seg_len);
+    const long long blocks = ceil_div(per_seg * p.n_seg, 256);
+    CNGI_REQUIRE(blocks < (1LL << 31), "imaging_weight_grid: too many work items");
+    if (a->precision == CNGI_F32)
+        iw_grid_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else
+        iw_grid_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    CNGI_CUDA_TRY(cudaGetLastError());
+    return CNGI_OK;
+}
+
+extern "C" int cngi_b200_briggs_factors(const double *density, const double *sum_weight, double *briggs_factors,
+                                        int64_t n_planes, int64_t n_cells, double robust, int32_t weighting, void *stream)
+{
+    using namespace cngi;
+    CNGI_REQUIRE(density && sum_weight && briggs_factors, "briggs_factors: null pointer");
+    CNGI_REQUIRE(n_planes > 0 && n_planes < 65536 && n_cells > 0, "briggs_factors: bad sizes");
+    CNGI_REQUIRE(weighting == 0 || weighting == 1, "briggs_factors: weighting must be 0 (briggs) or 1 (uniform)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (weighting == 0) {
+        CNGI_CUDA_TRY(cudaMemsetAsync(briggs_factors, 0, n_planes * sizeof(double), st));
+        long long bx = ceil_div(n_cells, 256 * 8);
+        const long long cap = ceil_div((long long)sm_count() * 8, n_planes);
+        if (bx > cap) bx = cap;
+        if (bx < 1) bx = 1;
+        iw_sumsq_kernel<<<dim3((unsigned)bx, (unsigned)n_planes), 256, 0, st>>>(density, briggs_factors, n_cells);
+        CNGI_CUDA_TRY(cudaGetLastError());
+    }
+    const double k = 5.0 * pow(10.0, -robust);
+    iw_briggs_finalize_kernel<<<(unsigned)ceil_div(n_planes, 128), 128, 0, st>>>(briggs_factors, sum_weight, n_planes, k * k,
+                                                                                weighting);
+    CNGI_CUDA_TRY(cudaGetLastError());
+    return CNGI_OK;
+}
+
+extern "C" int cngi_b200_imaging_weight_degrid(const cngi_iw_degrid_args *a, void *stream)
+{
+    using namespace cngi;
+    CNGI_REQUIRE(a != nullptr, "imaging_weight_degrid: null args");
+    CNGI_REQUIRE(a->natural_weight && a->uvw && a->freq_chan && a->density && a->briggs_factors && a->imaging_weight,
+                 "imaging_weight_degrid: null array pointer");
+    CNGI_REQUIRE(a->precision == CNGI_F32 || a->precision == CNGI_F64, "imaging_weight_degrid: bad precision");
+    CNGI_REQUIRE(a->chan_mode != CNGI_CHAN_GENERAL || a->chan_map, "imaging_weight_degrid: chan_map is null");
+    const long long total = (long long)a->n_time * a->n_baseline * a->n_chan;
+    if (total == 0 || a->n_pol == 0) return CNGI_OK;
+    IwParams p{};
+    p.n_time = (int)a->n_time, p.n_baseline = (int)a->n_baseline, p.n_chan = (int)a->n_chan, p.n_pol = (int)a->n_pol;
+    p.n_ic = (int)a->n_imag_chan, p.n_ip = (int)a->n_imag_pol, p.n_u = (int)a->n_u, p.n_v = (int)a->n_v;
+    p.weight = a->natural_weight, p.uvw = a->uvw, p.freq = a->freq_chan, p.chan_map = a->chan_map, p.pol_map = a->pol_map;
+    p.density = const_cast<double *>(a->density), p.dl = a->delta_lm[0], p.dm = a->delta_lm[1], p.chan_mode = a->chan_mode;
+    p.bf = a->briggs_factors, p.out = a->imaging_weight;
+    p.ds_u = a->density_stride[0], p.ds_v = a->density_stride[1], p.ds_c = a->density_stride[2], p.ds_p = a->density_stride[3];
+    const long long blocks = ceil_div(total, 256);
+    CNGI_REQUIRE(blocks < (1LL << 31), "imaging_weight_degrid: too many samples");
+    if (a->precision == CNGI_F32)
+        iw_degrid_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else
+        iw_degrid_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    CNGI_CUDA_TRY(cudaGetLastError());
+    return CNGI_OK;
+}

@@ -1,0 +1,624 @@
+// standard_grid.cu -- A1/A2 of SURVEY.md section 8: the prolate-spheroidal convolutional gridder.
+// Replaces _standard_grid_jit (/root/reference/ngcasa/imaging/_imaging_utils/_standard_grid.py:242-371).
+//
+// Two kernels:
+//
+//  * std_grid_naive_kernel  -- one thread per (time, baseline, chan) sample, S*S global reductions per
+//    polarisation.  Order-independent, any support; it is the correctness anchor and the fallback for
+//    supports the track kernel is not instantiated for.
+//
+//  * std_grid_track_kernel  -- the product kernel.  A work item walks ONE baseline through time (and
+//    through `G` neighbouring channels when they share an image plane) and keeps the S x S stamp it is
+//    currently under in REGISTERS: S lanes per item, lane r owns the grid column u == r (mod S) and holds
+//    S accumulators (v == j (mod S)) per polarisation.  Because a baseline moves a fraction of a cell per
+//    integration, a sample usually lands on the same S x S cells as the previous one, so accumulators
+//    are flushed to the grid (native REDG.ADD.F32x2 / F64) only when their cell leaves the stamp --
+//    typically a few reductions per sample instead of S*S.  There is no shared-memory fp atomic anywhere:
+//    on sm_100a those compile to ATOMS.CAST.SPIN loops (checked with cuobjdump), REDG is native.
+//
+//    Each warp runs a two-phase loop over rounds of 32 samples:
+//      phase 1 (32 lanes, one sample each): coalesced vectorised loads of vis/weight/flag (+ uvw),
+//        fp64 bit-exact cell/offset/mask math, tap lookup from the shared-memory CF table, and staging of
+//        {cell ids, weighted data, the S u-taps and S v-taps in residue order} into the warp's slice of
+//        shared memory;
+//      phase 2 (S lanes per item, IPW items per warp): each item consumes its staged samples in order,
+//        broadcast-reading the records, flushing on cell change, then S*PP FMAs per lane.
+//    Only __syncwarp() separates the phases; warps never wait for each other.
+#include "common.cuh"
+
+namespace cngi {
+
+struct StdParams {
+    int n_time, n_baseline, n_chan, n_pol;
+    int n_ic, n_ip, n_u, n_v;
+    const void *vis;
+    const void *weight;
+    const uint8_t *flag;
+    const double *uvw;
+    const double *freq;
+    const int64_t *chan_map;
+    const int64_t *pol_map;
+    const double *cgk;
+    void *grid;
+    double *sum_weight;
+    double dl, dm;
+    int support, oversampling, do_psf, chan_mode;
+    int table_len;
+    // track kernel decomposition
+    int G, log2G, seg_len, n_seg, n_cspan, n_pgrp;
+    long long n_tasks;
+};
+
+__device__ __forceinline__ int chan_of(const StdParams &p, int c)
+{
+    if (p.chan_mode == CNGI_CHAN_CUBE) return c;
+    if (p.chan_mode == CNGI_CHAN_CONTINUUM) return 0;
+    return (int)p.chan_map[c];
+}
+__device__ __forceinline__ int pol_of(const StdParams &p, int ip) { return p.pol_map ? (int)p.pol_map[ip] : ip; }
+
+// Adds `val` into base[index] with one reduction per distinct index in the warp when the warp hits at
+// most two distinct indices (continuum imaging: every lane hits the same sum_weight slot).
+__device__ __forceinline__ void warp_grouped_add(double *base, int index, double val, bool active)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(FULL, active);
+    for (int round = 0; round < 2 && todo; ++round) {
+        const int leader = __ffs(todo) - 1;
+        const int idx0 = __shfl_sync(FULL, index, leader);
+        const bool mine = active && (index == idx0) && ((todo >> lane) & 1u);
+        const unsigned grp = __ballot_sync(FULL, mine);
+        double v = mine ? val : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == leader) atomicAdd(base + idx0, v);
+        todo &= ~grp;
+    }
+    if ((todo >> lane) & 1u) atomicAdd(base + index, val);
+}
+
+// ------------------------------------------------------------------------------------------------
+//  naive kernel
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool CPLX>
+__global__ void __launch_bounds__(256) std_grid_naive_kernel(StdParams p)
+{
+    using CT = typename Cplx<T>::type;
+    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = idx < total;
+    const int c = in_range ? (int)(idx % p.n_chan) : 0;
+    const long long tb = in_range ? idx / p.n_chan : 0;
+    const int half = p.support / 2;
+    CellPos cp;
+    bool ok = in_range;
+    if (ok) {
+        const double us = uv_scale_of(p.freq[c], p.dl, p.n_u);
+        const double vs = uv_scale_of(p.freq[c], p.dm, p.n_v);
+        ok = locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], us, vs, p.n_u, p.n_v, cp);
+    }
+    if (ok) ok = stamp_inside(cp.uc, cp.vc, half, p.n_u, p.n_v);
+    int uoff = 0, voff = 0, a_chan = 0;
+    if (ok) {
+        uoff = oversample_offset(cp.uc, cp.u_pos, p.oversampling);
+        voff = oversample_offset(cp.vc, cp.v_pos, p.oversampling);
+        a_chan = chan_of(p, c);
+    }
+    for (int ip = 0; ip < p.n_pol; ++ip) {   // uniform trip count: the warp-level reduction below needs it
+        bool use = ok;
+        double w = 0.0, wre = 0.0, wim = 0.0;
+        int a_pol = 0;
+        if (use) {
+            const long long s = idx * p.n_pol + ip;
+            w = (double)((const T *)p.weight)[s];
+            if (p.do_psf) {
+                wre = w;
+            } else {
+                const CT d = ((const CT *)p.vis)[s];
+                weighted_vis((double)d.x, (double)d.y, w, wre, wim);
+                if (p.flag && p.flag[s]) wre = nan("");
+            }
+            use = !masked(wre, wim);
+        }
+        double norm = 0.0;
+        if (use) {
+            a_pol = pol_of(p, ip);
+            const long long plane = ((long long)a_chan * p.n_ip + a_pol) * p.n_u;
+            for (int iv = -half; iv < p.support - half; ++iv) {
+                const double cv = p.cgk[abs(p.oversampling * iv + voff)];
+                for (int iu = -half; iu < p.support - half; ++iu) {
+                    const double conv = p.cgk[abs(p.oversampling * iu + uoff)] * cv;
+                    const long long cell = (plane + cp.uc + iu) * p.n_v + cp.vc + iv;
+                    if (CPLX) {
+                        CT val;
+                        val.x = (T)(conv * wre);
+                        val.y = (T)(conv * wim);
+                        red_add((CT *)p.grid + cell, val);
+                    } else {
+                        red_add((T *)p.grid + cell, (T)(conv * wre));
+                    }
+                    norm += conv;
+                }
+            }
+        }
+        warp_grouped_add(p.sum_weight, a_chan * p.n_ip + a_pol, w * norm, use);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+//  track kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kTrackBlock = 256;
+
+template <typename T, bool CPLX, int S, int PP> struct TrackCfg {
+    static constexpr int IPW = (S <= 3) ? 8 : (S <= 7) ? 4 : (S <= 15) ? 2 : 1;   // items per warp
+    static constexpr int ITER = 32 / IPW;                                         // samples per item per round
+    static constexpr int NC = CPLX ? 2 : 1;
+    static constexpr int TPV = 16 / (int)sizeof(T);                               // T's per 16-byte vector
+    static constexpr int SP = (S + TPV - 1) / TPV * TPV;                          // padded tap count
+    static constexpr int WD = (PP * NC + TPV - 1) / TPV * TPV;                    // padded weighted-data count
+    static constexpr int OFF_IDX = 0;
+    static constexpr int OFF_WD = 16;
+    static constexpr int OFF_CV = OFF_WD + WD * (int)sizeof(T);
+    static constexpr int OFF_CU = OFF_CV + SP * (int)sizeof(T);
+    static constexpr int RAW_BYTES = OFF_CU + SP * (int)sizeof(T);
+    // 16 * odd bytes per record: a quarter warp of 128-bit stores then covers all 32 banks.
+    static constexpr int REC_BYTES = ((RAW_BYTES / 16) % 2 == 0) ? RAW_BYTES + 16 : RAW_BYTES;
+    static constexpr int WARP_BYTES = 32 * REC_BYTES;
+};
+
+template <typename T, bool CPLX, int S, int PP>
+__global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p)
+{
+    using Cfg = TrackCfg<T, CPLX, S, PP>;
+    using CT = typename Cplx<T>::type;
+    constexpr int IPW = Cfg::IPW, ITER = Cfg::ITER, SP = Cfg::SP, NC = Cfg::NC;
+    constexpr int HALF = S / 2;
+    const unsigned FULL = 0xffffffffu;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    T *table = reinterpret_cast<T *>(smem);
+    const int table_bytes = (p.table_len * (int)sizeof(T) + 15) / 16 * 16;
+    for (int i = threadIdx.x; i < p.table_len; i += blockDim.x) table[i] = (T)p.cgk[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * (kTrackBlock / 32) + warp;
+    if (task >= p.n_tasks) return;   // no block-wide barrier after this point
+    unsigned char *wbuf = smem + table_bytes + warp * Cfg::WARP_BYTES;
+
+    // ---- task decode: (time segment, baseline, pol group, channel span), channel span fastest ------
+    const int cspan = (int)(task % p.n_cspan);
+    long long rest = task / p.n_cspan;
+    const int pgrp = (int)(rest % p.n_pgrp);
+    rest /= p.n_pgrp;
+    const int b = (int)(rest % p.n_baseline);
+    const int seg = (int)(rest / p.n_baseline);
+    const int t_lo = seg * p.seg_len;
+    const int t_hi = min(p.n_time, t_lo + p.seg_len);
+    const int G = p.G;
+    const int spr = ITER >> p.log2G;   // time steps per round
+    const int c_base = cspan * IPW * G;
+    const int p0 = pgrp * PP;
+    const int npol = min(PP, p.n_pol - p0);
+
+    // ---- phase-1 role: lane <-> staged sample ------------------------------------------------------
+    const int k1 = lane % IPW;
+    const int q1 = lane / IPW;
+    const int g1 = q1 & (G - 1);
+    const int row1 = q1 >> p.log2G;
+    const int c1 = c_base + k1 * G + g1;
+    const bool chan_ok = c1 < p.n_chan;
+    double us = 0.0, vs = 0.0;
+    int a_chan1 = 0;
+    if (chan_ok) {
+        const double f = p.freq[c1];
+        us = uv_scale_of(f, p.dl, p.n_u);
+        vs = uv_scale_of(f, p.dm, p.n_v);
+        a_chan1 = chan_of(p, c1);
+    }
+    double sw_acc[PP];
+#pragma unroll
+    for (int ip = 0; ip < PP; ++ip) sw_acc[ip] = 0.0;
+
+    // ---- phase-2 role: lane <-> (item, u residue) --------------------------------------------------
+    const bool active2 = lane < IPW * S;
+    const int k2 = lane / S;
+    const int r2 = lane - k2 * S;
+    int apol[PP];
+#pragma unroll
+    for (int ip = 0; ip < PP; ++ip) apol[ip] = (ip < npol) ? pol_of(p, p0 + ip) : 0;
+    T acc_re[S][PP], acc_im[S][PP];
+#pragma unroll
+    for (int j = 0; j < S; ++j)
+#pragma unroll
+        for (int ip = 0; ip < PP; ++ip) acc_re[j][ip] = acc_im[j][ip] = (T)0;
+    int cur_plane = -1, cur_u = -1, cur_vc = 0, cur_vcm = 0;
+
+    auto v_cell = [&](int j, int vc, int vcm) {   // the v in [vc-HALF, vc+HALF] with v == j (mod S)
+        int tv = vcm - j;
+        if (tv < 0) tv += S;
+        return vc + HALF - tv;
+    };
+    auto flush_one = [&](int j, int v) {
+#pragma unroll
+        for (int ip = 0; ip < PP; ++ip) {
+            if (ip < npol) {
+                const long long cell = (((long long)cur_plane * p.n_ip + apol[ip]) * p.n_u + cur_u) * p.n_v + v;
+                if (CPLX) {
+                    if (acc_re[j][ip] != (T)0 || acc_im[j][ip] != (T)0) {
+                        CT val;
+                        val.x = acc_re[j][ip];
+                        val.y = acc_im[j][ip];
+                        red_add((CT *)p.grid + cell, val);
+                    }
+                } else {
+                    if (acc_re[j][ip] != (T)0) red_add((T *)p.grid + cell, acc_re[j][ip]);
+                }
+            }
+            acc_re[j][ip] = (T)0;
+            acc_im[j][ip] = (T)0;
+        }
+    };
+
+    // ---- raw sample registers (software prefetch: loads of round n+1 fly during phase 2 of round n) --
+    double raw_u = 0.0, raw_v = 0.0;
+    CT raw_vis[PP];
+    T raw_w[PP];
+    unsigned raw_flag = 0;
+    bool raw_ok = false;
+    auto load_raw = [&](int t0) {
+        const int t = t0 + row1;
+        raw_ok = chan_ok && (row1 < spr) && (t < t_hi);
+        raw_flag = 0;
+        if (raw_ok) {
+            const long long tb = (long long)t * p.n_baseline + b;
+            raw_u = p.uvw[tb * 3];
+            raw_v = p.uvw[tb * 3 + 1];
+            const long long s = (tb * p.n_chan + c1) * p.n_pol + p0;
+            if (PP == 2 && npol == 2 && (p.n_pol & 1) == 0) {   // 2 pols, aligned: one vector load each
+                const T *wp = (const T *)p.weight + s;
+                if (sizeof(T) == 4) {
+                    const float2 w2 = *reinterpret_cast<const float2 *>(wp);
+                    raw_w[0] = (T)w2.x;
+                    raw_w[PP - 1] = (T)w2.y;
+                } else {
+                    const double2 w2 = *reinterpret_cast<const double2 *>(wp);
+                    raw_w[0] = (T)w2.x;
+                    raw_w[PP - 1] = (T)w2.y;
+                }
+                if (!p.do_psf) {
+                    if (sizeof(T) == 4) {
+                        const float4 d = *reinterpret_cast<const float4 *>((const CT *)p.vis + s);
+                        raw_vis[0].x = (T)d.x;
+                        raw_vis[0].y = (T)d.y;
+                        raw_vis[PP - 1].x = (T)d.z;
+                        raw_vis[PP - 1].y = (T)d.w;
+                    } else {
+                        raw_vis[0] = ((const CT *)p.vis)[s];
+                        raw_vis[PP - 1] = ((const CT *)p.vis)[s + 1];
+                    }
+                    if (p.flag) {
+                        const uchar2 f2 = *reinterpret_cast<const uchar2 *>(p.flag + s);
+                        raw_flag = (f2.x ? 1u : 0u) | (f2.y ? 2u : 0u);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int ip = 0; ip < PP; ++ip) {
+                    if (ip < npol) {
+                        raw_w[ip] = ((const T *)p.weight)[s + ip];
+                        if (!p.do_psf) {
+                            raw_vis[ip] = ((const CT *)p.vis)[s + ip];
+                            if (p.flag && p.flag[s + ip]) raw_flag |= 1u << ip;
+                        }
+                    }
+                }
+            }
+        }
+    };
+
+    // ---- phase 1: locate, mask, look up taps, stage ------------------------------------------------
+    auto stage = [&]() {
+        unsigned char *rec = wbuf + lane * Cfg::REC_BYTES;
+        int4 idx = make_int4(-1, 0, 0, 0);
+        CellPos cp;
+        bool ok = raw_ok && locate_centre(raw_u, raw_v, us, vs, p.n_u, p.n_v, cp);
+        if (ok) ok = stamp_inside(cp.uc, cp.vc, HALF, p.n_u, p.n_v);
+        if (ok) {
+            T wd[Cfg::WD];
+#pragma unroll
+            for (int i = 0; i < Cfg::WD; ++i) wd[i] = (T)0;
+            double wsel[PP];
+            bool any = false;
+#pragma unroll
+            for (int ip = 0; ip < PP; ++ip) {
+                wsel[ip] = 0.0;
+                if (ip < npol) {
+                    const double w = (double)raw_w[ip];
+                    double wre = w, wim = 0.0;
+                    if (!p.do_psf) {
+                        weighted_vis((double)raw_vis[ip].x, (double)raw_vis[ip].y, w, wre, wim);
+                        if (raw_flag & (1u << ip)) wre = nan("");
+                    }
+                    if (!masked(wre, wim)) {
+                        any = true;
+                        wsel[ip] = w;
+                        wd[ip * NC] = (T)wre;
+                        if (CPLX) wd[ip * NC + NC - 1] = (T)wim;
+                    }
+                }
+            }
+            if (any) {
+                const int uoff = oversample_offset(cp.uc, cp.u_pos, p.oversampling);
+                const int voff = oversample_offset(cp.vc, cp.v_pos, p.oversampling);
+                const int ub = (cp.uc - HALF) % S;   // residue of the first stamp column / row
+                const int vb = (cp.vc - HALF) % S;
+                T *rcu = reinterpret_cast<T *>(rec + Cfg::OFF_CU);
+                T *rcv = reinterpret_cast<T *>(rec + Cfg::OFF_CV);
+                double su = 0.0, sv = 0.0;
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    const T tu = table[abs(p.oversampling * (q - HALF) + uoff)];
+                    const T tv = table[abs(p.oversampling * (q - HALF) + voff)];
+                    int ju = ub + q;
+                    if (ju >= S) ju -= S;
+                    int jv = vb + q;
+                    if (jv >= S) jv -= S;
+                    rcu[ju] = tu;
+                    rcv[jv] = tv;
+                    su += (double)tu;
+                    sv += (double)tv;
+                }
+                const double norm = su * sv;   // == sum over the stamp of cu*cv
+#pragma unroll
+                for (int ip = 0; ip < PP; ++ip) sw_acc[ip] += wsel[ip] * norm;
+                T *rwd = reinterpret_cast<T *>(rec + Cfg::OFF_WD);
+                if (sizeof(T) == 4) {
+#pragma unroll
+                    for (int i = 0; i < Cfg::WD; i += 4)
+                        *reinterpret_cast<float4 *>(rwd + i) = make_float4(wd[i], wd[i + 1], wd[i + 2], wd[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < Cfg::WD; i += 2)
+                        *reinterpret_cast<double2 *>(rwd + i) = make_double2(wd[i], wd[i + 1]);
+                }
+                const int ucm = (ub == 0) ? S - 1 : ub - 1;   // (uc + HALF) mod S
+                const int vcm = (vb == 0) ? S - 1 : vb - 1;
+                idx = make_int4(cp.uc, cp.vc, a_chan1, ucm | (vcm << 8));
+            }
+        }
+        *reinterpret_cast<int4 *>(rec + Cfg::OFF_IDX) = idx;
+    };
+
+    // ---- phase 2: consume ----------------------------------------------------------------------------
+    auto consume = [&]() {
+#pragma unroll 1
+        for (int i = 0; i < ITER; ++i) {
+            const unsigned char *rec = wbuf + (i * IPW + k2) * Cfg::REC_BYTES;
+            const int4 idx = *reinterpret_cast<const int4 *>(rec + Cfg::OFF_IDX);
+            if (idx.x < 0) continue;
+            int tu = (idx.w & 0xff) - r2;
+            if (tu < 0) tu += S;
+            const int my_u = idx.x + HALF - tu;
+            const int vc = idx.y, vcm = idx.w >> 8;
+            if (my_u != cur_u || idx.z != cur_plane) {
+                if (cur_u >= 0) {
+#pragma unroll
+                    for (int j = 0; j < S; ++j) flush_one(j, v_cell(j, cur_vc, cur_vcm));
+                }
+                cur_u = my_u;
+                cur_plane = idx.z;
+                cur_vc = vc;
+                cur_vcm = vcm;
+            } else if (vc != cur_vc) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const int old_v = v_cell(j, cur_vc, cur_vcm);
+                    if (old_v != v_cell(j, vc, vcm)) flush_one(j, old_v);
+                }
+                cur_vc = vc;
+                cur_vcm = vcm;
+            }
+            const T cu = reinterpret_cast<const T *>(rec + Cfg::OFF_CU)[r2];
+            T cv[SP], wd[Cfg::WD];
+            if (sizeof(T) == 4) {
+#pragma unroll
+                for (int q = 0; q < SP; q += 4) {
+                    const float4 x = *reinterpret_cast<const float4 *>(rec + Cfg::OFF_CV + q * 4);
+                    cv[q] = x.x, cv[q + 1] = x.y, cv[q + 2] = x.z, cv[q + 3] = x.w;
+                }
+#pragma unroll
+                for (int q = 0; q < Cfg::WD; q += 4) {
+                    const float4 x = *reinterpret_cast<const float4 *>(rec + Cfg::OFF_WD + q * 4);
+                    wd[q] = x.x, wd[q + 1] = x.y, wd[q + 2] = x.z, wd[q + 3] = x.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < SP; q += 2) {
+                    const double2 x = *reinterpret_cast<const double2 *>(rec + Cfg::OFF_CV + q * 8);
+                    cv[q] = x.x, cv[q + 1] = x.y;
+                }
+#pragma unroll
+                for (int q = 0; q < Cfg::WD; q += 2) {
+                    const double2 x = *reinterpret_cast<const double2 *>(rec + Cfg::OFF_WD + q * 8);
+                    wd[q] = x.x, wd[q + 1] = x.y;
+                }
+            }
+#pragma unroll
+            for (int ip = 0; ip < PP; ++ip) {
+                const T tre = cu * wd[ip * NC];
+                const T tim = CPLX ? cu * wd[ip * NC + NC - 1] : (T)0;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    acc_re[j][ip] = fma(tre, cv[j], acc_re[j][ip]);
+                    if (CPLX) acc_im[j][ip] = fma(tim, cv[j], acc_im[j][ip]);
+                }
+            }
+        }
+    };
+
+    // ---- main loop over rounds ---------------------------------------------------------------------
+    load_raw(t_lo);
+    for (int t0 = t_lo; t0 < t_hi; t0 += spr) {
+        stage();
+        __syncwarp();
+        if (t0 + spr < t_hi) load_raw(t0 + spr);
+        if (active2) consume();
+        __syncwarp();
+    }
+    if (active2 && cur_u >= 0) {
+#pragma unroll
+        for (int j = 0; j < S; ++j) flush_one(j, v_cell(j, cur_vc, cur_vcm));
+    }
+
+    // ---- sum_weight: lanes that share a channel reduce first, then one reduction per image plane -------
+    const int span = IPW * G;   // lanes L and L + span handle the same channel
+#pragma unroll
+    for (int ip = 0; ip < PP; ++ip) {
+        double v = sw_acc[ip];
+        for (int o = span; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+        const bool lead = (lane < span) && chan_ok && (ip < npol);
+        warp_grouped_add(p.sum_weight, a_chan1 * p.n_ip + apol[ip], v, lead);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+//  host launchers
+// ------------------------------------------------------------------------------------------------
+static int validate(const cngi_std_grid_args *a)
+{
+    CNGI_REQUIRE(a != nullptr, "standard_grid: null args");
+    CNGI_REQUIRE(a->n_time >= 0 && a->n_baseline >= 0 && a->n_chan >= 0 && a->n_pol >= 0,
+                 "standard_grid: negative sample dimension");
+    CNGI_REQUIRE(a->n_u > 0 && a->n_v > 0 && a->n_imag_chan > 0 && a->n_imag_pol > 0, "standard_grid: empty grid");
+    CNGI_REQUIRE(a->n_u < (1 << 24) && a->n_v < (1 << 24), "standard_grid: grid side too large");
+    CNGI_REQUIRE(a->n_imag_chan * a->n_u < (1LL << 31), "standard_grid: n_imag_chan*n_u overflows int32");
+    CNGI_REQUIRE(a->n_time * a->n_baseline < (1LL << 31) && a->n_chan < (1 << 24) && a->n_pol <= 64,
+                 "standard_grid: sample dimensions out of range");
+    CNGI_REQUIRE(a->precision == CNGI_F32 || a->precision == CNGI_F64, "standard_grid: bad precision %d", a->precision);
+    CNGI_REQUIRE(a->support >= 1 && a->oversampling >= 0, "standard_grid: bad support/oversampling");
+    CNGI_REQUIRE(a->do_psf || a->complex_grid, "standard_grid: image mode needs a complex grid");
+    CNGI_REQUIRE(a->do_psf || a->vis != nullptr, "standard_grid: vis is null in image mode");
+    CNGI_REQUIRE(a->weight && a->uvw && a->freq_chan && a->cgk_1D && a->grid && a->sum_weight,
+                 "standard_grid: null array pointer");
+    CNGI_REQUIRE(a->chan_mode != CNGI_CHAN_GENERAL || a->chan_map != nullptr, "standard_grid: chan_map is null");
+    CNGI_REQUIRE(a->chan_mode >= 0 && a->chan_mode <= 2, "standard_grid: bad chan_mode");
+    if (a->chan_mode == CNGI_CHAN_CUBE)
+        CNGI_REQUIRE(a->n_imag_chan >= a->n_chan, "standard_grid: cube mode needs n_imag_chan >= n_chan");
+    if (!a->pol_map) CNGI_REQUIRE(a->n_imag_pol >= a->n_pol, "standard_grid: identity pol_map needs n_imag_pol >= n_pol");
+    return CNGI_OK;
+}
+
+static StdParams make_params(const cngi_std_grid_args *a)
+{
+    StdParams p{};
+    p.n_time = (int)a->n_time, p.n_baseline = (int)a->n_baseline, p.n_chan = (int)a->n_chan, p.n_pol = (int)a->n_pol;
+    p.n_ic = (int)a->n_imag_chan, p.n_ip = (int)a->n_imag_pol, p.n_u = (int)a->n_u, p.n_v = (int)a->n_v;
+    p.vis = a->vis, p.weight = a->weight, p.flag = a->do_psf ? nullptr : a->flag, p.uvw = a->uvw, p.freq = a->freq_chan;
+    p.chan_map = a->chan_map, p.pol_map = a->pol_map, p.cgk = a->cgk_1D, p.grid = a->grid, p.sum_weight = a->sum_weight;
+    p.dl = a->delta_lm[0], p.dm = a->delta_lm[1];
+    p.support = a->support, p.oversampling = a->oversampling, p.do_psf = a->do_psf, p.chan_mode = a->chan_mode;
+    p.table_len = a->oversampling * (a->support / 2 + 1);
+    if (p.table_len < 1) p.table_len = 1;
+    return p;
+}
+
+template <typename T, bool CPLX> static int launch_naive(StdParams p, cudaStream_t st)
+{
+    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
+    if (total == 0 || p.n_pol == 0) return CNGI_OK;
+    const long long blocks = ceil_div(total, 256);
+    CNGI_REQUIRE(blocks < (1LL << 31), "standard_grid: too many samples for one launch");
+    std_grid_naive_kernel<T, CPLX><<<(unsigned)blocks, 256, 0, st>>>(p);
+    CNGI_CUDA_TRY(cudaGetLastError());
+    return CNGI_OK;
+}
+
+template <typename T, bool CPLX, int S, int PP>
+static int launch_track(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
+{
+    using Cfg = TrackCfg<T, CPLX, S, PP>;
+    if (p.n_time == 0 || p.n_baseline == 0 || p.n_chan == 0 || p.n_pol == 0) return CNGI_OK;
+    // channels walked per item: only worth it when neighbouring channels share an image plane
+    int G = a->chan_group;
+    if (G <= 0) G = (p.chan_mode == CNGI_CHAN_CONTINUUM) ? Cfg::ITER : 1;
+    if (G > Cfg::ITER) G = Cfg::ITER;
+    while (G > 1 && (Cfg::IPW * G / 2) >= p.n_chan) G >>= 1;   // do not span more channels than exist
+    int log2G = 0;
+    while ((1 << (log2G + 1)) <= G) ++log2G;
+    G = 1 << log2G;
+    p.G = G, p.log2G = log2G;
+    const int spr = Cfg::ITER / G;
+    p.n_cspan = (int)ceil_div(p.n_chan, Cfg::IPW * G);
+    p.n_pgrp = (int)ceil_div(p.n_pol, PP);
+    const long long per_seg = (long long)p.n_baseline * p.n_cspan * p.n_pgrp;
+    int seg_len = a->time_segment;
+    if (seg_len <= 0) {
+        // aim for ~16 resident-warp waves so the tail is small, but keep segments long enough that the
+        // final flush (S*S cells per item) is amortised
+        const long long target = (long long)sm_count() * 24 * 16;
+        long long n_seg = ceil_div(target, per_seg);
+        if (n_seg < 1) n_seg = 1;
+        seg_len = (int)ceil_div(p.n_time, n_seg);
+        const int min_len = 64 * spr / Cfg::ITER > 8 ? 64 * spr / Cfg::ITER : 8;
+        if (seg_len < min_len) seg_len = min_len;
+    }
+    seg_len = (int)(ceil_div(seg_len, spr) * spr);
+    p.seg_len = seg_len;
+    p.n_seg = (int)ceil_div(p.n_time, seg_len);
+    p.n_tasks = per_seg * p.n_seg;
+    const int wpb = kTrackBlock / 32;
+    const long long blocks = ceil_div(p.n_tasks, wpb);
+    CNGI_REQUIRE(blocks < (1LL << 31), "standard_grid: too many work items for one launch");
+    const size_t smem = (size_t)((p.table_len * (int)sizeof(T) + 15) / 16 * 16) + (size_t)wpb * Cfg::WARP_BYTES;
+    CNGI_REQUIRE(smem <= 227 * 1024, "standard_grid: CF table too large for shared memory (%zu bytes)", smem);
+    auto kern = std_grid_track_kernel<T, CPLX, S, PP>;
+    CNGI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, kTrackBlock, smem, st>>>(p);
+    CNGI_CUDA_TRY(cudaGetLastError());
+    return CNGI_OK;
+}
+
+template <typename T, bool CPLX, int S> static int launch_track_pp(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
+{
+    if (p.n_pol == 1) return launch_track<T, CPLX, S, 1>(p, a, st);
+    return launch_track<T, CPLX, S, 2>(p, a, st);
+}
+
+template <typename T, bool CPLX> static int dispatch(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
+{
+    int algo = a->algorithm;
+    const bool track_ok = (a->support == 3 || a->support == 5 || a->support == 7 || a->support == 9) &&
+                          a->oversampling >= 1 && p.table_len <= 8192;
+    if (algo == CNGI_ALGO_AUTO) algo = track_ok ? CNGI_ALGO_TRACK : CNGI_ALGO_NAIVE;
+    if (algo == CNGI_ALGO_TRACK) {
+        if (!track_ok) {
+            set_error("standard_grid: track kernel supports support in {3,5,7,9} (got %d)", a->support);
+            return CNGI_ERR_UNSUPPORTED;
+        }
+        switch (a->support) {
+            case 3: return launch_track_pp<T, CPLX, 3>(p, a, st);
+            case 5: return launch_track_pp<T, CPLX, 5>(p, a, st);
+            case 7: return launch_track_pp<T, CPLX, 7>(p, a, st);
+            default: return launch_track_pp<T, CPLX, 9>(p, a, st);
+        }
+    }
+    return launch_naive<T, CPLX>(p, st);
+}
+
+}  // namespace cngi
+
+extern "C" int cngi_b200_standard_grid(const cngi_std_grid_args *a, void *stream)
+{
+    using namespace cngi;
+    int rc = validate(a);
+    if (rc != CNGI_OK) return rc;
+    StdParams p = make_params(a);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->precision == CNGI_F32)
+        return a->complex_grid ? dispatch<float, true>(p, a, st) : dispatch<float, false>(p, a, st);
+    return a->complex_grid ? dispatch<double, true>(p, a, st) : dispatch<double, false>(p, a, st);
+}

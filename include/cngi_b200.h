@@ -1,0 +1,246 @@
+/*
+ * cngi_b200.h -- C ABI of libcngi_b200.so: B200 (sm_100a) convolutional gridding for ngcasa.
+ *
+ * Drop-in boundary for ONE hot path of casangi/cngi_prototype: the per-chunk gridding operators
+ * that the reference's dask graphs call (paths relative to the reference tree):
+ *
+ *   ngcasa/imaging/_imaging_utils/_standard_grid.py:123   _standard_grid_numpy_wrap        -> cngi_b200_standard_grid
+ *   ngcasa/imaging/_imaging_utils/_standard_grid.py:180   _standard_grid_psf_numpy_wrap    -> cngi_b200_standard_grid (do_psf)
+ *                                                         (do_imaging_weight, support 1)   -> cngi_b200_imaging_weight_grid
+ *   ngcasa/imaging/make_imaging_weight.py:198             calculate_briggs_parms           -> cngi_b200_briggs_factors
+ *   ngcasa/imaging/_imaging_utils/_standard_grid.py:443   _standard_imaging_weight_degrid_numpy_wrap
+ *                                                                                          -> cngi_b200_imaging_weight_degrid
+ *   ngcasa/imaging/_imaging_utils/_aperture_grid.py:294   _aperture_grid_numpy_wrap        -> cngi_b200_aperture_grid
+ *   ngcasa/imaging/_imaging_utils/_aperture_grid.py:333   _aperture_psf_grid_numpy_wrap    -> cngi_b200_aperture_grid (do_psf)
+ *   ngcasa/imaging/_imaging_utils/_aperture_grid.py:146   _aperture_weight_grid_numpy_wrap -> cngi_b200_aperture_weight_grid
+ *   ngcasa/imaging/predict_modelvis_image.py:20 (stub)    degrid predict                   -> cngi_b200_standard_degrid
+ *   ngcasa/imaging/make_image.py:116-130                  ifft2 + crop + correct_image     -> cngi_b200_grid_to_image
+ *   ngcasa/imaging/_imaging_utils/_normalize.py:39-89     normalize_image                  -> cngi_b200_grid_to_image (pb/sinc)
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name ends in _host.  Arrays are C-order and
+ *     contiguous.  Complex values are interleaved (re, im).
+ *   - Sample arrays are (n_time, n_baseline, n_chan, n_pol); uvw is (n_time, n_baseline, 3) float64
+ *     metres; grids are kernel-side (n_imag_chan, n_imag_pol, n_u, n_v), v fastest -- the layout the
+ *     reference's jit functions use before the moveaxis at _standard_grid.py:101-104.
+ *   - Gridding entry points ACCUMULATE into caller-owned grid / sum_weight buffers (the reference's
+ *     wrappers allocate zeroed outputs; zero them yourself or with cudaMemsetAsync).
+ *   - precision: CNGI_F32 = vis complex64, weight float32, grid complex64/float32;
+ *                CNGI_F64 = vis complex128, weight float64, grid complex128/float64.
+ *     Cell indices, oversampling offsets and masks are always computed in IEEE fp64 with the
+ *     reference's operation order (no FMA contraction), so they are bit-exact in both precisions.
+ *     sum_weight is always float64.
+ *   - All functions are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream), re-entrant, and return 0 on success.  They never throw.  On failure the message is
+ *     available from cngi_b200_last_error() (thread-local).
+ *   - Bad samples are silently skipped exactly as the reference does (NaN u/v, stamp leaving the grid,
+ *     NaN or zero weighted data, field < 0); that is not an error.
+ */
+#ifndef CNGI_B200_H
+#define CNGI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNGI_B200_ABI_VERSION 1
+
+enum { CNGI_OK = 0, CNGI_ERR_INVALID = 1, CNGI_ERR_CUDA = 2, CNGI_ERR_UNSUPPORTED = 3, CNGI_ERR_NO_DEVICE = 4 };
+enum { CNGI_F32 = 0, CNGI_F64 = 1 };
+/* chan_map shortcut: CUBE = identity map (a_chan = i_chan), CONTINUUM = all zero
+   (_standard_grid.py:151-156); GENERAL reads the chan_map array. */
+enum { CNGI_CHAN_GENERAL = 0, CNGI_CHAN_CUBE = 1, CNGI_CHAN_CONTINUUM = 2 };
+/* kernel selection for the standard gridder */
+enum { CNGI_ALGO_AUTO = 0, CNGI_ALGO_NAIVE = 1, CNGI_ALGO_TRACK = 2 };
+
+int cngi_b200_abi_version(void);
+const char *cngi_b200_last_error(void);
+/* 0 if a compute-capability 10.x device is current/available; CNGI_ERR_NO_DEVICE otherwise. */
+int cngi_b200_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * A1/A2  standard (prolate-spheroidal, separable taps) gridder.   _standard_grid.py:242-371
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cngi_std_grid_args {
+    int64_t n_time, n_baseline, n_chan, n_pol;      /* sample array shape                           */
+    int64_t n_imag_chan, n_imag_pol, n_u, n_v;      /* grid shape                                   */
+    const void *vis;            /* complex [n_time,n_baseline,n_chan,n_pol]; ignored when do_psf      */
+    const void *weight;         /* real, same shape                                                  */
+    const uint8_t *flag;        /* optional (may be NULL), same shape; non-zero => vis treated as NaN */
+    const double *uvw;          /* [n_time,n_baseline,3]                                             */
+    const double *freq_chan;    /* [n_chan] Hz                                                       */
+    const int64_t *chan_map;    /* [n_chan]; may be NULL unless chan_mode == CNGI_CHAN_GENERAL       */
+    const int64_t *pol_map;     /* [n_pol];  NULL = identity                                         */
+    const double *cgk_1D;       /* [oversampling*(support/2+1)] half tap table (always float64)      */
+    void *grid;                 /* complex or real [n_imag_chan,n_imag_pol,n_u,n_v], accumulated      */
+    double *sum_weight;         /* [n_imag_chan,n_imag_pol], accumulated                             */
+    double delta_lm[2];         /* cell size in radians, x already negated (_check_imaging_parms:39)  */
+    int32_t support, oversampling;
+    int32_t precision;          /* CNGI_F32 / CNGI_F64                                               */
+    int32_t do_psf;             /* grid weights only (real data)                                     */
+    int32_t complex_grid;       /* grid cell type; image mode requires 1                             */
+    int32_t chan_mode;          /* CNGI_CHAN_*                                                       */
+    int32_t algorithm;          /* CNGI_ALGO_*                                                       */
+    int32_t chan_group;         /* track kernel: channels walked per work item (0 = auto)            */
+    int32_t time_segment;       /* track kernel: time steps per work item (0 = auto)                 */
+    int32_t reserved;
+} cngi_std_grid_args;
+
+int cngi_b200_standard_grid(const cngi_std_grid_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A2  imaging-weight density grid: support 1, nearest cell + conjugate cell, pol-averaged weight when
+ *     n_pol >= 2, sum_weight doubled.   _standard_grid.py:306-318,328-330,362-369 as called from
+ *     make_imaging_weight.py:153-161.  density / sum_weight are float64 in both precisions; the
+ *     conjugate cell IS bounds checked here (the reference does not).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cngi_iw_grid_args {
+    int64_t n_time, n_baseline, n_chan, n_pol;
+    int64_t n_imag_chan, n_imag_pol, n_u, n_v;
+    const void *weight;         /* real [n_time,n_baseline,n_chan,n_pol] (precision selects f32/f64)  */
+    const double *uvw;
+    const double *freq_chan;
+    const int64_t *chan_map;
+    const int64_t *pol_map;
+    double *density;            /* float64 [n_imag_chan,n_imag_pol,n_u,n_v], accumulated              */
+    double *sum_weight;         /* float64 [n_imag_chan,n_imag_pol], accumulated                      */
+    double delta_lm[2];
+    int32_t precision;
+    int32_t chan_mode;
+} cngi_iw_grid_args;
+
+int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *args, void *stream);
+
+/* A3  briggs_factors[0] = (5*10^-robust)^2 / (sum(density^2)/sum_weight), [1] = 1  (weighting 0 = briggs)
+ *     or [0] = 1, [1] = 0 (weighting 1 = uniform).   make_imaging_weight.py:198-213
+ *     density [n_planes, n_u*n_v] float64, sum_weight [n_planes], briggs_factors [2, n_planes] float64. */
+int cngi_b200_briggs_factors(const double *density, const double *sum_weight, double *briggs_factors,
+                             int64_t n_planes, int64_t n_cells, double robust, int32_t weighting, void *stream);
+
+/* A4  imaging_weight = (pol-averaged) natural weight / (f0*density[cell] + f1).  _standard_grid.py:466-518
+ *     density is addressed through element strides so that both the kernel-side (chan,pol,u,v) and the
+ *     API-side (u,v,chan,pol) layouts work without a transpose. */
+typedef struct cngi_iw_degrid_args {
+    int64_t n_time, n_baseline, n_chan, n_pol;
+    int64_t n_imag_chan, n_imag_pol, n_u, n_v;
+    const void *natural_weight; /* real [n_time,n_baseline,n_chan,n_pol]                              */
+    const double *uvw;
+    const double *freq_chan;
+    const int64_t *chan_map;
+    const int64_t *pol_map;
+    const double *density;      /* float64                                                           */
+    int64_t density_stride[4];  /* element strides for (u, v, chan, pol)                              */
+    const double *briggs_factors; /* [2, n_imag_chan, n_imag_pol]                                     */
+    void *imaging_weight;       /* real out [n_time,n_baseline,n_chan,n_pol], fully overwritten       */
+    double delta_lm[2];
+    int32_t precision;
+    int32_t chan_mode;
+} cngi_iw_degrid_args;
+
+int cngi_b200_imaging_weight_degrid(const cngi_iw_degrid_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A5/A6  aperture (A-projection / mosaic) gridders.   _aperture_grid.py:376-513 and :180-291
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cngi_aperture_grid_args {
+    int64_t n_time, n_baseline, n_chan, n_pol;
+    int64_t n_imag_chan, n_imag_pol, n_u, n_v;
+    const void *vis;                 /* complex; ignored when do_psf or grid_weights                 */
+    const void *weight;              /* imaging weight, real                                        */
+    const uint8_t *flag;             /* optional                                                    */
+    const double *uvw;
+    const double *freq_chan;
+    const int64_t *chan_map, *pol_map;
+    const int64_t *field;            /* [n_time,n_baseline] FIELD_ID column; <= -1 => row skipped     */
+    const int64_t *field_id;         /* [n_field] ids in phase_gradient order                        */
+    const int64_t *cf_baseline_map;  /* [n_baseline] */
+    const int64_t *cf_chan_map;      /* [n_chan]     */
+    const int64_t *cf_pol_map;       /* [n_pol]      */
+    const double *conv_kernel;       /* float64 [n_cfb,n_cfc,n_cfp,n_cu,n_cv] (CONV_KERNEL or WEIGHT_CONV_KERNEL) */
+    const int64_t *weight_support;   /* [n_cfb,n_cfc,n_cfp,2]                                        */
+    const double *phase_gradient;    /* complex128 [n_field,n_cu,n_cv]                               */
+    void *grid;                      /* complex [n_imag_chan,n_imag_pol,n_u,n_v], accumulated         */
+    double *sum_weight;
+    double delta_lm[2];
+    int64_t n_field, n_cfb, n_cfc, n_cfp, n_cu, n_cv;
+    int32_t oversampling[2];
+    int32_t max_support;             /* max over weight_support (host knows it; bounds test :397,447) */
+    int32_t precision;
+    int32_t do_psf;
+    int32_t chan_mode;
+} cngi_aperture_grid_args;
+
+int cngi_b200_aperture_grid(const cngi_aperture_grid_args *args, void *stream);
+/* A6: stamps at the grid centre with unshifted CF indices; `vis`, `flag`, `do_psf` ignored. */
+int cngi_b200_aperture_weight_grid(const cngi_aperture_grid_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A7  degridding predict = adjoint of A1 (no reference implementation; predict_modelvis_image.py:20-40
+ *     is a stub).  vis[t,b,c,p] = sum_taps cgk*cgk*model_grid[chan_map[c], pol_map[p], ...]; samples the
+ *     gridder would skip get 0.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cngi_std_degrid_args {
+    int64_t n_time, n_baseline, n_chan, n_pol;
+    int64_t n_imag_chan, n_imag_pol, n_u, n_v;
+    const void *model_grid;     /* complex [n_imag_chan,n_imag_pol,n_u,n_v]                           */
+    const double *uvw;
+    const double *freq_chan;
+    const int64_t *chan_map, *pol_map;
+    const double *cgk_1D;
+    void *vis;                  /* complex out [n_time,n_baseline,n_chan,n_pol], fully overwritten    */
+    double delta_lm[2];
+    int32_t support, oversampling;
+    int32_t precision;
+    int32_t chan_mode;
+} cngi_std_degrid_args;
+
+int cngi_b200_standard_degrid(const cngi_std_degrid_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A9/A10  grid -> image: fftshift(ifft2(ifftshift(G))) (cuFFT, unnormalised inverse == numpy ifft2 * N),
+ *         centre crop, real part, / sum_weight (0 -> 1), / correcting image [* sinc * pb], pb_limit mask.
+ *         make_image.py:116-130, _remove_padding.py:20-31, _normalize.py:39-89
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cngi_fft_plan cngi_fft_plan; /* opaque: cuFFT plan + work buffer for n_planes of n_u x n_v */
+
+int cngi_b200_fft_plan_create(cngi_fft_plan **plan, int64_t n_u, int64_t n_v, int64_t max_planes,
+                              int32_t precision);
+int cngi_b200_fft_plan_destroy(cngi_fft_plan *plan);
+
+typedef struct cngi_grid_to_image_args {
+    int64_t n_planes;           /* n_imag_chan * n_imag_pol                                          */
+    int64_t n_u, n_v;           /* padded grid size                                                  */
+    int64_t image_size[2];      /* cropped image size (l, m)                                         */
+    const void *grid;           /* complex or real [n_planes,n_u,n_v]; not modified                   */
+    int32_t grid_is_complex;
+    int32_t precision;
+    const double *sum_weight;   /* [n_planes] or NULL (no division)                                  */
+    const double *corr_u;       /* [image_size[0]] separable correcting function along l, or NULL     */
+    const double *corr_v;       /* [image_size[1]] along m; image is divided by corr_u[i]*corr_v[j]   */
+    const void *norm_image;     /* optional real [n_planes or 1, l, m] extra divisor (PB / WEIGHT_PB)  */
+    int64_t norm_image_planes;  /* 1 = broadcast over planes                                         */
+    const void *pb_image;       /* optional real [n_planes or 1, l, m]: pixels with pb < pb_limit -> 0 */
+    int64_t pb_image_planes;
+    double pb_limit;
+    int32_t divide_by_centre;   /* make_psf_with_gcf.py:140: divide plane by its centre pixel          */
+    int32_t single_precision_roundtrip; /* _normalize.py:86-87                                        */
+    void *image;                /* real out [n_planes, l, m] (kernel-side plane order)                */
+} cngi_grid_to_image_args;
+
+int cngi_b200_grid_to_image(cngi_fft_plan *plan, const cngi_grid_to_image_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer entry point: what a ctypes / cgo-style binding calls with numpy-like HOST arrays.
+ * Streams the sample arrays through pinned staging buffers in time chunks (H2D overlapped with the
+ * gridding kernels on a second stream), accumulates on the device, and copies grid + sum_weight back.
+ * All pointers in `args` are HOST pointers here; grid/sum_weight are overwritten (allocate-and-return
+ * semantics of _standard_grid_numpy_wrap).  Synchronous.
+ * ---------------------------------------------------------------------------------------------- */
+int cngi_b200_standard_grid_host(const cngi_std_grid_args *args_host, int64_t time_chunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNGI_B200_H */

@@ -1,0 +1,108 @@
+"""CPU-only checks of the drop-in boundary: the shared library builds for sm_100a, loads, and exports every
+symbol include/cngi_b200.h declares; ctypes structs match the header's field lists; without a GPU the
+product path fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+HEADER = os.path.join(ROOT, "include", "cngi_b200.h")
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from cngi_prototype_b200 import build
+    return build.build()
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cngi_b200_\w+)\s*\(", src)))
+
+
+def _struct_fields(name):
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, flags=re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            ident = re.findall(r"(\w+)\s*(?:\[\d+\])?\s*$", part.strip())[0]
+            fields.append(ident)
+    return fields
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    lib = ctypes.CDLL(libpath)
+    names = _declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), "libcngi_b200.so does not export %s" % n
+    from cngi_prototype_b200 import _lib
+    assert sorted(_lib.EXPORTS) == names
+    assert lib.cngi_b200_abi_version() == 1
+
+
+@pytest.mark.parametrize("cname,pyname", [("cngi_std_grid_args", "StdGridArgs"), ("cngi_iw_grid_args", "IwGridArgs"),
+                                          ("cngi_iw_degrid_args", "IwDegridArgs"),
+                                          ("cngi_aperture_grid_args", "ApertureGridArgs"),
+                                          ("cngi_std_degrid_args", "StdDegridArgs"),
+                                          ("cngi_grid_to_image_args", "GridToImageArgs")])
+def test_ctypes_structs_match_header(cname, pyname):
+    from cngi_prototype_b200 import _lib
+    py = [f[0] for f in getattr(_lib, pyname)._fields_]
+    assert py == _struct_fields(cname)
+
+
+def test_sass_has_native_reductions_and_no_shared_fp_atomics(libpath):
+    """The design rests on REDG (native global fp reductions) and avoids shared-memory fp atomics (CAS loops)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", libpath], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in sass
+    assert "RED.E.ADD.F32x2" in sass or "REDG.E.ADD.F32x2" in sass
+    assert "ATOMS.CAST" not in sass
+
+
+def test_no_cpu_fallback_without_gpu(libpath):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cngi_prototype_b200 import _lib, _standard_grid, synth
+    from cngi_prototype_b200._gridding_convolutional_kernels import _create_prolate_spheroidal_kernel_1D
+    d = synth.make_vis_set(4, 4, 2, 2, 1e9, 1.1e9, 300.0, 60.0, seed=0)
+    gp = synth.grid_parms_for(32, d["cell"])
+    with pytest.raises(_lib.CngiError):
+        _standard_grid._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"],
+                                                 _create_prolate_spheroidal_kernel_1D(100, 7), gp)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cngi_prototype_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_ps_tables_match_reference_golden():
+    from cngi_prototype_b200 import _gridding_convolutional_kernels as k
+    d = np.load(os.path.join(ROOT, "tests", "golden", "ps_tables.npz"))
+    assert np.array_equal(k._create_prolate_spheroidal_kernel_1D(100, 7), d["cgk_1D_os100_s7"])
+    assert np.array_equal(k._create_prolate_spheroidal_kernel_1D(50, 5), d["cgk_1D_os50_s5"])
+    assert np.array_equal(k._create_prolate_spheroidal_image_2D([12, 12]), d["corr_image_12x12"])
+    assert np.array_equal(k._create_prolate_spheroidal_image_2D([15, 13]), d["corr_image_15x13"])
+    cu, cv = k.correcting_function_1D([15, 13], [9, 8])
+    full = d["corr_image_15x13"]
+    assert np.array_equal(np.outer(cu, cv), full[15 // 2 - 9 // 2:15 // 2 - 9 // 2 + 9, 13 // 2 - 4:13 // 2 - 4 + 8])
