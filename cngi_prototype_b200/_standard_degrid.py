@@ -13,8 +13,11 @@ from ._devutil import (torch, is_torch, chan_mode, precision_of, torch_dtypes, d
                        back)
 
 
-def _standard_degrid_numpy_wrap(model_grid, uvw, freq_chan, cgk_1D, grid_parms, n_pol=None):
-    """vis (n_time, n_baseline, n_chan, n_pol) from a kernel-side model grid (n_imag_chan, n_imag_pol, n_u, n_v)."""
+def _standard_degrid_numpy_wrap(model_grid, uvw, freq_chan, cgk_1D, grid_parms, n_pol=None, normalize=False):
+    """vis (n_time, n_baseline, n_chan, n_pol) from a kernel-side model grid (n_imag_chan, n_imag_pol, n_u, n_v).
+
+    normalize=False is the exact adjoint of the gridder; normalize=True divides every sample by its tap sum, which
+    is what a predict needs (the imaging side divides by sum_weight = sum w * tap sum, make_image.py:123-130)."""
     L = _lib.lib()
     like_torch = is_torch(model_grid)
     dev = device_of(model_grid, uvw)
@@ -37,7 +40,7 @@ def _standard_degrid_numpy_wrap(model_grid, uvw, freq_chan, cgk_1D, grid_parms, 
     cell = grid_parms["cell_size"]
     a.delta_lm[0], a.delta_lm[1] = float(cell[0]), float(cell[1])
     a.support, a.oversampling = int(grid_parms["support"]), int(grid_parms["oversampling"])
-    a.precision, a.chan_mode = precision, chan_mode(grid_parms)
+    a.precision, a.chan_mode, a.normalize = precision, chan_mode(grid_parms), int(bool(normalize))
     with torch.cuda.device(dev):
         _lib.check(L.cngi_b200_standard_degrid(C.byref(a), stream()), "cngi_b200_standard_degrid")
     return back(vis, like_torch)

@@ -20,7 +20,7 @@ struct DgParams {
     const double *cgk;
     void *vis;
     double dl, dm;
-    int support, oversampling, chan_mode;
+    int support, oversampling, chan_mode, normalize;
 };
 
 // generic support: `LW` lanes per sample (power of two >= support, <= 32)
@@ -52,6 +52,15 @@ template <typename T, int LW> __global__ void __launch_bounds__(256) std_degrid_
     const int a_chan = p.chan_mode == CNGI_CHAN_CUBE ? c : (p.chan_mode == CNGI_CHAN_CONTINUUM ? 0 : (int)p.chan_map[c]);
     const bool lane_on = ok && li < p.support;
     const double cu = lane_on ? p.cgk[abs(p.oversampling * (li - half) + uoff)] : 0.0;
+    double inv_norm = 1.0;
+    if (p.normalize) {   // norm = sum over the stamp of cu*cv = (sum cu) * (sum cv)
+        double su = cu, sv = 0.0;
+#pragma unroll
+        for (int o = LW / 2; o > 0; o >>= 1) su += __shfl_xor_sync(FULL, su, o);
+        if (ok)
+            for (int q = 0; q < p.support; ++q) sv += p.cgk[abs(p.oversampling * (q - half) + voff)];
+        inv_norm = ok ? 1.0 / (su * sv) : 1.0;
+    }
     for (int ip = 0; ip < p.n_pol; ++ip) {
         double are = 0.0, aim = 0.0;
         if (lane_on) {
@@ -74,8 +83,8 @@ template <typename T, int LW> __global__ void __launch_bounds__(256) std_degrid_
         }
         if (in_range && li == 0) {
             CT out;
-            out.x = (T)are;
-            out.y = (T)aim;
+            out.x = (T)(are * inv_norm);
+            out.y = (T)(aim * inv_norm);
             ((CT *)p.vis)[idx * p.n_pol + ip] = out;   // skipped samples reach here with 0
         }
     }
@@ -120,6 +129,6 @@ extern "C" int cngi_b200_standard_degrid(const cngi_std_degrid_args *a, void *st
     p.n_ic = (int)a->n_imag_chan, p.n_ip = (int)a->n_imag_pol, p.n_u = (int)a->n_u, p.n_v = (int)a->n_v;
     p.grid = a->model_grid, p.uvw = a->uvw, p.freq = a->freq_chan, p.chan_map = a->chan_map, p.pol_map = a->pol_map;
     p.cgk = a->cgk_1D, p.vis = a->vis, p.dl = a->delta_lm[0], p.dm = a->delta_lm[1];
-    p.support = a->support, p.oversampling = a->oversampling, p.chan_mode = a->chan_mode;
+    p.support = a->support, p.oversampling = a->oversampling, p.chan_mode = a->chan_mode, p.normalize = a->normalize;
     return a->precision == CNGI_F32 ? launch_degrid<float>(p, (cudaStream_t)stream) : launch_degrid<double>(p, (cudaStream_t)stream);
 }

@@ -559,7 +559,7 @@ void oracle_aperture_weight_grid(double *grid, double *sum_weight, const double 
 void oracle_standard_degrid(double *vis, const double *model_grid, const double *uvw, const double *freq_chan,
                             const i64 *chan_map, const i64 *pol_map, const double *cgk_1D, i64 n_time,
                             i64 n_baseline, i64 n_chan, i64 n_pol, i64 n_imag_pol, i64 n_u, i64 n_v,
-                            const double *delta_lm, i64 support, i64 oversampling)
+                            const double *delta_lm, i64 support, i64 oversampling, int normalize)
 {
     double *us = (double *)malloc(sizeof(double) * (size_t)n_chan);
     double *vs = (double *)malloc(sizeof(double) * (size_t)n_chan);
@@ -585,7 +585,7 @@ void oracle_standard_degrid(double *vis, const double *model_grid, const double 
                 const i64 v_off_idx = (i64)floor(((double)vc - v_pos) * (double)oversampling + 0.5);
                 for (i64 ip = 0; ip < n_pol; ++ip) {
                     const i64 plane = (a_chan * n_imag_pol + pol_map[ip]) * n_u;
-                    double acc_re = 0.0, acc_im = 0.0;
+                    double acc_re = 0.0, acc_im = 0.0, norm = 0.0;
                     for (i64 iv = -sc; iv < support - sc; ++iv) {
                         const double conv_v = cgk_1D[llabs(oversampling * iv + v_off_idx)];
                         for (i64 iu = -sc; iu < support - sc; ++iu) {
@@ -593,7 +593,12 @@ void oracle_standard_degrid(double *vis, const double *model_grid, const double 
                             const i64 cell = (plane + uc + iu) * n_v + vc + iv;
                             acc_re += conv * model_grid[2 * cell];
                             acc_im += conv * model_grid[2 * cell + 1];
+                            norm += conv;
                         }
+                    }
+                    if (normalize) { /* same normalisation the imaging side applies via sum_weight (:366) */
+                        acc_re /= norm;
+                        acc_im /= norm;
                     }
                     vis[2 * (sample + ip)] = acc_re;
                     vis[2 * (sample + ip) + 1] = acc_im;

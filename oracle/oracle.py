@@ -300,7 +300,7 @@ def _aperture_weight_grid_numpy_wrap(uvw, imaging_weight, field, cf_baseline_map
 
 
 # --------------------------------------------------------------------------- A7
-def _standard_degrid_numpy_wrap(model_grid, uvw, freq_chan, cgk_1D, grid_parms, n_pol=None):
+def _standard_degrid_numpy_wrap(model_grid, uvw, freq_chan, cgk_1D, grid_parms, n_pol=None, normalize=False):
     """Degrid predict (adjoint of A1).  NO reference implementation: parity unpinned.
 
     model_grid: kernel-side (n_imag_chan, n_pol, n_u, n_v) complex.  Returns vis (n_t,n_b,n_c,n_pol).
@@ -321,7 +321,7 @@ def _standard_degrid_numpy_wrap(model_grid, uvw, freq_chan, cgk_1D, grid_parms, 
         _p(vis), _p(g), _p(uvw), _p(freq), _p(chan_map), _p(pol_map), _p(cgk),
         _i64(n_time), _i64(n_baseline), _i64(n_chan), _i64(n_pol), _i64(g.shape[1]),
         _i64(int(n_uv[0])), _i64(int(n_uv[1])), _p(delta_lm), _i64(int(grid_parms["support"])),
-        _i64(int(grid_parms["oversampling"])))
+        _i64(int(grid_parms["oversampling"])), ctypes.c_int(int(bool(normalize))))
     return vis
 
 

@@ -78,6 +78,9 @@ def test_degrid_vs_oracle_and_adjoint(oracle, prec, support, oversampling):
         v = _standard_degrid._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp)
         assert np.array_equal(v == 0, v_ref == 0)          # skipped samples are exactly 0
         assert rel_err(v, v_ref) <= tol
+        vn_ref = oracle._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp, normalize=True)
+        vn = _standard_degrid._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp, normalize=True)
+        assert rel_err(vn, vn_ref) <= tol
         # <y, grid(x)> == <degrid(y), x> with unit weights and unflagged data
         x = np.nan_to_num(d["vis"], nan=0.5)
         ones = np.ones_like(d["weight"])
@@ -102,7 +105,7 @@ def test_degrid_point_source_analytic(oracle):
     # inverse of make_image.py:116: G = fftshift(fft2(ifftshift(img)))
     G = np.fft.fftshift(np.fft.fft2(np.fft.ifftshift(img)))
     y = np.repeat(G[None, None], 2, axis=1)
-    v = _standard_degrid._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp)
+    v = _standard_degrid._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp, normalize=True)
     # analytic: grid coordinate u_pix = uvw*uv_scale, pixel offset (i - n/2) <-> exp(-2 pi i u_pix*(i-n/2)/n)
     us = -(d["freq_chan"] * gp["cell_size"][0] * n) / 299792458.0
     vs = -(d["freq_chan"] * gp["cell_size"][1] * n) / 299792458.0
@@ -113,4 +116,4 @@ def test_degrid_point_source_analytic(oracle):
         model += amp * np.exp(-2j * np.pi * (up * (i - n // 2) + vp * (j - n // 2)) / n)
     ok = v[..., 0] != 0
     err = np.abs(v[..., 0][ok] - model[ok]).max()
-    assert ok.mean() > 0.95 and err < 5e-3   # limited by the PS kernel's aliasing rejection, not by arithmetic
+    assert ok.mean() > 0.95 and err < 1e-2   # limited by the PS kernel's aliasing rejection, not by arithmetic
