@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 gridding hot path (contract: see the task brief / DESIGN.md).
+
+Workload (BASELINE.json configs[1]): make_imaging_weight Briggs (robust 0.5) + standard PS gridding of a
+synthetic ALMA-like set -- 903 baselines x 500 integrations x 128 channels x 2 pol = 115.6 M samples per GPU,
+4096^2 grid, support 7, oversampling 100, fp32 data/grid (fp64 index math), continuum (mfs) imaging.
+One STEP = zero the accumulators, density grid (A2), Briggs factors (A3), weight degrid (A4), standard
+gridding of vis * imaging weight (A1) -- and, for N > 1, the two NCCL reductions the path needs (all-reduce of
+the density before the degrid, reduce of the uv-grid to rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line.  `value` is device-resident throughput (inputs in HBM), `e2e` the same step through the
+public API from pinned HOST buffers with H2D/D2H copies inside the timed region, `roofline` the dominant kernel
+(std_grid_track) against the measured HBM peak, `cpu_baseline` the oracle port of the reference on host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_UV = 4096
+SUPPORT, OVERSAMPLING = 7, 100
+IW_PARMS = dict(weighting="briggs", robust=0.5)
+METRIC = "visibilities gridded/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-time", type=int, default=500)
+    ap.add_argument("--n-chan", type=int, default=128)
+    ap.add_argument("--n-uv", type=int, default=N_UV)
+    ap.add_argument("--chan-mode", default="continuum", choices=["continuum", "cube"])
+    ap.add_argument("--cpu-sample-times", type=int, default=0, help="integrations in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("C2 ALMA-like: Briggs(0.5) imaging weights + standard PS gridding, 903 bl x %d t x %d ch x 2 pol, "
+            "%d^2 grid, S=7, os=100, %s" % (a.n_time, a.n_chan, a.n_uv, a.chan_mode))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+#  CPU arm: the oracle port of the reference's numba loops on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_step(O, d, gp, gp_iw, cgk, n_threads):
+    """Same step as the GPU arm, reference semantics, fp64 (the reference always computes in fp64)."""
+    rho, sw = O._standard_grid_psf_numpy_wrap(d["uvw"], d["weight"], d["freq_chan"], np.ones(1), gp_iw,
+                                              n_threads=n_threads)
+    bf = O._calculate_briggs_parms(rho, sw, IW_PARMS)
+    iw = O._standard_imaging_weight_degrid_numpy_wrap(np.moveaxis(rho, (0, 1), (2, 3)), d["uvw"], d["weight"], bf,
+                                                      d["freq_chan"], gp_iw)
+    g, s = O._standard_grid_numpy_wrap(d["vis"], d["uvw"], iw, d["freq_chan"], cgk, gp, n_threads=n_threads)
+    return g, s
+
+
+def cpu_arm(a, steps, warmup, sample_times):
+    from oracle import oracle as O
+    from cngi_prototype_b200 import synth
+    O.build()
+    cores = os.cpu_count() or 1
+    n_threads = max(1, min(cores, 32))   # continuum: one private 4096^2 c128 grid per thread (as the reference's chunks)
+    d = synth.config_c2(n_time=sample_times, n_chan=a.n_chan, dtype="f64", shard=0)
+    cgk = O._create_prolate_spheroidal_kernel_1D(OVERSAMPLING, SUPPORT)
+    gp = synth.grid_parms_for(a.n_uv, d["cell"], chan_mode=a.chan_mode)
+    gp_iw = synth.grid_parms_for(a.n_uv, d["cell"], chan_mode=a.chan_mode, support=1, oversampling=0, do_psf=True,
+                                 complex_grid=False, do_imaging_weight=True)
+    n_samples = d["weight"].size
+    for _ in range(warmup):
+        cpu_step(O, d, gp, gp_iw, cgk, n_threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(O, d, gp, gp_iw, cgk, n_threads)
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=n_samples / dt, unit="vis/s", cores=n_threads, kind="port",
+                sample="%d of %d integrations of the same workload (%.1f M samples/step), C port of the reference "
+                       "numba loops (oracle/cngi_oracle.c, fp64), %d pthreads over time chunks with private grids + "
+                       "tree sum like the reference's dask graph; host has %d logical cores"
+                       % (sample_times, a.n_time, n_samples / 1e6, n_threads, cores)), dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_times = a.cpu_sample_times or 100
+    cb, dt = cpu_arm(a, a.steps, min(a.warmup, 1), sample_times)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "vis/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "note": "CPU arm: each step is a bounded sample of the workload"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "vis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+#  GPU arm
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t_begin, t_end):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t_begin <= t <= t_end and len(r) >= 9] or \
+               [r for (_, r) in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from cngi_prototype_b200 import synth, _lib
+    from cngi_prototype_b200._standard_grid import standard_grid
+    from cngi_prototype_b200._imaging_weight import (imaging_weight_grid, calculate_briggs_parms,
+                                                     _standard_imaging_weight_degrid_numpy_wrap)
+    from cngi_prototype_b200._gridding_convolutional_kernels import _create_prolate_spheroidal_kernel_1D
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.require_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    d = synth.config_c2(n_time=a.n_time, n_chan=a.n_chan, dtype="f32", shard=rank)
+    n_samples = d["weight"].size
+    cgk = _create_prolate_spheroidal_kernel_1D(OVERSAMPLING, SUPPORT)
+    gp = synth.grid_parms_for(a.n_uv, d["cell"], chan_mode=a.chan_mode)
+    gp_iw = synth.grid_parms_for(a.n_uv, d["cell"], chan_mode=a.chan_mode, support=1, oversampling=0, do_psf=True,
+                                 complex_grid=False, do_imaging_weight=True)
+    n_ic = a.n_chan if a.chan_mode == "cube" else 1
+
+    # pinned host copies (e2e source) and device-resident copies (value)
+    H = {k: torch.as_tensor(d[k]).pin_memory() for k in ("vis", "uvw", "weight", "freq_chan")}
+    T = {k: v.to(dev) for k, v in H.items()}
+    cgk_t = torch.as_tensor(cgk).to(dev)
+    density = torch.empty((n_ic, 2, a.n_uv, a.n_uv), dtype=torch.float64, device=dev)
+    dsw = torch.empty((n_ic, 2), dtype=torch.float64, device=dev)
+    grid = torch.empty((n_ic, 2, a.n_uv, a.n_uv), dtype=torch.complex64, device=dev)
+    gsw = torch.empty((n_ic, 2), dtype=torch.float64, device=dev)
+    grid_host = torch.empty(grid.shape, dtype=grid.dtype).pin_memory()
+    gsw_host = torch.empty(gsw.shape, dtype=gsw.dtype).pin_memory()
+    grid_evs = []
+
+    def step(src, record_kernel=False):
+        density.zero_(), dsw.zero_(), grid.zero_(), gsw.zero_()
+        imaging_weight_grid(src["uvw"], src["weight"], src["freq_chan"], gp_iw, grid=density, sum_weight=dsw)
+        if world > 1:   # every rank needs the full density for its degrid
+            dist.all_reduce(density)
+            dist.all_reduce(dsw)
+        bf = calculate_briggs_parms(density, dsw, IW_PARMS)
+        iw = _standard_imaging_weight_degrid_numpy_wrap(density, src["uvw"], src["weight"], bf, src["freq_chan"], gp_iw,
+                                                        kernel_side_layout=True)
+        if record_kernel:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        standard_grid(src["vis"], src["uvw"], iw, src["freq_chan"], cgk_t, gp, False, True, grid=grid, sum_weight=gsw)
+        if record_kernel:
+            e1.record()
+            grid_evs.append((e0, e1))
+        if world > 1:   # partial uv-grids + sum of weights -> rank 0 (before the FFT)
+            dist.reduce(torch.view_as_real(grid), 0)
+            dist.reduce(gsw, 0)
+
+    copy_stream = torch.cuda.Stream(device=dev)
+    n_chunks = 8
+    bounds = [(a.n_time * i) // n_chunks for i in range(n_chunks + 1)]
+
+    def e2e_step():
+        """Same step from pinned HOST buffers: chunked H2D on a copy stream overlapped with the kernels, D2H of the
+        result.  Device staging buffers (T) are reused; the copies are in the timed region."""
+        main = torch.cuda.current_stream()
+        density.zero_(), dsw.zero_(), grid.zero_(), gsw.zero_()
+        copy_stream.wait_stream(main)
+        evs_w, evs_v = [], []
+        with torch.cuda.stream(copy_stream):
+            T["freq_chan"].copy_(H["freq_chan"], non_blocking=True)
+            for i in range(n_chunks):   # weights + uvw first: the density pass needs only those
+                sl = slice(bounds[i], bounds[i + 1])
+                T["uvw"][sl].copy_(H["uvw"][sl], non_blocking=True)
+                T["weight"][sl].copy_(H["weight"][sl], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                evs_w.append(ev)
+            for i in range(n_chunks):
+                sl = slice(bounds[i], bounds[i + 1])
+                T["vis"][sl].copy_(H["vis"][sl], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                evs_v.append(ev)
+        for i in range(n_chunks):
+            sl = slice(bounds[i], bounds[i + 1])
+            main.wait_event(evs_w[i])
+            imaging_weight_grid(T["uvw"][sl], T["weight"][sl], T["freq_chan"], gp_iw, grid=density, sum_weight=dsw)
+        if world > 1:
+            dist.all_reduce(density)
+            dist.all_reduce(dsw)
+        bf = calculate_briggs_parms(density, dsw, IW_PARMS)
+        iw = _standard_imaging_weight_degrid_numpy_wrap(density, T["uvw"], T["weight"], bf, T["freq_chan"], gp_iw,
+                                                        kernel_side_layout=True)
+        for i in range(n_chunks):
+            sl = slice(bounds[i], bounds[i + 1])
+            main.wait_event(evs_v[i])
+            standard_grid(T["vis"][sl], T["uvw"][sl], iw[sl], T["freq_chan"], cgk_t, gp, False, True, grid=grid,
+                          sum_weight=gsw)
+        if world > 1:
+            dist.reduce(torch.view_as_real(grid), 0)
+            dist.reduce(gsw, 0)
+        if rank == 0:
+            grid_host.copy_(grid, non_blocking=True)
+            gsw_host.copy_(gsw, non_blocking=True)
+
+    def timed(fn, steps, warmup, **kw):
+        for _ in range(warmup):
+            fn(**kw)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn(**kw)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_end = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t_begin, t_end
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms_step, t_begin, t_end = timed(lambda: step(T, record_kernel=True), a.steps, max(a.warmup, 3))
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    kern_ms = float(np.mean([e0.elapsed_time(e1) for (e0, e1) in grid_evs[-a.steps:]]))
+
+    e2e = None
+    if not a.no_e2e:
+        ms_e2e, _, _ = timed(e2e_step, a.steps, 3)
+        h2d = sum(H[k].numel() * H[k].element_size() for k in H)
+        d2h = grid_host.numel() * grid_host.element_size() + gsw_host.numel() * 8
+        e2e = {"value": world * n_samples / (ms_e2e * 1e-3), "unit": "vis/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "note": "pinned host buffers -> chunked H2D (copy stream) overlapped with kernels -> D2H of grid+sum_weight"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (std_grid_track), algorithmic bytes per SURVEY.md section 8d:
+    # n_samples * (8 B vis + 4 B weight) + uvw + grid written once
+    peak, peak_src = peaks()
+    alg_bytes = n_samples * 12 + a.n_time * d["n_baseline"] * 24 + n_ic * 2 * a.n_uv * a.n_uv * 8
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("std_grid_track_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "std_grid_track_kernel<float,complex,S=7,PP=2>",
+                "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src,
+                "note": "the kernel is FP32-issue bound (49 taps x 2 pol x 2 FMA per sample), not HBM bound; see DESIGN.md"}
+
+    cb = None
+    if not a.no_cpu_baseline:
+        cb, _ = cpu_arm(a, 1, 1, a.cpu_sample_times or 100)
+
+    line = {"metric": METRIC, "value": world * n_samples / (ms_step * 1e-3), "unit": "vis/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "samples_per_gpu": int(n_samples),
+                       "l2": "inputs (1.4 GB/step) are larger than L2 (126 MB), no explicit flush",
+                       "parallelism": "time-sharded x%d, NCCL all-reduce(density) + reduce(grid)" % world if world > 1 else "single GPU"},
+            "vis_tap_per_s": world * n_samples * SUPPORT * SUPPORT / (ms_step * 1e-3),
+            "gridding_kernel_vis_per_s": n_samples / (kern_ms * 1e-3),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * a.steps, "roofline": roofline, "cpu_baseline": cb}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.gpus > 1 and "RANK" not in os.environ:   # plain `python bench.py --gpus N`: relaunch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

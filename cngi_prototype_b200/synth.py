@@ -43,21 +43,31 @@ def pick_cell_size(uvw, freq, margin=1.15):
 
 
 def make_vis_set(n_ant, n_time, n_chan, n_pol, freq_lo, freq_hi, sigma_m, integration_s, dec_deg=34.0,
-                 seed=1234, flag_frac=0.02, complex_data=True, bad_rows=True, dtype="f64"):
+                 seed=1234, flag_frac=0.02, complex_data=True, bad_rows=True, dtype="f64", layout_seed=None,
+                 time_offset=None):
     """Returns dict(vis, uvw, weight, freq_chan, cell, n_baseline).
 
     vis ~ CN(0,1) with flag_frac of samples NaN (apply_flags semantics, cngi/vis/apply_flags.py:53),
     weight ~ U(0.5,1.5) with a few exact zeros and NaNs, a few NaN uvw rows (bad_rows).
+    layout_seed / time_offset: shards of ONE observation (same array, consecutive time ranges, different
+    noise) for the multi-GPU runs -- then the cell size comes from the baseline lengths, not from the tracks,
+    so that every shard uses the same grid.
     """
     rng = np.random.default_rng(seed)
-    xyz = antenna_layout(n_ant, sigma_m, rng)
+    sharded = layout_seed is not None or time_offset is not None
+    xyz = antenna_layout(n_ant, sigma_m, np.random.default_rng(layout_seed) if layout_seed is not None else rng)
     bl = baseline_vectors(xyz)
     n_bl = len(bl)
     span = EARTH_RATE * integration_s * n_time
     ha = np.linspace(-span / 2, span / 2, n_time)
+    if time_offset is not None:
+        ha = EARTH_RATE * integration_s * (time_offset + np.arange(n_time))
     uvw = uvw_tracks(bl, ha, np.deg2rad(dec_deg))
     freq = np.linspace(freq_lo, freq_hi, n_chan)
-    cell = pick_cell_size(uvw, freq)
+    if sharded:
+        cell = 1.0 / (2.0 * np.max(np.linalg.norm(bl, axis=1)) * np.max(freq) / C_LIGHT * 1.15)
+    else:
+        cell = pick_cell_size(uvw, freq)
     shape = (n_time, n_bl, n_chan, n_pol)
     fdt = np.float32 if dtype == "f32" else np.float64
     weight = rng.uniform(0.5, 1.5, size=shape).astype(fdt)
@@ -99,10 +109,14 @@ def config_c1(n_time=1000, n_chan=64, seed=1234, dtype="f64"):
     return make_vis_set(27, n_time, n_chan, 2, 1.0e9, 1.128e9, 350.0, integration, seed=seed, dtype=dtype)
 
 
-def config_c2(n_time=500, n_chan=128, seed=4321, dtype="f32"):
-    """ALMA-like: 43 antennas (903 baselines) x 500 x 6 s x 128 chan x 2 pol, 345-347 GHz."""
-    return make_vis_set(43, n_time, n_chan, 2, 345.0e9, 347.0e9, 300.0, 6.0, dec_deg=-23.0, seed=seed,
-                        dtype=dtype)
+def config_c2(n_time=500, n_chan=128, seed=4321, dtype="f32", shard=None):
+    """ALMA-like: 43 antennas (903 baselines) x 500 x 6 s x 128 chan x 2 pol, 345-347 GHz.
+    shard=r gives the r-th consecutive 500-integration block of one long observation (multi-GPU weak scaling)."""
+    if shard is None:
+        return make_vis_set(43, n_time, n_chan, 2, 345.0e9, 347.0e9, 300.0, 6.0, dec_deg=-23.0, seed=seed,
+                            dtype=dtype)
+    return make_vis_set(43, n_time, n_chan, 2, 345.0e9, 347.0e9, 300.0, 6.0, dec_deg=-23.0, seed=seed + 1000 * shard,
+                        dtype=dtype, layout_seed=seed, time_offset=shard * n_time - 2000)
 
 
 def config_c4(n_time=1000, n_chan=64, seed=99, dtype="f64"):
