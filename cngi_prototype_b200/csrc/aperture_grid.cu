@@ -33,6 +33,7 @@ struct ApParams {
     double dl, dm;
     int n_field, n_cfb, n_cfc, n_cfp, n_cu, n_cv;
     int os_u, os_v, max_support, do_psf, chan_mode;
+    const double *scale;   // [2, n_chan] uv_scale table
     double *buckets;       // A6: [n_field, n_cfb, n_cfc, n_cfp, n_ic, n_ip] weight sums
 };
 
@@ -57,10 +58,7 @@ __device__ __forceinline__ bool ap_locate(const ApParams &p, long long tb, int c
     if (!(f > -1)) return false;
     field_indx = ap_find_field(p, f);
     if (field_indx < 0) return false;
-    const double fr = p.freq[c];
-    if (!locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], uv_scale_of(fr, p.dl, p.n_u), uv_scale_of(fr, p.dm, p.n_v), p.n_u,
-                       p.n_v, cp))
-        return false;
+    if (!locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], p.scale[c], p.scale[p.n_chan + c], p.n_u, p.n_v, cp)) return false;
     return stamp_inside(cp.uc, cp.vc, p.max_support, p.n_u, p.n_v);
 }
 
@@ -232,11 +230,18 @@ extern "C" int cngi_b200_aperture_grid(const cngi_aperture_grid_args *a, void *s
     if (total == 0 || p.n_pol == 0) return CNGI_OK;
     const long long blocks = ceil_div(total, 256);
     CNGI_REQUIRE(blocks < (1LL << 31), "aperture_grid: too many samples");
+    cudaStream_t st = (cudaStream_t)stream;
+    double *scale = nullptr;
+    rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
+    if (rc != CNGI_OK) return rc;
+    p.scale = scale;
     if (a->precision == CNGI_F32)
-        aperture_grid_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+        aperture_grid_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(p);
     else
-        aperture_grid_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
-    CNGI_CUDA_TRY(cudaGetLastError());
+        aperture_grid_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scale, st);
+    CNGI_CUDA_TRY(e);
     return CNGI_OK;
 }
 
@@ -251,6 +256,10 @@ extern "C" int cngi_b200_aperture_weight_grid(const cngi_aperture_grid_args *a, 
     cudaStream_t st = (cudaStream_t)stream;
     const long long n_buckets = (long long)p.n_field * p.n_cfb * p.n_cfc * p.n_cfp * p.n_ic * p.n_ip;
     CNGI_REQUIRE(n_buckets < (1LL << 31), "aperture_weight_grid: too many (field, cf, plane) buckets");
+    double *scale = nullptr;
+    rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
+    if (rc != CNGI_OK) return rc;
+    p.scale = scale;
     CNGI_CUDA_TRY(cudaMallocAsync((void **)&p.buckets, n_buckets * sizeof(double), st));
     CNGI_CUDA_TRY(cudaMemsetAsync(p.buckets, 0, n_buckets * sizeof(double), st));
     const long long blocks = ceil_div(total, 256);
@@ -264,6 +273,7 @@ extern "C" int cngi_b200_aperture_weight_grid(const cngi_aperture_grid_args *a, 
     }
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(p.buckets, st);
+    cudaFreeAsync(scale, st);
     CNGI_CUDA_TRY(e);
     return CNGI_OK;
 }

@@ -97,8 +97,34 @@ __device__ __forceinline__ void red_add(double2 *p, double2 v)
     atomicAdd(&p->y, v.y);
 }
 
+// Adds `val` into base[index] with one reduction per distinct index in the warp when the warp hits at
+// most two distinct indices (continuum imaging: every lane hits the same sum_weight slot).
+__device__ __forceinline__ void warp_grouped_add(double *base, int index, double val, bool active)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(FULL, active);
+    for (int round = 0; round < 2 && todo; ++round) {
+        const int leader = __ffs(todo) - 1;
+        const int idx0 = __shfl_sync(FULL, index, leader);
+        const bool mine = active && (index == idx0) && ((todo >> lane) & 1u);
+        const unsigned grp = __ballot_sync(FULL, mine);
+        double v = mine ? val : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == leader) atomicAdd(base + idx0, v);
+        todo &= ~grp;
+    }
+    if ((todo >> lane) & 1u) atomicAdd(base + index, val);
+}
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();
+
+// uv_scale[0][c], uv_scale[1][c] for all channels in a stream-ordered scratch buffer (one ddiv per channel
+// instead of one per sample for the kernels that map a thread to a single sample).  Free with cudaFreeAsync.
+int make_uv_scale_table(const double *freq, int n_chan, double dl, double dm, int n_u, int n_v, cudaStream_t st,
+                        double **table);
 
 }  // namespace cngi

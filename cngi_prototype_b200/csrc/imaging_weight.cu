@@ -27,6 +27,7 @@ struct IwParams {
     const double *bf;
     long long ds_u, ds_v, ds_c, ds_p;
     void *out;
+    const double *scale;   // [2, n_chan] uv_scale table
 };
 
 __device__ __forceinline__ int iw_chan_of(const IwParams &p, int c)
@@ -36,32 +37,50 @@ __device__ __forceinline__ int iw_chan_of(const IwParams &p, int c)
     return (int)p.chan_map[c];
 }
 
-// thread <-> (time segment, baseline, chan); chan fastest so weight loads coalesce across the warp
-template <typename T> __global__ void __launch_bounds__(256) iw_grid_kernel(IwParams p)
+// thread <-> (time segment, baseline, group of G consecutive channels); group index fastest, so a warp reads
+// 32*G consecutive channels of one row (coalesced).  The thread walks time (outer) and its G channels (inner,
+// boustrophedon so consecutive samples stay neighbours in the uv plane) and run-length accumulates while the
+// (plane, cell, conjugate cell) key is unchanged.  With G > 1 (channels sharing an image plane, i.e. continuum)
+// this removes most same-address reductions: neighbouring channels of a baseline fall into the same cell.
+template <typename T, int G> __global__ void __launch_bounds__(256) iw_grid_kernel(IwParams p)
 {
-    const long long n_items = (long long)p.n_seg * p.n_baseline * p.n_chan;
-    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= n_items) return;
-    const int c = (int)(item % p.n_chan);
-    const long long r = item / p.n_chan;
+    const int n_cg = (p.n_chan + G - 1) / G;
+    const long long n_items = (long long)p.n_seg * p.n_baseline * n_cg;
+    long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = item < n_items;   // no early return: the warp reduces sum_weight together at the end
+    if (!in_range) item = 0;
+    const int cg = (int)(item % n_cg);
+    const long long r = item / n_cg;
     const int b = (int)(r % p.n_baseline);
     const int seg = (int)(r / p.n_baseline);
-    const int t_lo = seg * p.seg_len, t_hi = min(p.n_time, t_lo + p.seg_len);
-    const double f = p.freq[c];
-    const double us = uv_scale_of(f, p.dl, p.n_u), vs = uv_scale_of(f, p.dm, p.n_v);
-    const int a_chan = iw_chan_of(p, c);
+    const int t_lo = seg * p.seg_len, t_hi = in_range ? min(p.n_time, t_lo + p.seg_len) : t_lo;
+    const int c0 = cg * G;
+    const int ng = min(G, p.n_chan - c0);
+    double us[G], vs[G];
+    int a_chan[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int c = min(c0 + g, p.n_chan - 1);
+        const double f = p.freq[c];
+        us[g] = uv_scale_of(f, p.dl, p.n_u);
+        vs[g] = uv_scale_of(f, p.dm, p.n_v);
+        a_chan[g] = iw_chan_of(p, c);
+    }
     const bool average = p.n_pol >= 2;               // (n_pol >= 2) and do_imaging_weight, :328-330
     const double mid_u = (double)(p.n_u / 2), mid_v = (double)(p.n_v / 2);
 
-    int cur_u = -1, cur_v = 0, cur_cu = 0, cur_cv = 0;
-    double acc = 0.0, sw = 0.0;
+    int cur_plane = -1, cur_u = 0, cur_v = 0, cur_cu = 0, cur_cv = 0;
+    double acc = 0.0;
+    double sw[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) sw[g] = 0.0;
 
     auto flush = [&]() {
-        if (cur_u < 0 || acc == 0.0) return;
+        if (cur_plane < 0 || acc == 0.0) return;
         const bool conj_ok = cur_cu >= 0 && cur_cu < p.n_u && cur_cv >= 0 && cur_cv < p.n_v;
         for (int ip = 0; ip < p.n_pol; ++ip) {
             const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
-            double *plane = p.density + ((long long)a_chan * p.n_ip + a_pol) * p.n_u * (long long)p.n_v;
+            double *plane = p.density + ((long long)cur_plane * p.n_ip + a_pol) * p.n_u * (long long)p.n_v;
             atomicAdd(plane + (long long)cur_u * p.n_v + cur_v, acc);
             if (conj_ok) atomicAdd(plane + (long long)cur_cu * p.n_v + cur_cv, acc);
         }
@@ -70,28 +89,68 @@ template <typename T> __global__ void __launch_bounds__(256) iw_grid_kernel(IwPa
 
     for (int t = t_lo; t < t_hi; ++t) {
         const long long tb = (long long)t * p.n_baseline + b;
-        CellPos cp;
-        if (!locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], us, vs, p.n_u, p.n_v, cp)) continue;
-        if (!stamp_inside(cp.uc, cp.vc, 0, p.n_u, p.n_v)) continue;
-        const T *w = (const T *)p.weight + (tb * p.n_chan + c) * p.n_pol;
-        const double wd = average ? __ddiv_rn(__dadd_rn((double)w[0], (double)w[1]), 2.0) : (double)w[0];
-        if (isnan(wd) || wd == 0.0) continue;
-        // conjugate cell: int(-u + centre + 0.5)   (:309-318)
-        const double un = -__dmul_rn(p.uvw[tb * 3], us), vn = -__dmul_rn(p.uvw[tb * 3 + 1], vs);
-        const int cu = __double2int_rz(__dadd_rn(__dadd_rn(un, mid_u), 0.5));
-        const int cv = __double2int_rz(__dadd_rn(__dadd_rn(vn, mid_v), 0.5));
-        if (cp.uc != cur_u || cp.vc != cur_v || cu != cur_cu || cv != cur_cv) {
-            flush();
-            cur_u = cp.uc, cur_v = cp.vc, cur_cu = cu, cur_cv = cv;
+        const double uu = p.uvw[tb * 3], vv = p.uvw[tb * 3 + 1];
+        const T *wrow = (const T *)p.weight + (tb * p.n_chan + c0) * p.n_pol;
+        double wd[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {   // issue all loads of the row before the dependent math
+            wd[g] = 0.0;
+            if (g < ng) {
+                if (average) {
+                    double w0, w1;
+                    if (p.n_pol == 2) {
+                        if (sizeof(T) == 4) {
+                            const float2 w2 = *reinterpret_cast<const float2 *>(wrow + g * 2);
+                            w0 = (double)w2.x, w1 = (double)w2.y;
+                        } else {
+                            const double2 w2 = *reinterpret_cast<const double2 *>(wrow + g * 2);
+                            w0 = w2.x, w1 = w2.y;
+                        }
+                    } else {
+                        w0 = (double)wrow[g * p.n_pol], w1 = (double)wrow[g * p.n_pol + 1];
+                    }
+                    wd[g] = __ddiv_rn(__dadd_rn(w0, w1), 2.0);
+                } else {
+                    wd[g] = (double)wrow[g];
+                }
+            }
         }
-        acc += wd;
-        sw += wd + wd;   // sum_weight gets sel_weight*norm twice (:366-369), norm == cgk_1D[0] == 1
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+            const int g = (t & 1) ? G - 1 - gi : gi;
+            if (g >= ng) continue;
+            CellPos cp;
+            if (!locate_centre(uu, vv, us[g], vs[g], p.n_u, p.n_v, cp)) continue;
+            if (!stamp_inside(cp.uc, cp.vc, 0, p.n_u, p.n_v)) continue;
+            const double w = wd[g];
+            if (isnan(w) || w == 0.0) continue;
+            // conjugate cell: int(-u + centre + 0.5)   (:309-318)
+            const double un = -__dmul_rn(uu, us[g]), vn = -__dmul_rn(vv, vs[g]);
+            const int cu = __double2int_rz(__dadd_rn(__dadd_rn(un, mid_u), 0.5));
+            const int cv = __double2int_rz(__dadd_rn(__dadd_rn(vn, mid_v), 0.5));
+            if (a_chan[g] != cur_plane || cp.uc != cur_u || cp.vc != cur_v || cu != cur_cu || cv != cur_cv) {
+                flush();
+                cur_plane = a_chan[g], cur_u = cp.uc, cur_v = cp.vc, cur_cu = cu, cur_cv = cv;
+            }
+            acc += w;
+            sw[g] += w + w;   // sum_weight gets sel_weight*norm twice (:366-369), norm == cgk_1D[0] == 1
+        }
     }
     flush();
-    if (sw != 0.0) {
-        for (int ip = 0; ip < p.n_pol; ++ip) {
+    // sum_weight: fold channels of the same plane inside the thread, then one reduction per plane per warp
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        bool first = true;   // no earlier channel of this thread maps to the same plane
+#pragma unroll
+        for (int h = 0; h < G; ++h)
+            if (h < g && a_chan[h] == a_chan[g]) first = false;
+        double v = 0.0;
+#pragma unroll
+        for (int h = 0; h < G; ++h)
+            if (first && h >= g && h < ng && a_chan[h] == a_chan[g]) v += sw[h];
+        for (int ip = 0; ip < p.n_pol; ++ip) {   // n_pol is uniform, so the warp stays converged
             const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
-            atomicAdd(p.sum_weight + a_chan * p.n_ip + a_pol, sw);
+            warp_grouped_add(p.sum_weight, a_chan[g] * p.n_ip + a_pol, v, in_range && g < ng && v != 0.0);
         }
     }
 }
@@ -141,10 +200,8 @@ template <typename T> __global__ void __launch_bounds__(256) iw_degrid_kernel(Iw
     const long long tb = idx / p.n_chan;
     T *out = (T *)p.out + idx * p.n_pol;
     const T *nat = (const T *)p.weight + idx * p.n_pol;
-    const double f = p.freq[c];
     CellPos cp;
-    bool ok = locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], uv_scale_of(f, p.dl, p.n_u), uv_scale_of(f, p.dm, p.n_v),
-                            p.n_u, p.n_v, cp);
+    bool ok = locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], p.scale[c], p.scale[p.n_chan + c], p.n_u, p.n_v, cp);
     if (ok) ok = stamp_inside(cp.uc, cp.vc, 0, p.n_u, p.n_v);
     if (!ok) {   // off-grid or NaN uv: output stays 0 (:460,493,502)
         for (int ip = 0; ip < p.n_pol; ++ip) out[ip] = (T)0;
@@ -186,18 +243,36 @@ extern "C" int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *a, void *s
     p.weight = a->weight, p.uvw = a->uvw, p.freq = a->freq_chan, p.chan_map = a->chan_map, p.pol_map = a->pol_map;
     p.density = a->density, p.sum_weight = a->sum_weight, p.dl = a->delta_lm[0], p.dm = a->delta_lm[1];
     p.chan_mode = a->chan_mode;
-    const long long per_seg = (long long)p.n_baseline * p.n_chan;
-    long long n_seg = ceil_div((long long)sm_count() * 2048 * 4, per_seg);   // ~4 waves of full occupancy
+    // channels per thread: only useful when neighbouring channels share a plane
+    int G = 1;
+    if (p.chan_mode != CNGI_CHAN_CUBE)
+        while (G < 8 && G * 2 <= p.n_chan) G *= 2;
+    const long long per_seg = (long long)p.n_baseline * ceil_div(p.n_chan, G);
+    long long n_seg = ceil_div((long long)sm_count() * 2048 * 2, per_seg);   // ~2 waves of full occupancy
     if (n_seg < 1) n_seg = 1;
     p.seg_len = (int)ceil_div(p.n_time, n_seg);
     if (p.seg_len < 16) p.seg_len = 16;
     p.n_seg = (int)ceil_div(p.n_time, p.seg_len);
     const long long blocks = ceil_div(per_seg * p.n_seg, 256);
     CNGI_REQUIRE(blocks < (1LL << 31), "imaging_weight_grid: too many work items");
-    if (a->precision == CNGI_F32)
-        iw_grid_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
-    else
-        iw_grid_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CNGI_IW_LAUNCH(TT, GG) iw_grid_kernel<TT, GG><<<(unsigned)blocks, 256, 0, st>>>(p)
+    if (a->precision == CNGI_F32) {
+        switch (G) {
+            case 1: CNGI_IW_LAUNCH(float, 1); break;
+            case 2: CNGI_IW_LAUNCH(float, 2); break;
+            case 4: CNGI_IW_LAUNCH(float, 4); break;
+            default: CNGI_IW_LAUNCH(float, 8); break;
+        }
+    } else {
+        switch (G) {
+            case 1: CNGI_IW_LAUNCH(double, 1); break;
+            case 2: CNGI_IW_LAUNCH(double, 2); break;
+            case 4: CNGI_IW_LAUNCH(double, 4); break;
+            default: CNGI_IW_LAUNCH(double, 8); break;
+        }
+    }
+#undef CNGI_IW_LAUNCH
     CNGI_CUDA_TRY(cudaGetLastError());
     return CNGI_OK;
 }
@@ -245,10 +320,17 @@ extern "C" int cngi_b200_imaging_weight_degrid(const cngi_iw_degrid_args *a, voi
     p.ds_u = a->density_stride[0], p.ds_v = a->density_stride[1], p.ds_c = a->density_stride[2], p.ds_p = a->density_stride[3];
     const long long blocks = ceil_div(total, 256);
     CNGI_REQUIRE(blocks < (1LL << 31), "imaging_weight_degrid: too many samples");
+    cudaStream_t st = (cudaStream_t)stream;
+    double *scale = nullptr;
+    int rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
+    if (rc != CNGI_OK) return rc;
+    p.scale = scale;
     if (a->precision == CNGI_F32)
-        iw_degrid_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+        iw_degrid_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(p);
     else
-        iw_degrid_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
-    CNGI_CUDA_TRY(cudaGetLastError());
+        iw_degrid_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scale, st);
+    CNGI_CUDA_TRY(e);
     return CNGI_OK;
 }

@@ -27,6 +27,23 @@ int sm_count()
     return cached[dev];
 }
 
+__global__ void uv_scale_kernel(const double *freq, int n_chan, double dl, double dm, int n_u, int n_v, double *table)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chan) return;
+    table[c] = uv_scale_of(freq[c], dl, n_u);
+    table[n_chan + c] = uv_scale_of(freq[c], dm, n_v);
+}
+
+int make_uv_scale_table(const double *freq, int n_chan, double dl, double dm, int n_u, int n_v, cudaStream_t st,
+                        double **table)
+{
+    CNGI_CUDA_TRY(cudaMallocAsync((void **)table, (size_t)2 * n_chan * sizeof(double), st));
+    uv_scale_kernel<<<(n_chan + 127) / 128, 128, 0, st>>>(freq, n_chan, dl, dm, n_u, n_v, *table);
+    CNGI_CUDA_TRY(cudaGetLastError());
+    return CNGI_OK;
+}
+
 }  // namespace cngi
 
 extern "C" int cngi_b200_abi_version(void) { return CNGI_B200_ABI_VERSION; }

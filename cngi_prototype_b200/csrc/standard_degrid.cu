@@ -21,6 +21,7 @@ struct DgParams {
     void *vis;
     double dl, dm;
     int support, oversampling, chan_mode, normalize;
+    const double *scale;   // [2, n_chan] uv_scale table
 };
 
 // generic support: `LW` lanes per sample (power of two >= support, <= 32)
@@ -39,10 +40,8 @@ template <typename T, int LW> __global__ void __launch_bounds__(256) std_degrid_
     const int c = (int)(idx % p.n_chan);
     const long long tb = idx / p.n_chan;
     const int half = p.support / 2;
-    const double f = p.freq[c];
     CellPos cp;
-    bool ok = locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], uv_scale_of(f, p.dl, p.n_u), uv_scale_of(f, p.dm, p.n_v), p.n_u,
-                            p.n_v, cp);
+    bool ok = locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], p.scale[c], p.scale[p.n_chan + c], p.n_u, p.n_v, cp);
     if (ok) ok = stamp_inside(cp.uc, cp.vc, half, p.n_u, p.n_v);
     int uoff = 0, voff = 0;
     if (ok) {
@@ -90,7 +89,7 @@ template <typename T, int LW> __global__ void __launch_bounds__(256) std_degrid_
     }
 }
 
-template <typename T> static int launch_degrid(const DgParams &p, cudaStream_t st)
+template <typename T> static int launch_degrid(DgParams p, cudaStream_t st)
 {
     const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
     int lw = 1;
@@ -99,6 +98,10 @@ template <typename T> static int launch_degrid(const DgParams &p, cudaStream_t s
     const long long warps = ceil_div(total, spw);
     const long long blocks = ceil_div(warps * 32, 256);
     CNGI_REQUIRE(blocks < (1LL << 31), "standard_degrid: too many samples");
+    double *scale = nullptr;
+    int rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
+    if (rc != CNGI_OK) return rc;
+    p.scale = scale;
     switch (lw) {
         case 1: std_degrid_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(p); break;
         case 2: std_degrid_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(p); break;
@@ -107,7 +110,9 @@ template <typename T> static int launch_degrid(const DgParams &p, cudaStream_t s
         case 16: std_degrid_kernel<T, 16><<<(unsigned)blocks, 256, 0, st>>>(p); break;
         default: std_degrid_kernel<T, 32><<<(unsigned)blocks, 256, 0, st>>>(p); break;
     }
-    CNGI_CUDA_TRY(cudaGetLastError());
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scale, st);
+    CNGI_CUDA_TRY(e);
     return CNGI_OK;
 }
 

@@ -25,6 +25,7 @@
 //        broadcast-reading the records, flushing on cell change, then S*PP FMAs per lane.
 //    Only __syncwarp() separates the phases; warps never wait for each other.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace cngi {
 
@@ -47,6 +48,7 @@ struct StdParams {
     // track kernel decomposition
     int G, log2G, seg_len, n_seg, n_cspan, n_pgrp;
     long long n_tasks;
+    const double *scale;   // naive kernel: [2, n_chan] uv_scale table
 };
 
 __device__ __forceinline__ int chan_of(const StdParams &p, int c)
@@ -56,27 +58,6 @@ __device__ __forceinline__ int chan_of(const StdParams &p, int c)
     return (int)p.chan_map[c];
 }
 __device__ __forceinline__ int pol_of(const StdParams &p, int ip) { return p.pol_map ? (int)p.pol_map[ip] : ip; }
-
-// Adds `val` into base[index] with one reduction per distinct index in the warp when the warp hits at
-// most two distinct indices (continuum imaging: every lane hits the same sum_weight slot).
-__device__ __forceinline__ void warp_grouped_add(double *base, int index, double val, bool active)
-{
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    unsigned todo = __ballot_sync(FULL, active);
-    for (int round = 0; round < 2 && todo; ++round) {
-        const int leader = __ffs(todo) - 1;
-        const int idx0 = __shfl_sync(FULL, index, leader);
-        const bool mine = active && (index == idx0) && ((todo >> lane) & 1u);
-        const unsigned grp = __ballot_sync(FULL, mine);
-        double v = mine ? val : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if (lane == leader) atomicAdd(base + idx0, v);
-        todo &= ~grp;
-    }
-    if ((todo >> lane) & 1u) atomicAdd(base + index, val);
-}
 
 // ------------------------------------------------------------------------------------------------
 //  naive kernel
@@ -94,9 +75,7 @@ __global__ void __launch_bounds__(256) std_grid_naive_kernel(StdParams p)
     CellPos cp;
     bool ok = in_range;
     if (ok) {
-        const double us = uv_scale_of(p.freq[c], p.dl, p.n_u);
-        const double vs = uv_scale_of(p.freq[c], p.dm, p.n_v);
-        ok = locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], us, vs, p.n_u, p.n_v, cp);
+        ok = locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], p.scale[c], p.scale[p.n_chan + c], p.n_u, p.n_v, cp);
     }
     if (ok) ok = stamp_inside(cp.uc, cp.vc, half, p.n_u, p.n_v);
     int uoff = 0, voff = 0, a_chan = 0;
@@ -149,15 +128,40 @@ __global__ void __launch_bounds__(256) std_grid_naive_kernel(StdParams p)
 // ------------------------------------------------------------------------------------------------
 //  track kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kTrackBlock = 256;
+// Packed pair arithmetic.  Accumulators are (re, im) pairs (complex grid) or (pol0, pol1) pairs (real grid), so
+// that on sm_100a every fp32 update is one FFMA2 (fma.rn.f32x2: two FMAs per issue slot, the only way to reach
+// the full FP32 rate with three register operands).  fp64 uses two DFMAs.
+template <typename T> struct Pair;
+template <> struct Pair<float> { using type = float2; };
+template <> struct Pair<double> { using type = double2; };
+
+__device__ __forceinline__ float2 pk_fma(float2 a, float s, float2 c)
+{
+    float2 b = make_float2(s, s), d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(*reinterpret_cast<unsigned long long *>(&d))
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
+          "l"(*reinterpret_cast<unsigned long long *>(&c)));
+    return d;
+}
+__device__ __forceinline__ float2 pk_mul(float2 a, float s)
+{
+    float2 b = make_float2(s, s), d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long *>(&d))
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return d;
+}
+__device__ __forceinline__ double2 pk_fma(double2 a, double s, double2 c) { return make_double2(fma(a.x, s, c.x), fma(a.y, s, c.y)); }
+__device__ __forceinline__ double2 pk_mul(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
 
 template <typename T, bool CPLX, int S, int PP> struct TrackCfg {
     static constexpr int IPW = (S <= 3) ? 8 : (S <= 7) ? 4 : (S <= 15) ? 2 : 1;   // items per warp
     static constexpr int ITER = 32 / IPW;                                         // samples per item per round
-    static constexpr int NC = CPLX ? 2 : 1;
+    static constexpr int NV = CPLX ? PP : (PP + 1) / 2;                           // accumulator pairs per cell
     static constexpr int TPV = 16 / (int)sizeof(T);                               // T's per 16-byte vector
     static constexpr int SP = (S + TPV - 1) / TPV * TPV;                          // padded tap count
-    static constexpr int WD = (PP * NC + TPV - 1) / TPV * TPV;                    // padded weighted-data count
+    static constexpr int WD = (NV * 2 + TPV - 1) / TPV * TPV;                     // padded weighted-data count
     static constexpr int OFF_IDX = 0;
     static constexpr int OFF_WD = 16;
     static constexpr int OFF_CV = OFF_WD + WD * (int)sizeof(T);
@@ -168,12 +172,15 @@ template <typename T, bool CPLX, int S, int PP> struct TrackCfg {
     static constexpr int WARP_BYTES = 32 * REC_BYTES;
 };
 
-template <typename T, bool CPLX, int S, int PP>
-__global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p)
+constexpr int kSameFlag = 1 << 16;   // record idx.w: this sample has the same (plane, uc, vc) as the item's previous one
+
+template <typename T, bool CPLX, int S, int PP, int BLK>
+__global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
 {
     using Cfg = TrackCfg<T, CPLX, S, PP>;
     using CT = typename Cplx<T>::type;
-    constexpr int IPW = Cfg::IPW, ITER = Cfg::ITER, SP = Cfg::SP, NC = Cfg::NC;
+    using P2 = typename Pair<T>::type;
+    constexpr int IPW = Cfg::IPW, ITER = Cfg::ITER, SP = Cfg::SP, NV = Cfg::NV;
     constexpr int HALF = S / 2;
     const unsigned FULL = 0xffffffffu;
 
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const long long task = (long long)blockIdx.x * (kTrackBlock / 32) + warp;
+    const long long task = (long long)blockIdx.x * (BLK / 32) + warp;
     if (task >= p.n_tasks) return;   // no block-wide barrier after this point
     unsigned char *wbuf = smem + table_bytes + warp * Cfg::WARP_BYTES;
 
@@ -203,6 +210,7 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
     const int c_base = cspan * IPW * G;
     const int p0 = pgrp * PP;
     const int npol = min(PP, p.n_pol - p0);
+    const long long plane_cells = (long long)p.n_u * p.n_v;
 
     // ---- phase-1 role: lane <-> staged sample ------------------------------------------------------
     const int k1 = lane % IPW;
@@ -222,6 +230,7 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
     double sw_acc[PP];
 #pragma unroll
     for (int ip = 0; ip < PP; ++ip) sw_acc[ip] = 0.0;
+    long long carry_key = -1;   // key of the item's last sample of the previous round (lanes < IPW use it)
 
     // ---- phase-2 role: lane <-> (item, u residue) --------------------------------------------------
     const bool active2 = lane < IPW * S;
@@ -230,37 +239,38 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
     int apol[PP];
 #pragma unroll
     for (int ip = 0; ip < PP; ++ip) apol[ip] = (ip < npol) ? pol_of(p, p0 + ip) : 0;
-    T acc_re[S][PP], acc_im[S][PP];
+    P2 acc[S][NV];
 #pragma unroll
     for (int j = 0; j < S; ++j)
 #pragma unroll
-        for (int ip = 0; ip < PP; ++ip) acc_re[j][ip] = acc_im[j][ip] = (T)0;
+        for (int n = 0; n < NV; ++n) acc[j][n].x = acc[j][n].y = (T)0;
     int cur_plane = -1, cur_u = -1, cur_vc = 0, cur_vcm = 0;
-
-    auto v_cell = [&](int j, int vc, int vcm) {   // the v in [vc-HALF, vc+HALF] with v == j (mod S)
-        int tv = vcm - j;
-        if (tv < 0) tv += S;
-        return vc + HALF - tv;
-    };
-    auto flush_one = [&](int j, int v) {
+    long long plane_off[PP];   // element offset of plane (cur_plane, apol[ip]) in the grid
 #pragma unroll
-        for (int ip = 0; ip < PP; ++ip) {
-            if (ip < npol) {
-                const long long cell = (((long long)cur_plane * p.n_ip + apol[ip]) * p.n_u + cur_u) * p.n_v + v;
-                if (CPLX) {
-                    if (acc_re[j][ip] != (T)0 || acc_im[j][ip] != (T)0) {
-                        CT val;
-                        val.x = acc_re[j][ip];
-                        val.y = acc_im[j][ip];
-                        red_add((CT *)p.grid + cell, val);
-                    }
-                } else {
-                    if (acc_re[j][ip] != (T)0) red_add((T *)p.grid + cell, acc_re[j][ip]);
+    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = 0;
+
+    // flush accumulator j (grid cell (cur_u, v) of the current plane) with native reductions, then clear it
+    auto flush_one = [&](int j, int v) {
+        const int cell = cur_u * p.n_v + v;
+        if (CPLX) {
+#pragma unroll
+            for (int ip = 0; ip < PP; ++ip) {
+                if (ip < npol && (acc[j][ip].x != (T)0 || acc[j][ip].y != (T)0)) {
+                    CT val;
+                    val.x = acc[j][ip].x;
+                    val.y = acc[j][ip].y;
+                    red_add((CT *)p.grid + plane_off[ip] + cell, val);
                 }
             }
-            acc_re[j][ip] = (T)0;
-            acc_im[j][ip] = (T)0;
+        } else {
+#pragma unroll
+            for (int ip = 0; ip < PP; ++ip) {
+                const T v1 = (ip & 1) ? acc[j][ip / 2].y : acc[j][ip / 2].x;
+                if (ip < npol && v1 != (T)0) red_add((T *)p.grid + plane_off[ip] + cell, v1);
+            }
         }
+#pragma unroll
+        for (int n = 0; n < NV; ++n) acc[j][n].x = acc[j][n].y = (T)0;
     };
 
     // ---- raw sample registers (software prefetch: loads of round n+1 fly during phase 2 of round n) --
@@ -271,7 +281,7 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
     bool raw_ok = false;
     auto load_raw = [&](int t0) {
         const int t = t0 + row1;
-        raw_ok = chan_ok && (row1 < spr) && (t < t_hi);
+        raw_ok = chan_ok && (t < t_hi);
         raw_flag = 0;
         if (raw_ok) {
             const long long tb = (long long)t * p.n_baseline + b;
@@ -324,6 +334,7 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
     auto stage = [&]() {
         unsigned char *rec = wbuf + lane * Cfg::REC_BYTES;
         int4 idx = make_int4(-1, 0, 0, 0);
+        long long key = -1;
         CellPos cp;
         bool ok = raw_ok && locate_centre(raw_u, raw_v, us, vs, p.n_u, p.n_v, cp);
         if (ok) ok = stamp_inside(cp.uc, cp.vc, HALF, p.n_u, p.n_v);
@@ -346,8 +357,12 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
                     if (!masked(wre, wim)) {
                         any = true;
                         wsel[ip] = w;
-                        wd[ip * NC] = (T)wre;
-                        if (CPLX) wd[ip * NC + NC - 1] = (T)wim;
+                        if (CPLX) {
+                            wd[2 * ip] = (T)wre;
+                            wd[2 * ip + 1] = (T)wim;
+                        } else {
+                            wd[ip] = (T)wre;   // pair n holds (pol 2n, pol 2n+1)
+                        }
                     }
                 }
             }
@@ -388,42 +403,61 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
                 const int ucm = (ub == 0) ? S - 1 : ub - 1;   // (uc + HALF) mod S
                 const int vcm = (vb == 0) ? S - 1 : vb - 1;
                 idx = make_int4(cp.uc, cp.vc, a_chan1, ucm | (vcm << 8));
+                key = ((long long)a_chan1 * p.n_u + cp.uc) * p.n_v + cp.vc;
             }
         }
+        // the item's previous sample is IPW slots back (or the last slot of the previous round)
+        long long prev = __shfl_up_sync(FULL, key, IPW);
+        if (lane < IPW) prev = carry_key;
+        carry_key = __shfl_sync(FULL, key, 32 - IPW + k1);
+        if (key >= 0 && key == prev) idx.w |= kSameFlag;
         *reinterpret_cast<int4 *>(rec + Cfg::OFF_IDX) = idx;
     };
 
     // ---- phase 2: consume ----------------------------------------------------------------------------
     auto consume = [&]() {
-#pragma unroll 1
+#pragma unroll 2
         for (int i = 0; i < ITER; ++i) {
             const unsigned char *rec = wbuf + (i * IPW + k2) * Cfg::REC_BYTES;
             const int4 idx = *reinterpret_cast<const int4 *>(rec + Cfg::OFF_IDX);
             if (idx.x < 0) continue;
-            int tu = (idx.w & 0xff) - r2;
-            if (tu < 0) tu += S;
-            const int my_u = idx.x + HALF - tu;
-            const int vc = idx.y, vcm = idx.w >> 8;
-            if (my_u != cur_u || idx.z != cur_plane) {
-                if (cur_u >= 0) {
+            if (!(idx.w & kSameFlag)) {   // the stamp moved (or first sample): which accumulators leave?
+                int tu = (idx.w & 0xff) - r2;
+                if (tu < 0) tu += S;
+                const int my_u = idx.x + HALF - tu;
+                const int vc = idx.y, vcm = (idx.w >> 8) & 0xff;
+                if (my_u != cur_u || idx.z != cur_plane) {   // my column changed: all S accumulators go
+                    if (cur_u >= 0) {
 #pragma unroll
-                    for (int j = 0; j < S; ++j) flush_one(j, v_cell(j, cur_vc, cur_vcm));
-                }
-                cur_u = my_u;
-                cur_plane = idx.z;
-                cur_vc = vc;
-                cur_vcm = vcm;
-            } else if (vc != cur_vc) {
+                        for (int j = 0; j < S; ++j) {
+                            int tv = cur_vcm - j;
+                            if (tv < 0) tv += S;
+                            flush_one(j, cur_vc + HALF - tv);
+                        }
+                    }
+                    if (idx.z != cur_plane) {
 #pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    const int old_v = v_cell(j, cur_vc, cur_vcm);
-                    if (old_v != v_cell(j, vc, vcm)) flush_one(j, old_v);
+                        for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)idx.z * p.n_ip + apol[ip]) * plane_cells;
+                    }
+                    cur_u = my_u, cur_plane = idx.z, cur_vc = vc, cur_vcm = vcm;
+                } else if (vc != cur_vc) {   // the window slid by d rows: the rows that dropped out go
+                    const int d = vc - cur_vc;
+                    // tv = distance of accumulator j's row from the top of the old window; rows with tv < a (d < 0)
+                    // or tv >= bnd (d > 0) left the window
+                    const int a = d < 0 ? min(-d, S) : 0;
+                    const int bnd = d > 0 ? max(S - d, 0) : S;
+#pragma unroll
+                    for (int j = 0; j < S; ++j) {
+                        int tv = cur_vcm - j;
+                        if (tv < 0) tv += S;
+                        if (tv < a || tv >= bnd) flush_one(j, cur_vc + HALF - tv);
+                    }
+                    cur_vc = vc, cur_vcm = vcm;
                 }
-                cur_vc = vc;
-                cur_vcm = vcm;
             }
             const T cu = reinterpret_cast<const T *>(rec + Cfg::OFF_CU)[r2];
-            T cv[SP], wd[Cfg::WD];
+            T cv[SP];
+            P2 wd[Cfg::WD / 2];
             if (sizeof(T) == 4) {
 #pragma unroll
                 for (int q = 0; q < SP; q += 4) {
@@ -433,7 +467,7 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
 #pragma unroll
                 for (int q = 0; q < Cfg::WD; q += 4) {
                     const float4 x = *reinterpret_cast<const float4 *>(rec + Cfg::OFF_WD + q * 4);
-                    wd[q] = x.x, wd[q + 1] = x.y, wd[q + 2] = x.z, wd[q + 3] = x.w;
+                    wd[q / 2].x = x.x, wd[q / 2].y = x.y, wd[q / 2 + 1].x = x.z, wd[q / 2 + 1].y = x.w;
                 }
             } else {
 #pragma unroll
@@ -444,18 +478,14 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
 #pragma unroll
                 for (int q = 0; q < Cfg::WD; q += 2) {
                     const double2 x = *reinterpret_cast<const double2 *>(rec + Cfg::OFF_WD + q * 8);
-                    wd[q] = x.x, wd[q + 1] = x.y;
+                    wd[q / 2].x = x.x, wd[q / 2].y = x.y;
                 }
             }
 #pragma unroll
-            for (int ip = 0; ip < PP; ++ip) {
-                const T tre = cu * wd[ip * NC];
-                const T tim = CPLX ? cu * wd[ip * NC + NC - 1] : (T)0;
+            for (int n = 0; n < NV; ++n) {
+                const P2 t = pk_mul(wd[n], cu);
 #pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    acc_re[j][ip] = fma(tre, cv[j], acc_re[j][ip]);
-                    if (CPLX) acc_im[j][ip] = fma(tim, cv[j], acc_im[j][ip]);
-                }
+                for (int j = 0; j < S; ++j) acc[j][n] = pk_fma(t, cv[j], acc[j][n]);
             }
         }
     };
@@ -471,7 +501,11 @@ __global__ void __launch_bounds__(kTrackBlock) std_grid_track_kernel(StdParams p
     }
     if (active2 && cur_u >= 0) {
 #pragma unroll
-        for (int j = 0; j < S; ++j) flush_one(j, v_cell(j, cur_vc, cur_vcm));
+        for (int j = 0; j < S; ++j) {
+            int tv = cur_vcm - j;
+            if (tv < 0) tv += S;
+            flush_one(j, cur_vc + HALF - tv);
+        }
     }
 
     // ---- sum_weight: lanes that share a channel reduce first, then one reduction per image plane -------
@@ -495,7 +529,7 @@ static int validate(const cngi_std_grid_args *a)
                  "standard_grid: negative sample dimension");
     CNGI_REQUIRE(a->n_u > 0 && a->n_v > 0 && a->n_imag_chan > 0 && a->n_imag_pol > 0, "standard_grid: empty grid");
     CNGI_REQUIRE(a->n_u < (1 << 24) && a->n_v < (1 << 24), "standard_grid: grid side too large");
-    CNGI_REQUIRE(a->n_imag_chan * a->n_u < (1LL << 31), "standard_grid: n_imag_chan*n_u overflows int32");
+    CNGI_REQUIRE(a->n_u * a->n_v < (1LL << 31), "standard_grid: n_u*n_v overflows int32");
     CNGI_REQUIRE(a->n_time * a->n_baseline < (1LL << 31) && a->n_chan < (1 << 24) && a->n_pol <= 64,
                  "standard_grid: sample dimensions out of range");
     CNGI_REQUIRE(a->precision == CNGI_F32 || a->precision == CNGI_F64, "standard_grid: bad precision %d", a->precision);
@@ -532,7 +566,34 @@ template <typename T, bool CPLX> static int launch_naive(StdParams p, cudaStream
     if (total == 0 || p.n_pol == 0) return CNGI_OK;
     const long long blocks = ceil_div(total, 256);
     CNGI_REQUIRE(blocks < (1LL << 31), "standard_grid: too many samples for one launch");
+    double *scale = nullptr;
+    int rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
+    if (rc != CNGI_OK) return rc;
+    p.scale = scale;
     std_grid_naive_kernel<T, CPLX><<<(unsigned)blocks, 256, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scale, st);
+    CNGI_CUDA_TRY(e);
+    return CNGI_OK;
+}
+
+static int track_block_override()
+{
+    // development knob: CNGI_TRACK_BLOCK=128|256 overrides the block size picked per precision
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CNGI_TRACK_BLOCK");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+template <typename T, bool CPLX, int S, int PP, int BLK>
+static int launch_track_blk(StdParams p, long long blocks, size_t smem, cudaStream_t st)
+{
+    auto kern = std_grid_track_kernel<T, CPLX, S, PP, BLK>;
+    CNGI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, BLK, smem, st>>>(p);
     CNGI_CUDA_TRY(cudaGetLastError());
     return CNGI_OK;
 }
@@ -570,16 +631,16 @@ static int launch_track(StdParams p, const cngi_std_grid_args *a, cudaStream_t s
     p.seg_len = seg_len;
     p.n_seg = (int)ceil_div(p.n_time, seg_len);
     p.n_tasks = per_seg * p.n_seg;
-    const int wpb = kTrackBlock / 32;
+    // fp64 accumulators need ~150 registers/thread: smaller blocks let three of them share an SM
+    int blk = sizeof(T) == 8 ? 128 : 256;
+    if (track_block_override() == 128 || track_block_override() == 256) blk = track_block_override();
+    const int wpb = blk / 32;
     const long long blocks = ceil_div(p.n_tasks, wpb);
     CNGI_REQUIRE(blocks < (1LL << 31), "standard_grid: too many work items for one launch");
     const size_t smem = (size_t)((p.table_len * (int)sizeof(T) + 15) / 16 * 16) + (size_t)wpb * Cfg::WARP_BYTES;
     CNGI_REQUIRE(smem <= 227 * 1024, "standard_grid: CF table too large for shared memory (%zu bytes)", smem);
-    auto kern = std_grid_track_kernel<T, CPLX, S, PP>;
-    CNGI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)blocks, kTrackBlock, smem, st>>>(p);
-    CNGI_CUDA_TRY(cudaGetLastError());
-    return CNGI_OK;
+    if (blk == 128) return launch_track_blk<T, CPLX, S, PP, 128>(p, blocks, smem, st);
+    return launch_track_blk<T, CPLX, S, PP, 256>(p, blocks, smem, st);
 }
 
 template <typename T, bool CPLX, int S> static int launch_track_pp(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
