@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libcngi_b200.so")
+LIB_PATH = os.environ.get("CNGI_B200_LIB") or os.path.join(HERE, "csrc", "libcngi_b200.so")   # env: tuning builds only
 
 F32, F64 = 0, 1
 CHAN_GENERAL, CHAN_CUBE, CHAN_CONTINUUM = 0, 1, 2

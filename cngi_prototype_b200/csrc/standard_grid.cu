@@ -26,6 +26,7 @@
 //    Only __syncwarp() separates the phases; warps never wait for each other.
 #include "common.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 namespace cngi {
 
@@ -47,6 +48,7 @@ struct StdParams {
     int table_len;
     // track kernel decomposition
     int G, log2G, seg_len, n_seg, n_cspan, n_pgrp;
+    int c_lo, c_n;         // channel window handled by this launch (bounds the shared-memory channel table)
     long long n_tasks;
     const double *scale;   // naive kernel: [2, n_chan] uv_scale table
 };
@@ -135,14 +137,12 @@ template <typename T> struct Pair;
 template <> struct Pair<float> { using type = float2; };
 template <> struct Pair<double> { using type = double2; };
 
-__device__ __forceinline__ float2 pk_fma(float2 a, float s, float2 c)
+__device__ __forceinline__ void pk_fma_acc(float2 &c, float2 a, float s)   // c += a * (s, s); accumulator tied in place
 {
-    float2 b = make_float2(s, s), d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;"
-        : "=l"(*reinterpret_cast<unsigned long long *>(&d))
-        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
-          "l"(*reinterpret_cast<unsigned long long *>(&c)));
-    return d;
+    float2 b = make_float2(s, s);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(*reinterpret_cast<unsigned long long *>(&c))
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
 }
 __device__ __forceinline__ float2 pk_mul(float2 a, float s)
 {
@@ -152,7 +152,11 @@ __device__ __forceinline__ float2 pk_mul(float2 a, float s)
         : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
     return d;
 }
-__device__ __forceinline__ double2 pk_fma(double2 a, double s, double2 c) { return make_double2(fma(a.x, s, c.x), fma(a.y, s, c.y)); }
+__device__ __forceinline__ void pk_fma_acc(double2 &c, double2 a, double s)
+{
+    c.x = fma(a.x, s, c.x);
+    c.y = fma(a.y, s, c.y);
+}
 __device__ __forceinline__ double2 pk_mul(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
 
 template <typename T, bool CPLX, int S, int PP> struct TrackCfg {
@@ -174,8 +178,16 @@ template <typename T, bool CPLX, int S, int PP> struct TrackCfg {
 
 constexpr int kSameFlag = 1 << 16;   // record idx.w: this sample has the same (plane, uc, vc) as the item's previous one
 
+#ifndef CNGI_TRACK_MINB128
+#define CNGI_TRACK_MINB128 4   // min resident blocks per SM asked of ptxas (caps registers/thread); tuned on B200
+#endif
+#ifndef CNGI_TRACK_MINB256
+#define CNGI_TRACK_MINB256 2
+#endif
+
 template <typename T, bool CPLX, int S, int PP, int BLK>
-__global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
+__global__ void __launch_bounds__(BLK, (sizeof(T) == 4 ? (BLK == 128 ? CNGI_TRACK_MINB128 : CNGI_TRACK_MINB256) : 1))
+std_grid_track_kernel(StdParams p)
 {
     using Cfg = TrackCfg<T, CPLX, S, PP>;
     using CT = typename Cplx<T>::type;
@@ -187,14 +199,21 @@ __global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
     extern __shared__ __align__(16) unsigned char smem[];
     T *table = reinterpret_cast<T *>(smem);
     const int table_bytes = (p.table_len * (int)sizeof(T) + 15) / 16 * 16;
+    double *scale = reinterpret_cast<double *>(smem + table_bytes);   // uv_scale[0][c], uv_scale[1][c]
+    const int scale_bytes = 2 * p.c_n * (int)sizeof(double);
     for (int i = threadIdx.x; i < p.table_len; i += blockDim.x) table[i] = (T)p.cgk[i];
+    for (int i = threadIdx.x; i < p.c_n; i += blockDim.x) {
+        const double f = p.freq[p.c_lo + i];
+        scale[i] = uv_scale_of(f, p.dl, p.n_u);
+        scale[p.c_n + i] = uv_scale_of(f, p.dm, p.n_v);
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long task = (long long)blockIdx.x * (BLK / 32) + warp;
     if (task >= p.n_tasks) return;   // no block-wide barrier after this point
-    unsigned char *wbuf = smem + table_bytes + warp * Cfg::WARP_BYTES;
+    unsigned char *wbuf = smem + table_bytes + scale_bytes + warp * Cfg::WARP_BYTES;
 
     // ---- task decode: (time segment, baseline, pol group, channel span), channel span fastest ------
     const int cspan = (int)(task % p.n_cspan);
@@ -207,7 +226,8 @@ __global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
     const int t_hi = min(p.n_time, t_lo + p.seg_len);
     const int G = p.G;
     const int spr = ITER >> p.log2G;   // time steps per round
-    const int c_base = cspan * IPW * G;
+    const int c_base = p.c_lo + cspan * IPW * G;
+    const int c_end = p.c_lo + p.c_n;
     const int p0 = pgrp * PP;
     const int npol = min(PP, p.n_pol - p0);
     const long long plane_cells = (long long)p.n_u * p.n_v;
@@ -217,16 +237,15 @@ __global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
     const int q1 = lane / IPW;
     const int g1 = q1 & (G - 1);
     const int row1 = q1 >> p.log2G;
-    const int c1 = c_base + k1 * G + g1;
-    const bool chan_ok = c1 < p.n_chan;
-    double us = 0.0, vs = 0.0;
-    int a_chan1 = 0;
-    if (chan_ok) {
-        const double f = p.freq[c1];
-        us = uv_scale_of(f, p.dl, p.n_u);
-        vs = uv_scale_of(f, p.dm, p.n_v);
-        a_chan1 = chan_of(p, c1);
-    }
+    // Channels of an item are walked boustrophedon (forward on even time steps, backward on odd ones) when they all
+    // share one image plane, so that consecutive samples of an item are always uv neighbours.
+    const bool zigzag = (p.chan_mode == CNGI_CHAN_CONTINUUM) && G > 1;
+    const int c_fwd = c_base + k1 * G + g1;
+    const int c_bwd = c_base + k1 * G + (G - 1 - g1);
+    int c1 = c_fwd;                                  // channel of the sample held in the raw registers
+    bool chan_ok = c_fwd < c_end;
+    const bool any_chan_ok = zigzag ? (c_fwd < c_end || c_bwd < c_end) : chan_ok;
+    const int a_chan1 = chan_ok ? chan_of(p, c_fwd) : 0;   // zigzag only runs in continuum mode: plane 0 either way
     double sw_acc[PP];
 #pragma unroll
     for (int ip = 0; ip < PP; ++ip) sw_acc[ip] = 0.0;
@@ -260,17 +279,19 @@ __global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
                     val.x = acc[j][ip].x;
                     val.y = acc[j][ip].y;
                     red_add((CT *)p.grid + plane_off[ip] + cell, val);
+                    acc[j][ip].x = acc[j][ip].y = (T)0;   // zero only when flushed (see the real-grid branch)
                 }
             }
         } else {
 #pragma unroll
             for (int ip = 0; ip < PP; ++ip) {
-                const T v1 = (ip & 1) ? acc[j][ip / 2].y : acc[j][ip / 2].x;
-                if (ip < npol && v1 != (T)0) red_add((T *)p.grid + plane_off[ip] + cell, v1);
+                T &v1 = (ip & 1) ? acc[j][ip / 2].y : acc[j][ip / 2].x;
+                if (ip < npol && v1 != (T)0) {   // zero only what was flushed: unconditional writes in this divergent
+                    red_add((T *)p.grid + plane_off[ip] + cell, v1);   // path make ptxas copy the accumulators
+                    v1 = (T)0;
+                }
             }
         }
-#pragma unroll
-        for (int n = 0; n < NV; ++n) acc[j][n].x = acc[j][n].y = (T)0;
     };
 
     // ---- raw sample registers (software prefetch: loads of round n+1 fly during phase 2 of round n) --
@@ -281,6 +302,10 @@ __global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
     bool raw_ok = false;
     auto load_raw = [&](int t0) {
         const int t = t0 + row1;
+        if (zigzag) {
+            c1 = (t & 1) ? c_bwd : c_fwd;
+            chan_ok = c1 < c_end;
+        }
         raw_ok = chan_ok && (t < t_hi);
         raw_flag = 0;
         if (raw_ok) {
@@ -336,7 +361,8 @@ __global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
         int4 idx = make_int4(-1, 0, 0, 0);
         long long key = -1;
         CellPos cp;
-        bool ok = raw_ok && locate_centre(raw_u, raw_v, us, vs, p.n_u, p.n_v, cp);
+        bool ok = raw_ok;
+        if (ok) ok = locate_centre(raw_u, raw_v, scale[c1 - p.c_lo], scale[p.c_n + c1 - p.c_lo], p.n_u, p.n_v, cp);
         if (ok) ok = stamp_inside(cp.uc, cp.vc, HALF, p.n_u, p.n_v);
         if (ok) {
             T wd[Cfg::WD];
@@ -420,6 +446,34 @@ __global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
         for (int i = 0; i < ITER; ++i) {
             const unsigned char *rec = wbuf + (i * IPW + k2) * Cfg::REC_BYTES;
             const int4 idx = *reinterpret_cast<const int4 *>(rec + Cfg::OFF_IDX);
+            // taps and data are fetched together with the cell ids (before the branches below), so an iteration
+            // exposes one shared-memory latency instead of two
+            const T cu = reinterpret_cast<const T *>(rec + Cfg::OFF_CU)[r2];
+            T cv[SP];
+            P2 wd[Cfg::WD / 2];
+            if (sizeof(T) == 4) {
+#pragma unroll
+                for (int q = 0; q < SP; q += 4) {
+                    const float4 x = *reinterpret_cast<const float4 *>(rec + Cfg::OFF_CV + q * 4);
+                    cv[q] = x.x, cv[q + 1] = x.y, cv[q + 2] = x.z, cv[q + 3] = x.w;
+                }
+#pragma unroll
+                for (int q = 0; q < Cfg::WD; q += 4) {
+                    const float4 x = *reinterpret_cast<const float4 *>(rec + Cfg::OFF_WD + q * 4);
+                    wd[q / 2].x = x.x, wd[q / 2].y = x.y, wd[q / 2 + 1].x = x.z, wd[q / 2 + 1].y = x.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < SP; q += 2) {
+                    const double2 x = *reinterpret_cast<const double2 *>(rec + Cfg::OFF_CV + q * 8);
+                    cv[q] = x.x, cv[q + 1] = x.y;
+                }
+#pragma unroll
+                for (int q = 0; q < Cfg::WD; q += 2) {
+                    const double2 x = *reinterpret_cast<const double2 *>(rec + Cfg::OFF_WD + q * 8);
+                    wd[q / 2].x = x.x, wd[q / 2].y = x.y;
+                }
+            }
             if (idx.x < 0) continue;
             if (!(idx.w & kSameFlag)) {   // the stamp moved (or first sample): which accumulators leave?
                 int tu = (idx.w & 0xff) - r2;
@@ -455,37 +509,11 @@ __global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
                     cur_vc = vc, cur_vcm = vcm;
                 }
             }
-            const T cu = reinterpret_cast<const T *>(rec + Cfg::OFF_CU)[r2];
-            T cv[SP];
-            P2 wd[Cfg::WD / 2];
-            if (sizeof(T) == 4) {
-#pragma unroll
-                for (int q = 0; q < SP; q += 4) {
-                    const float4 x = *reinterpret_cast<const float4 *>(rec + Cfg::OFF_CV + q * 4);
-                    cv[q] = x.x, cv[q + 1] = x.y, cv[q + 2] = x.z, cv[q + 3] = x.w;
-                }
-#pragma unroll
-                for (int q = 0; q < Cfg::WD; q += 4) {
-                    const float4 x = *reinterpret_cast<const float4 *>(rec + Cfg::OFF_WD + q * 4);
-                    wd[q / 2].x = x.x, wd[q / 2].y = x.y, wd[q / 2 + 1].x = x.z, wd[q / 2 + 1].y = x.w;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < SP; q += 2) {
-                    const double2 x = *reinterpret_cast<const double2 *>(rec + Cfg::OFF_CV + q * 8);
-                    cv[q] = x.x, cv[q + 1] = x.y;
-                }
-#pragma unroll
-                for (int q = 0; q < Cfg::WD; q += 2) {
-                    const double2 x = *reinterpret_cast<const double2 *>(rec + Cfg::OFF_WD + q * 8);
-                    wd[q / 2].x = x.x, wd[q / 2].y = x.y;
-                }
-            }
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
                 const P2 t = pk_mul(wd[n], cu);
 #pragma unroll
-                for (int j = 0; j < S; ++j) acc[j][n] = pk_fma(t, cv[j], acc[j][n]);
+                for (int j = 0; j < S; ++j) pk_fma_acc(acc[j][n], t, cv[j]);
             }
         }
     };
@@ -514,7 +542,7 @@ __global__ void __launch_bounds__(BLK) std_grid_track_kernel(StdParams p)
     for (int ip = 0; ip < PP; ++ip) {
         double v = sw_acc[ip];
         for (int o = span; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
-        const bool lead = (lane < span) && chan_ok && (ip < npol);
+        const bool lead = (lane < span) && any_chan_ok && (ip < npol);
         warp_grouped_add(p.sum_weight, a_chan1 * p.n_ip + apol[ip], v, lead);
     }
 }
@@ -603,44 +631,52 @@ static int launch_track(StdParams p, const cngi_std_grid_args *a, cudaStream_t s
 {
     using Cfg = TrackCfg<T, CPLX, S, PP>;
     if (p.n_time == 0 || p.n_baseline == 0 || p.n_chan == 0 || p.n_pol == 0) return CNGI_OK;
-    // channels walked per item: only worth it when neighbouring channels share an image plane
-    int G = a->chan_group;
-    if (G <= 0) G = (p.chan_mode == CNGI_CHAN_CONTINUUM) ? Cfg::ITER : 1;
-    if (G > Cfg::ITER) G = Cfg::ITER;
-    while (G > 1 && (Cfg::IPW * G / 2) >= p.n_chan) G >>= 1;   // do not span more channels than exist
-    int log2G = 0;
-    while ((1 << (log2G + 1)) <= G) ++log2G;
-    G = 1 << log2G;
-    p.G = G, p.log2G = log2G;
-    const int spr = Cfg::ITER / G;
-    p.n_cspan = (int)ceil_div(p.n_chan, Cfg::IPW * G);
-    p.n_pgrp = (int)ceil_div(p.n_pol, PP);
-    const long long per_seg = (long long)p.n_baseline * p.n_cspan * p.n_pgrp;
-    int seg_len = a->time_segment;
-    if (seg_len <= 0) {
-        // aim for ~16 resident-warp waves so the tail is small, but keep segments long enough that the
-        // final flush (S*S cells per item) is amortised
-        const long long target = (long long)sm_count() * 24 * 16;
-        long long n_seg = ceil_div(target, per_seg);
-        if (n_seg < 1) n_seg = 1;
-        seg_len = (int)ceil_div(p.n_time, n_seg);
-        const int min_len = 64 * spr / Cfg::ITER > 8 ? 64 * spr / Cfg::ITER : 8;
-        if (seg_len < min_len) seg_len = min_len;
+    constexpr int kMaxChanWindow = 2048;   // 32 KB of uv-scale table per block at most
+    for (int c_lo = 0; c_lo < p.n_chan; c_lo += kMaxChanWindow) {
+        p.c_lo = c_lo;
+        p.c_n = std::min(kMaxChanWindow, p.n_chan - c_lo);
+        // channels walked per item: only worth it when neighbouring channels share an image plane
+        int G = a->chan_group;
+        if (G <= 0) G = (p.chan_mode == CNGI_CHAN_CONTINUUM) ? Cfg::ITER : 1;
+        if (G > Cfg::ITER) G = Cfg::ITER;
+        while (G > 1 && (Cfg::IPW * G / 2) >= p.c_n) G >>= 1;   // do not span more channels than exist
+        int log2G = 0;
+        while ((1 << (log2G + 1)) <= G) ++log2G;
+        G = 1 << log2G;
+        p.G = G, p.log2G = log2G;
+        const int spr = Cfg::ITER / G;
+        p.n_cspan = (int)ceil_div(p.c_n, Cfg::IPW * G);
+        p.n_pgrp = (int)ceil_div(p.n_pol, PP);
+        const long long per_seg = (long long)p.n_baseline * p.n_cspan * p.n_pgrp;
+        int seg_len = a->time_segment;
+        if (seg_len <= 0) {
+            // aim for ~16 resident-warp waves so the tail is small, but keep segments long enough that the
+            // final flush (S*S cells per item) is amortised
+            const long long target = (long long)sm_count() * 24 * 16;
+            long long n_seg = ceil_div(target, per_seg);
+            if (n_seg < 1) n_seg = 1;
+            seg_len = (int)ceil_div(p.n_time, n_seg);
+            const int min_len = 64 * spr / Cfg::ITER > 8 ? 64 * spr / Cfg::ITER : 8;
+            if (seg_len < min_len) seg_len = min_len;
+        }
+        seg_len = (int)(ceil_div(seg_len, spr) * spr);
+        p.seg_len = seg_len;
+        p.n_seg = (int)ceil_div(p.n_time, seg_len);
+        p.n_tasks = per_seg * p.n_seg;
+        // fp64 accumulators need ~150 registers/thread: smaller blocks let three of them share an SM
+        int blk = 128;
+        if (track_block_override() == 128 || track_block_override() == 256) blk = track_block_override();
+        const int wpb = blk / 32;
+        const long long blocks = ceil_div(p.n_tasks, wpb);
+        CNGI_REQUIRE(blocks < (1LL << 31), "standard_grid: too many work items for one launch");
+        const size_t smem = (size_t)((p.table_len * (int)sizeof(T) + 15) / 16 * 16) + (size_t)2 * p.c_n * sizeof(double) +
+                            (size_t)wpb * Cfg::WARP_BYTES;
+        CNGI_REQUIRE(smem <= 227 * 1024, "standard_grid: CF table too large for shared memory (%zu bytes)", smem);
+        int rc = blk == 128 ? launch_track_blk<T, CPLX, S, PP, 128>(p, blocks, smem, st)
+                            : launch_track_blk<T, CPLX, S, PP, 256>(p, blocks, smem, st);
+        if (rc != CNGI_OK) return rc;
     }
-    seg_len = (int)(ceil_div(seg_len, spr) * spr);
-    p.seg_len = seg_len;
-    p.n_seg = (int)ceil_div(p.n_time, seg_len);
-    p.n_tasks = per_seg * p.n_seg;
-    // fp64 accumulators need ~150 registers/thread: smaller blocks let three of them share an SM
-    int blk = sizeof(T) == 8 ? 128 : 256;
-    if (track_block_override() == 128 || track_block_override() == 256) blk = track_block_override();
-    const int wpb = blk / 32;
-    const long long blocks = ceil_div(p.n_tasks, wpb);
-    CNGI_REQUIRE(blocks < (1LL << 31), "standard_grid: too many work items for one launch");
-    const size_t smem = (size_t)((p.table_len * (int)sizeof(T) + 15) / 16 * 16) + (size_t)wpb * Cfg::WARP_BYTES;
-    CNGI_REQUIRE(smem <= 227 * 1024, "standard_grid: CF table too large for shared memory (%zu bytes)", smem);
-    if (blk == 128) return launch_track_blk<T, CPLX, S, PP, 128>(p, blocks, smem, st);
-    return launch_track_blk<T, CPLX, S, PP, 256>(p, blocks, smem, st);
+    return CNGI_OK;
 }
 
 template <typename T, bool CPLX, int S> static int launch_track_pp(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
@@ -651,6 +687,9 @@ template <typename T, bool CPLX, int S> static int launch_track_pp(StdParams p, 
 
 template <typename T, bool CPLX> static int dispatch(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
 {
+#ifdef CNGI_TRACK_MINIMAL   // SASS experiments: instantiate one kernel only
+    return launch_track<float, true, 7, 2>(p, a, st);
+#else
     int algo = a->algorithm;
     const bool track_ok = (a->support == 3 || a->support == 5 || a->support == 7 || a->support == 9) &&
                           a->oversampling >= 1 && p.table_len <= 8192;
@@ -668,6 +707,7 @@ template <typename T, bool CPLX> static int dispatch(StdParams p, const cngi_std
         }
     }
     return launch_naive<T, CPLX>(p, st);
+#endif
 }
 
 }  // namespace cngi

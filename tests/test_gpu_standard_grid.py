@@ -137,6 +137,17 @@ def test_invariance_to_work_decomposition(sg, oracle, chan_group, time_segment):
         _check(g, s, g_ref, s_ref, TOL["f64"])
 
 
+def test_many_channels_span_several_channel_windows(sg, oracle):
+    """More channels than one shared-memory channel table holds (the launcher loops over 2048-channel windows)."""
+    from cngi_prototype_b200 import synth
+    d = synth.make_vis_set(3, 6, 2100, 1, 1e9, 1.5e9, 300.0, 300.0, seed=15)
+    cgk = oracle._create_prolate_spheroidal_kernel_1D(100, 7)
+    gp = synth.grid_parms_for(64, d["cell"], chan_mode="continuum")
+    g_ref, s_ref = oracle._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp)
+    g, s = sg._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp, algorithm=2)
+    _check(g, s, g_ref, s_ref, TOL["f64"])
+
+
 def test_random_order_uvw_no_coherence(sg, oracle):
     """uvw with no time coherence at all (worst case for the track kernel) must still be exact."""
     from cngi_prototype_b200 import synth
