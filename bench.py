@@ -37,7 +37,7 @@ METRIC = "visibilities gridded/sec"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-time", type=int, default=500)
@@ -131,7 +131,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -199,25 +199,22 @@ def run_b200(a):
     gsw_host = torch.empty(gsw.shape, dtype=gsw.dtype).pin_memory()
     grid_evs = []
 
+    from types import SimpleNamespace
+    from cngi_prototype_b200 import distributed as D
+    ops = D.cuda_ops()
+    bufs = SimpleNamespace(density=density, dsw=dsw, grid=grid, gsw=gsw)
+
+    def grid_hook(what):   # CUDA events around the dominant kernel, on the stream it is launched on
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if what == "begin":
+            grid_evs.append([ev, None])
+        else:
+            grid_evs[-1][1] = ev
+
     def step(src, record_kernel=False):
-        density.zero_(), dsw.zero_(), grid.zero_(), gsw.zero_()
-        imaging_weight_grid(src["uvw"], src["weight"], src["freq_chan"], gp_iw, grid=density, sum_weight=dsw)
-        if world > 1:   # every rank needs the full density for its degrid
-            dist.all_reduce(density)
-            dist.all_reduce(dsw)
-        bf = calculate_briggs_parms(density, dsw, IW_PARMS)
-        iw = _standard_imaging_weight_degrid_numpy_wrap(density, src["uvw"], src["weight"], bf, src["freq_chan"], gp_iw,
-                                                        kernel_side_layout=True)
-        if record_kernel:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        standard_grid(src["vis"], src["uvw"], iw, src["freq_chan"], cgk_t, gp, False, True, grid=grid, sum_weight=gsw)
-        if record_kernel:
-            e1.record()
-            grid_evs.append((e0, e1))
-        if world > 1:   # partial uv-grids + sum of weights -> rank 0 (before the FFT)
-            dist.reduce(torch.view_as_real(grid), 0)
-            dist.reduce(gsw, 0)
+        # the sharding / collective control flow is the one tests/test_distributed_gloo.py exercises on CPU
+        D.continuum_imaging_step(ops, src, gp, gp_iw, IW_PARMS, cgk_t, bufs, grid_hook=grid_hook if record_kernel else None)
 
     copy_stream = torch.cuda.Stream(device=dev)
     n_chunks = 8

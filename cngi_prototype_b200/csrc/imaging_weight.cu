@@ -109,7 +109,7 @@ template <typename T, int G> __global__ void __launch_bounds__(256) iw_grid_kern
                     } else {
                         w0 = (double)wrow[g * p.n_pol], w1 = (double)wrow[g * p.n_pol + 1];
                     }
-                    wd[g] = __ddiv_rn(__dadd_rn(w0, w1), 2.0);
+                    wd[g] = __dmul_rn(__dadd_rn(w0, w1), 0.5)   /* == /2.0 exactly */;
                 } else {
                     wd[g] = (double)wrow[g];
                 }
@@ -208,7 +208,7 @@ template <typename T> __global__ void __launch_bounds__(256) iw_degrid_kernel(Iw
         return;
     }
     const int a_chan = iw_chan_of(p, c);
-    const double avg = p.n_pol == 2 ? __ddiv_rn(__dadd_rn((double)nat[0], (double)nat[1]), 2.0) : 0.0;
+    const double avg = p.n_pol == 2 ? __dmul_rn(__dadd_rn((double)nat[0], (double)nat[1]), 0.5)   /* == /2.0 exactly */ : 0.0;
     for (int ip = 0; ip < p.n_pol; ++ip) {
         const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
         double iw = p.n_pol == 2 ? avg : (double)nat[ip];   // :508-511
@@ -218,7 +218,11 @@ template <typename T> __global__ void __launch_bounds__(256) iw_degrid_kernel(Iw
             if (!isnan(rho) && rho != 0.0) {
                 const double f0 = p.bf[a_chan * p.n_ip + a_pol];
                 const double f1 = p.bf[((long long)p.n_ic + a_chan) * p.n_ip + a_pol];
-                iw = __ddiv_rn(iw, __dadd_rn(__dmul_rn(f0, rho), f1));   // :515-516
+                const double den = __dadd_rn(__dmul_rn(f0, rho), f1);   // :515-516
+                if (sizeof(T) == 4)
+                    iw = (double)__fdiv_rn((float)iw, (float)den);   // result is stored as fp32 anyway
+                else
+                    iw = __ddiv_rn(iw, den);
             }
         }
         out[ip] = (T)iw;

@@ -1,0 +1,117 @@
+"""Multi-GPU decomposition of the gridding path: one process per GPU, torch.distributed (NCCL over NVLink).
+
+Replaces the reference's dask decomposition (one delayed task per (time, baseline, chan) chunk, each returning a
+full grid, summed by a pairwise `da.add` tree -- /root/reference/ngcasa/imaging/_imaging_utils/_standard_grid.py:58-98,
+_tree_sum_list :109-120) with device-resident partial grids and one collective per grid:
+
+  continuum (all channels -> one image plane): samples are sharded along TIME; every rank grids its shard into a
+      full partial grid; partial grids + sum_weight are summed with reduce (to the rank that runs the FFT) or
+      all-reduce (imaging-weight density: every rank needs all of it for its own degrid).
+  cube (channel c -> image plane c): samples are sharded along CHANNEL; each rank owns its image planes end to end
+      (grid -> FFT -> normalise), exactly like synthesis_imaging_cube.py:105-124; no exchange is needed.
+
+The collectives are size-independent of the sample count (one uv-grid), so they are issued once per step, after all
+local samples are gridded.  The compute operators are injected (`ops`), so the same control flow runs on GPUs with
+the CUDA operators (bench.py, NCCL) and on CPUs with the oracle (tests, gloo).
+"""
+from types import SimpleNamespace
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n, rank, world_size):
+    """Contiguous, balanced [lo, hi) block of n items for `rank` (first n % world_size ranks get one extra)."""
+    base, extra = divmod(int(n), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def time_shard(arrays, rank, world_size):
+    """Slices the time axis (axis 0) of every sample array in the dict; freq_chan and scalars pass through."""
+    n_time = arrays["uvw"].shape[0]
+    lo, hi = shard_range(n_time, rank, world_size)
+    out = {}
+    for k, v in arrays.items():
+        out[k] = v[lo:hi] if (hasattr(v, "shape") and len(v.shape) >= 2 and v.shape[0] == n_time) else v
+    return out
+
+
+def channel_shard(arrays, rank, world_size):
+    """Slices the channel axis: axis 2 of the 4-D sample arrays and axis 0 of freq_chan; uvw is replicated."""
+    n_chan = arrays["freq_chan"].shape[0]
+    lo, hi = shard_range(n_chan, rank, world_size)
+    out = {}
+    for k, v in arrays.items():
+        if k == "freq_chan":
+            out[k] = v[lo:hi]
+        elif hasattr(v, "shape") and len(v.shape) == 4:
+            out[k] = v[:, :, lo:hi]
+        else:
+            out[k] = v
+    return out
+
+
+def _as_real(t):
+    return torch.view_as_real(t) if t.is_complex() else t
+
+
+def allreduce_sum(*tensors):
+    """In-place sum over ranks (complex tensors are reduced as interleaved reals)."""
+    if world()[1] > 1:
+        for t in tensors:
+            dist.all_reduce(_as_real(t))
+
+
+def reduce_sum(dst, *tensors):
+    """In-place sum onto rank `dst` (other ranks' buffers are left unspecified, as with ncclReduce)."""
+    if world()[1] > 1:
+        for t in tensors:
+            dist.reduce(_as_real(t), dst)
+
+
+def continuum_imaging_step(ops, d, gp, gp_iw, iw_parms, cgk, bufs, grid_hook=None):
+    """One time-sharded continuum step on this rank's shard `d` (dict of vis, uvw, weight, freq_chan):
+
+        density grid -> ALL-REDUCE(density, sum_weight) -> Briggs factors -> weight degrid
+        -> standard gridding of vis * imaging weight -> REDUCE(grid, sum_weight) to rank 0.
+
+    `ops` provides imaging_weight_grid(uvw, w, freq, gp_iw, grid=, sum_weight=), briggs(density, sw, parms),
+    degrid(density, uvw, w, briggs, freq, gp_iw) and standard_grid(vis, uvw, w, freq, cgk, gp, grid=, sum_weight=);
+    `bufs` holds the accumulators density, dsw, grid, gsw (zeroed here).  Returns the imaging weights.
+    """
+    for t in (bufs.density, bufs.dsw, bufs.grid, bufs.gsw):
+        t.zero_()
+    ops.imaging_weight_grid(d["uvw"], d["weight"], d["freq_chan"], gp_iw, grid=bufs.density, sum_weight=bufs.dsw)
+    allreduce_sum(bufs.density, bufs.dsw)          # every rank needs the full density for its own degrid
+    bf = ops.briggs(bufs.density, bufs.dsw, iw_parms)
+    iw = ops.degrid(bufs.density, d["uvw"], d["weight"], bf, d["freq_chan"], gp_iw)
+    if grid_hook is not None:
+        grid_hook("begin")
+    ops.standard_grid(d["vis"], d["uvw"], iw, d["freq_chan"], cgk, gp, grid=bufs.grid, sum_weight=bufs.gsw)
+    if grid_hook is not None:
+        grid_hook("end")
+    reduce_sum(0, bufs.grid, bufs.gsw)             # partial uv-grids -> the rank that runs the FFT
+    return iw
+
+
+def cuda_ops():
+    """The product operators (libcngi_b200.so through the Python mirror) in the shape continuum_imaging_step expects."""
+    from ._standard_grid import standard_grid
+    from ._imaging_weight import (imaging_weight_grid, calculate_briggs_parms,
+                                  _standard_imaging_weight_degrid_numpy_wrap)
+
+    def degrid(density, uvw, w, bf, freq, gp_iw):
+        return _standard_imaging_weight_degrid_numpy_wrap(density, uvw, w, bf, freq, gp_iw, kernel_side_layout=True)
+
+    def grid(vis, uvw, w, freq, cgk, gp, grid=None, sum_weight=None):
+        return standard_grid(vis, uvw, w, freq, cgk, gp, False, True, grid=grid, sum_weight=sum_weight)
+
+    return SimpleNamespace(imaging_weight_grid=imaging_weight_grid, briggs=calculate_briggs_parms, degrid=degrid,
+                           standard_grid=grid)

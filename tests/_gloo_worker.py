@@ -1,0 +1,77 @@
+"""Worker for tests/test_distributed_gloo.py: one rank of a world_size-N gloo job on CPU.
+Runs the SAME control flow the GPU bench uses (cngi_prototype_b200.distributed.continuum_imaging_step) with the
+CPU oracle injected as the compute operators."""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+
+from cngi_prototype_b200 import synth, distributed as D  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+IW = dict(weighting="briggs", robust=0.5)
+
+
+def oracle_ops():
+    def iw_grid(uvw, w, freq, gp_iw, grid=None, sum_weight=None):
+        g, s = O._standard_grid_psf_numpy_wrap(uvw.numpy(), w.numpy(), freq.numpy(), np.ones(1), gp_iw)
+        grid += torch.from_numpy(g)
+        sum_weight += torch.from_numpy(s)
+
+    def briggs(density, sw, parms):
+        return torch.from_numpy(O._calculate_briggs_parms(density.numpy(), sw.numpy(), parms))
+
+    def degrid(density, uvw, w, bf, freq, gp_iw):
+        api = np.moveaxis(density.numpy(), (0, 1), (2, 3))
+        return torch.from_numpy(O._standard_imaging_weight_degrid_numpy_wrap(api, uvw.numpy(), w.numpy(), bf.numpy(),
+                                                                             freq.numpy(), gp_iw))
+
+    def std_grid(vis, uvw, w, freq, cgk, gp, grid=None, sum_weight=None):
+        g, s = O._standard_grid_numpy_wrap(vis.numpy(), uvw.numpy(), w.numpy(), freq.numpy(), cgk, gp)
+        grid += torch.from_numpy(g)
+        sum_weight += torch.from_numpy(s)
+
+    return SimpleNamespace(imaging_weight_grid=iw_grid, briggs=briggs, degrid=degrid, standard_grid=std_grid)
+
+
+def dataset():
+    d = synth.make_vis_set(7, 24, 6, 2, 1e9, 1.1e9, 300.0, 200.0, seed=17)
+    n = 96
+    gp = synth.grid_parms_for(n, d["cell"], chan_mode="continuum")
+    gp_iw = synth.grid_parms_for(n, d["cell"], chan_mode="continuum", support=1, oversampling=0, do_psf=True,
+                                 complex_grid=False, do_imaging_weight=True)
+    return d, gp, gp_iw, n
+
+
+def main():
+    out = sys.argv[1]
+    dist.init_process_group("gloo")
+    rank, ws = dist.get_rank(), dist.get_world_size()
+    d, gp, gp_iw, n = dataset()
+    cgk = O._create_prolate_spheroidal_kernel_1D(100, 7)
+    full = {k: torch.from_numpy(np.ascontiguousarray(d[k])) for k in ("vis", "uvw", "weight", "freq_chan")}
+    # continuum: time sharding + all-reduce(density) + reduce(grid)
+    shard = D.time_shard(full, rank, ws)
+    bufs = SimpleNamespace(density=torch.zeros((1, 2, n, n), dtype=torch.float64), dsw=torch.zeros((1, 2), dtype=torch.float64),
+                           grid=torch.zeros((1, 2, n, n), dtype=torch.complex128), gsw=torch.zeros((1, 2), dtype=torch.float64))
+    iw = D.continuum_imaging_step(oracle_ops(), shard, gp, gp_iw, IW, cgk, bufs)
+    # cube: channel sharding, no exchange; gather the owned planes only to check them
+    gpc = dict(gp, chan_mode="cube")
+    cs = D.channel_shard(full, rank, ws)
+    gc, sc = O._standard_grid_numpy_wrap(cs["vis"].numpy(), cs["uvw"].numpy(), cs["weight"].numpy(), cs["freq_chan"].numpy(),
+                                         cgk, gpc)
+    np.savez(os.path.join(out, "rank%d.npz" % rank), grid=bufs.grid.numpy(), gsw=bufs.gsw.numpy(), iw=iw.numpy(),
+             density=bufs.density.numpy(), cube_grid=gc, cube_sw=sc, chan_range=np.array(D.shard_range(6, rank, ws)),
+             time_range=np.array(D.shard_range(24, rank, ws)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

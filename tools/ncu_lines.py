@@ -17,7 +17,7 @@ for r in rows:
         fname = r[1].split("/")[-1]
     elif r[0] == "Line No":
         hdr = r
-    elif hdr and r[0].isdigit() and len(r) == len(hdr):
+    elif hdr and r[0].isdigit() and len(r) == len(hdr) and (not lines or len(r) == len(lines[0][1])):
         lines.append((fname, r))
 i_inst = hdr.index("Instructions Executed")
 i_thr = hdr.index("Thread Instructions Executed")
@@ -30,7 +30,7 @@ tot_t = sum(float(r[i_thr] or 0) for _, r in lines)
 print("total warp instructions %.4g   thread instr %.4g (avg active lanes %.1f)   samples %d" % (tot_i, tot_t, tot_t / tot_i, tot_s))
 agg = {}
 for i, h in stall_cols:
-    agg[h] = sum(float(r[i] or 0) for _, r in lines)
+    agg[h] = sum(float(r[i] or 0) for _, r in lines if i < len(r))
 print("stall mix: " + ", ".join("%s %.1f%%" % (h[6:], 100 * v / tot_s) for h, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
 lines.sort(key=lambda fr: -float(fr[1][i_inst] or 0))
 print("%6s %6s %5s  %s" % ("inst%", "samp%", "lanes", "line"))
