@@ -160,23 +160,26 @@ __device__ __forceinline__ void pk_fma_acc(double2 &c, double2 a, double s)
 __device__ __forceinline__ double2 pk_mul(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
 
 template <typename T, bool CPLX, int S, int PP> struct TrackCfg {
-    static constexpr int IPW = (S <= 3) ? 8 : (S <= 7) ? 4 : (S <= 15) ? 2 : 1;   // items per warp
-    static constexpr int ITER = 32 / IPW;                                         // samples per item per round
+    // The register window is W x W cells, W = the power of two above the support (8 for S = 7): one spare column /
+    // row of hysteresis, so a stamp that jitters by a cell between samples (channels swept back and forth across a
+    // cell boundary) flushes nothing, and all residue arithmetic is a bit mask.
+    static constexpr int W = (S < 4) ? 4 : (S < 8) ? 8 : (S < 16) ? 16 : 32;
+    static constexpr int IPW = 32 / W;                                            // items per warp
+    static constexpr int ITER = 32 / IPW;                                         // samples per item per round (== W)
     static constexpr int NV = CPLX ? PP : (PP + 1) / 2;                           // accumulator pairs per cell
     static constexpr int TPV = 16 / (int)sizeof(T);                               // T's per 16-byte vector
-    static constexpr int SP = (S + TPV - 1) / TPV * TPV;                          // padded tap count
     static constexpr int WD = (NV * 2 + TPV - 1) / TPV * TPV;                     // padded weighted-data count
     static constexpr int OFF_IDX = 0;
     static constexpr int OFF_WD = 16;
     static constexpr int OFF_CV = OFF_WD + WD * (int)sizeof(T);
-    static constexpr int OFF_CU = OFF_CV + SP * (int)sizeof(T);
-    static constexpr int RAW_BYTES = OFF_CU + SP * (int)sizeof(T);
+    static constexpr int OFF_CU = OFF_CV + W * (int)sizeof(T);
+    static constexpr int RAW_BYTES = OFF_CU + W * (int)sizeof(T);
     // 16 * odd bytes per record: a quarter warp of 128-bit stores then covers all 32 banks.
     static constexpr int REC_BYTES = ((RAW_BYTES / 16) % 2 == 0) ? RAW_BYTES + 16 : RAW_BYTES;
     static constexpr int WARP_BYTES = 32 * REC_BYTES;
 };
 
-constexpr int kSameFlag = 1 << 16;   // record idx.w: this sample has the same (plane, uc, vc) as the item's previous one
+constexpr int kSameFlag = 1;   // record idx.w: this sample has the same (plane, uc, vc) as the item's previous one
 
 #ifndef CNGI_TRACK_MINB128
 #define CNGI_TRACK_MINB128 4   // min resident blocks per SM asked of ptxas (caps registers/thread); tuned on B200
@@ -192,20 +195,33 @@ std_grid_track_kernel(StdParams p)
     using Cfg = TrackCfg<T, CPLX, S, PP>;
     using CT = typename Cplx<T>::type;
     using P2 = typename Pair<T>::type;
-    constexpr int IPW = Cfg::IPW, ITER = Cfg::ITER, SP = Cfg::SP, NV = Cfg::NV;
+    constexpr int W = Cfg::W, IPW = Cfg::IPW, ITER = Cfg::ITER, NV = Cfg::NV;
     constexpr int HALF = S / 2;
     const unsigned FULL = 0xffffffffu;
 
     extern __shared__ __align__(16) unsigned char smem[];
     T *table = reinterpret_cast<T *>(smem);
     const int table_bytes = (p.table_len * (int)sizeof(T) + 15) / 16 * 16;
-    double *scale = reinterpret_cast<double *>(smem + table_bytes);   // uv_scale[0][c], uv_scale[1][c]
+    double *scale = reinterpret_cast<double *>(smem + table_bytes);   // uv_scale[0][c], uv_scale[1][c] of the window
     const int scale_bytes = 2 * p.c_n * (int)sizeof(double);
+    // tapsum[off + os/2 + 1] = sum over the S taps of the stamp for oversampling offset `off`
+    double *tapsum = reinterpret_cast<double *>(smem + table_bytes + scale_bytes);
+    const int n_off = p.oversampling + 3;
+    const int tapsum_bytes = (n_off * (int)sizeof(double) + 15) / 16 * 16;
     for (int i = threadIdx.x; i < p.table_len; i += blockDim.x) table[i] = (T)p.cgk[i];
     for (int i = threadIdx.x; i < p.c_n; i += blockDim.x) {
         const double f = p.freq[p.c_lo + i];
         scale[i] = uv_scale_of(f, p.dl, p.n_u);
         scale[p.c_n + i] = uv_scale_of(f, p.dm, p.n_v);
+    }
+    for (int i = threadIdx.x; i < n_off; i += blockDim.x) {
+        const int off = i - p.oversampling / 2 - 1;
+        double sum = 0.0;
+        for (int q = 0; q < S; ++q) {
+            const int k = abs(p.oversampling * (q - HALF) + off);
+            if (k < p.table_len) sum += (double)(T)p.cgk[k];
+        }
+        tapsum[i] = sum;
     }
     __syncthreads();
 
@@ -213,7 +229,7 @@ std_grid_track_kernel(StdParams p)
     const int warp = threadIdx.x >> 5;
     const long long task = (long long)blockIdx.x * (BLK / 32) + warp;
     if (task >= p.n_tasks) return;   // no block-wide barrier after this point
-    unsigned char *wbuf = smem + table_bytes + scale_bytes + warp * Cfg::WARP_BYTES;
+    unsigned char *wbuf = smem + table_bytes + scale_bytes + tapsum_bytes + warp * Cfg::WARP_BYTES;
 
     // ---- task decode: (time segment, baseline, pol group, channel span), channel span fastest ------
     const int cspan = (int)(task % p.n_cspan);
@@ -251,26 +267,27 @@ std_grid_track_kernel(StdParams p)
     for (int ip = 0; ip < PP; ++ip) sw_acc[ip] = 0.0;
     long long carry_key = -1;   // key of the item's last sample of the previous round (lanes < IPW use it)
 
-    // ---- phase-2 role: lane <-> (item, u residue) --------------------------------------------------
-    const bool active2 = lane < IPW * S;
-    const int k2 = lane / S;
-    const int r2 = lane - k2 * S;
+    // ---- phase-2 role: lane <-> (item, u residue mod W) ----------------------------------------------
+    const int k2 = lane / W;
+    const int r2 = lane & (W - 1);
     int apol[PP];
 #pragma unroll
     for (int ip = 0; ip < PP; ++ip) apol[ip] = (ip < npol) ? pol_of(p, p0 + ip) : 0;
-    P2 acc[S][NV];
+    P2 acc[W][NV];
 #pragma unroll
-    for (int j = 0; j < S; ++j)
+    for (int j = 0; j < W; ++j)
 #pragma unroll
         for (int n = 0; n < NV; ++n) acc[j][n].x = acc[j][n].y = (T)0;
-    int cur_plane = -1, cur_u = -1, cur_vc = 0, cur_vcm = 0;
+    // register window of the item: columns [lo_u, lo_u + W), rows [lo_v, lo_v + W) of plane cur_plane
+    int cur_plane = -1, lo_u = 0, lo_v = 0;
     long long plane_off[PP];   // element offset of plane (cur_plane, apol[ip]) in the grid
 #pragma unroll
     for (int ip = 0; ip < PP; ++ip) plane_off[ip] = 0;
 
-    // flush accumulator j (grid cell (cur_u, v) of the current plane) with native reductions, then clear it
-    auto flush_one = [&](int j, int v) {
-        const int cell = cur_u * p.n_v + v;
+    // flush accumulator j (grid cell (u, v) of the current plane) with native reductions.  Accumulators are cleared
+    // only inside the non-zero test: unconditional writes in this divergent path make ptxas keep copies of them.
+    auto flush_one = [&](int j, int u, int v) {
+        const int cell = u * p.n_v + v;
         if (CPLX) {
 #pragma unroll
             for (int ip = 0; ip < PP; ++ip) {
@@ -279,19 +296,25 @@ std_grid_track_kernel(StdParams p)
                     val.x = acc[j][ip].x;
                     val.y = acc[j][ip].y;
                     red_add((CT *)p.grid + plane_off[ip] + cell, val);
-                    acc[j][ip].x = acc[j][ip].y = (T)0;   // zero only when flushed (see the real-grid branch)
+                    acc[j][ip].x = acc[j][ip].y = (T)0;
                 }
             }
         } else {
 #pragma unroll
             for (int ip = 0; ip < PP; ++ip) {
                 T &v1 = (ip & 1) ? acc[j][ip / 2].y : acc[j][ip / 2].x;
-                if (ip < npol && v1 != (T)0) {   // zero only what was flushed: unconditional writes in this divergent
-                    red_add((T *)p.grid + plane_off[ip] + cell, v1);   // path make ptxas copy the accumulators
+                if (ip < npol && v1 != (T)0) {
+                    red_add((T *)p.grid + plane_off[ip] + cell, v1);
                     v1 = (T)0;
                 }
             }
         }
+    };
+    auto my_column = [&]() { return lo_u + ((r2 - lo_u) & (W - 1)); };   // the u in the window with u == r2 (mod W)
+    auto flush_column = [&]() {                                          // all W accumulators of this lane
+        const int u = my_column();
+#pragma unroll
+        for (int j = 0; j < W; ++j) flush_one(j, u, lo_v + ((j - lo_v) & (W - 1)));
     };
 
     // ---- raw sample registers (software prefetch: loads of round n+1 fly during phase 2 of round n) --
@@ -374,20 +397,36 @@ std_grid_track_kernel(StdParams p)
             for (int ip = 0; ip < PP; ++ip) {
                 wsel[ip] = 0.0;
                 if (ip < npol) {
-                    const double w = (double)raw_w[ip];
-                    double wre = w, wim = 0.0;
-                    if (!p.do_psf) {
-                        weighted_vis((double)raw_vis[ip].x, (double)raw_vis[ip].y, w, wre, wim);
-                        if (raw_flag & (1u << ip)) wre = nan("");
-                    }
-                    if (!masked(wre, wim)) {
-                        any = true;
-                        wsel[ip] = w;
-                        if (CPLX) {
-                            wd[2 * ip] = (T)wre;
-                            wd[2 * ip + 1] = (T)wim;
+                    const T w = raw_w[ip];
+                    T wre = w, wim = (T)0;
+                    bool use;
+                    if (p.do_psf) {
+                        use = !(isnan(w) || w == (T)0);
+                    } else {
+                        const T a = raw_vis[ip].x, bq = raw_vis[ip].y;
+                        const bool flagged = (raw_flag >> ip) & 1u;
+                        if (sizeof(T) == 4 && isfinite(a) && isfinite(bq) && isfinite(w)) {
+                            // all finite: vis*w is NaN-free and is zero exactly when w == 0 or vis == 0, so the
+                            // reference's mask (_standard_grid.py:340) can be evaluated without the fp64 products
+                            use = !flagged && !(w == (T)0 || (a == (T)0 && bq == (T)0));
+                            wre = a * w;
+                            wim = bq * w;
                         } else {
-                            wd[ip] = (T)wre;   // pair n holds (pol 2n, pol 2n+1)
+                            double dre, dim;
+                            weighted_vis((double)a, (double)bq, (double)w, dre, dim);
+                            use = !flagged && !masked(dre, dim);
+                            wre = (T)dre;
+                            wim = (T)dim;
+                        }
+                    }
+                    if (use) {
+                        any = true;
+                        wsel[ip] = (double)w;
+                        if (CPLX) {
+                            wd[2 * ip] = wre;
+                            wd[2 * ip + 1] = wim;
+                        } else {
+                            wd[ip] = wre;   // pair n holds (pol 2n, pol 2n+1)
                         }
                     }
                 }
@@ -395,25 +434,21 @@ std_grid_track_kernel(StdParams p)
             if (any) {
                 const int uoff = oversample_offset(cp.uc, cp.u_pos, p.oversampling);
                 const int voff = oversample_offset(cp.vc, cp.v_pos, p.oversampling);
-                const int ub = (cp.uc - HALF) % S;   // residue of the first stamp column / row
-                const int vb = (cp.vc - HALF) % S;
                 T *rcu = reinterpret_cast<T *>(rec + Cfg::OFF_CU);
                 T *rcv = reinterpret_cast<T *>(rec + Cfg::OFF_CV);
-                double su = 0.0, sv = 0.0;
+                // taps go to slot (cell mod W); the W - S slots outside the stamp get a zero tap
 #pragma unroll
-                for (int q = 0; q < S; ++q) {
-                    const T tu = table[abs(p.oversampling * (q - HALF) + uoff)];
-                    const T tv = table[abs(p.oversampling * (q - HALF) + voff)];
-                    int ju = ub + q;
-                    if (ju >= S) ju -= S;
-                    int jv = vb + q;
-                    if (jv >= S) jv -= S;
-                    rcu[ju] = tu;
-                    rcv[jv] = tv;
-                    su += (double)tu;
-                    sv += (double)tv;
+                for (int q = 0; q < W; ++q) {
+                    T tu = (T)0, tv = (T)0;
+                    if (q < S) {
+                        tu = table[abs(p.oversampling * (q - HALF) + uoff)];
+                        tv = table[abs(p.oversampling * (q - HALF) + voff)];
+                    }
+                    rcu[(cp.uc - HALF + q) & (W - 1)] = tu;
+                    rcv[(cp.vc - HALF + q) & (W - 1)] = tv;
                 }
-                const double norm = su * sv;   // == sum over the stamp of cu*cv
+                const int o0 = p.oversampling / 2 + 1;
+                const double norm = tapsum[uoff + o0] * tapsum[voff + o0];   // == sum over the stamp of cu*cv
 #pragma unroll
                 for (int ip = 0; ip < PP; ++ip) sw_acc[ip] += wsel[ip] * norm;
                 T *rwd = reinterpret_cast<T *>(rec + Cfg::OFF_WD);
@@ -426,9 +461,7 @@ std_grid_track_kernel(StdParams p)
                     for (int i = 0; i < Cfg::WD; i += 2)
                         *reinterpret_cast<double2 *>(rwd + i) = make_double2(wd[i], wd[i + 1]);
                 }
-                const int ucm = (ub == 0) ? S - 1 : ub - 1;   // (uc + HALF) mod S
-                const int vcm = (vb == 0) ? S - 1 : vb - 1;
-                idx = make_int4(cp.uc, cp.vc, a_chan1, ucm | (vcm << 8));
+                idx = make_int4(cp.uc, cp.vc, a_chan1, 0);
                 key = ((long long)a_chan1 * p.n_u + cp.uc) * p.n_v + cp.vc;
             }
         }
@@ -449,11 +482,11 @@ std_grid_track_kernel(StdParams p)
             // taps and data are fetched together with the cell ids (before the branches below), so an iteration
             // exposes one shared-memory latency instead of two
             const T cu = reinterpret_cast<const T *>(rec + Cfg::OFF_CU)[r2];
-            T cv[SP];
+            T cv[W];
             P2 wd[Cfg::WD / 2];
             if (sizeof(T) == 4) {
 #pragma unroll
-                for (int q = 0; q < SP; q += 4) {
+                for (int q = 0; q < W; q += 4) {
                     const float4 x = *reinterpret_cast<const float4 *>(rec + Cfg::OFF_CV + q * 4);
                     cv[q] = x.x, cv[q + 1] = x.y, cv[q + 2] = x.z, cv[q + 3] = x.w;
                 }
@@ -464,7 +497,7 @@ std_grid_track_kernel(StdParams p)
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < SP; q += 2) {
+                for (int q = 0; q < W; q += 2) {
                     const double2 x = *reinterpret_cast<const double2 *>(rec + Cfg::OFF_CV + q * 8);
                     cv[q] = x.x, cv[q + 1] = x.y;
                 }
@@ -475,45 +508,41 @@ std_grid_track_kernel(StdParams p)
                 }
             }
             if (idx.x < 0) continue;
-            if (!(idx.w & kSameFlag)) {   // the stamp moved (or first sample): which accumulators leave?
-                int tu = (idx.w & 0xff) - r2;
-                if (tu < 0) tu += S;
-                const int my_u = idx.x + HALF - tu;
-                const int vc = idx.y, vcm = (idx.w >> 8) & 0xff;
-                if (my_u != cur_u || idx.z != cur_plane) {   // my column changed: all S accumulators go
-                    if (cur_u >= 0) {
+            if (!(idx.w & kSameFlag)) {   // the stamp moved (or first sample): does it still fit the register window?
+                const int need_u = idx.x - HALF, need_v = idx.y - HALF;   // lowest column / row the stamp touches
+                if (idx.z != cur_plane) {
+                    if (cur_plane >= 0) flush_column();
 #pragma unroll
-                        for (int j = 0; j < S; ++j) {
-                            int tv = cur_vcm - j;
-                            if (tv < 0) tv += S;
-                            flush_one(j, cur_vc + HALF - tv);
+                    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)idx.z * p.n_ip + apol[ip]) * plane_cells;
+                    cur_plane = idx.z, lo_u = need_u, lo_v = need_v;
+                } else {
+                    // slide the window by the least amount that makes the stamp fit (hysteresis of W - S cells)
+                    int new_u = lo_u, new_v = lo_v;
+                    if (need_u < lo_u) new_u = need_u;
+                    else if (need_u + S > lo_u + W) new_u = need_u + S - W;
+                    if (need_v < lo_v) new_v = need_v;
+                    else if (need_v + S > lo_v + W) new_v = need_v + S - W;
+                    if (new_u != lo_u) {   // my column leaves iff it is outside the new column range
+                        const int u = my_column();
+                        if (u < new_u || u >= new_u + W) flush_column();
+                        lo_u = new_u;
+                    }
+                    if (new_v != lo_v) {   // rows outside the new row range leave (cleared already if the column went)
+                        const int u = my_column();
+#pragma unroll
+                        for (int j = 0; j < W; ++j) {
+                            const int v = lo_v + ((j - lo_v) & (W - 1));
+                            if (v < new_v || v >= new_v + W) flush_one(j, u, v);
                         }
+                        lo_v = new_v;
                     }
-                    if (idx.z != cur_plane) {
-#pragma unroll
-                        for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)idx.z * p.n_ip + apol[ip]) * plane_cells;
-                    }
-                    cur_u = my_u, cur_plane = idx.z, cur_vc = vc, cur_vcm = vcm;
-                } else if (vc != cur_vc) {   // the window slid by d rows: the rows that dropped out go
-                    const int d = vc - cur_vc;
-                    // tv = distance of accumulator j's row from the top of the old window; rows with tv < a (d < 0)
-                    // or tv >= bnd (d > 0) left the window
-                    const int a = d < 0 ? min(-d, S) : 0;
-                    const int bnd = d > 0 ? max(S - d, 0) : S;
-#pragma unroll
-                    for (int j = 0; j < S; ++j) {
-                        int tv = cur_vcm - j;
-                        if (tv < 0) tv += S;
-                        if (tv < a || tv >= bnd) flush_one(j, cur_vc + HALF - tv);
-                    }
-                    cur_vc = vc, cur_vcm = vcm;
                 }
             }
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
                 const P2 t = pk_mul(wd[n], cu);
 #pragma unroll
-                for (int j = 0; j < S; ++j) pk_fma_acc(acc[j][n], t, cv[j]);
+                for (int j = 0; j < W; ++j) pk_fma_acc(acc[j][n], t, cv[j]);
             }
         }
     };
@@ -524,17 +553,10 @@ std_grid_track_kernel(StdParams p)
         stage();
         __syncwarp();
         if (t0 + spr < t_hi) load_raw(t0 + spr);
-        if (active2) consume();
+        consume();
         __syncwarp();
     }
-    if (active2 && cur_u >= 0) {
-#pragma unroll
-        for (int j = 0; j < S; ++j) {
-            int tv = cur_vcm - j;
-            if (tv < 0) tv += S;
-            flush_one(j, cur_vc + HALF - tv);
-        }
-    }
+    if (cur_plane >= 0) flush_column();
 
     // ---- sum_weight: lanes that share a channel reduce first, then one reduction per image plane -------
     const int span = IPW * G;   // lanes L and L + span handle the same channel
@@ -670,6 +692,7 @@ static int launch_track(StdParams p, const cngi_std_grid_args *a, cudaStream_t s
         const long long blocks = ceil_div(p.n_tasks, wpb);
         CNGI_REQUIRE(blocks < (1LL << 31), "standard_grid: too many work items for one launch");
         const size_t smem = (size_t)((p.table_len * (int)sizeof(T) + 15) / 16 * 16) + (size_t)2 * p.c_n * sizeof(double) +
+                            (size_t)(((p.oversampling + 3) * (int)sizeof(double) + 15) / 16 * 16) +
                             (size_t)wpb * Cfg::WARP_BYTES;
         CNGI_REQUIRE(smem <= 227 * 1024, "standard_grid: CF table too large for shared memory (%zu bytes)", smem);
         int rc = blk == 128 ? launch_track_blk<T, CPLX, S, PP, 128>(p, blocks, smem, st)
