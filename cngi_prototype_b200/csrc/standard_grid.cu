@@ -176,14 +176,7 @@ template <typename T, bool CPLX, int S, int PP> struct TrackCfg {
     static constexpr int RAW_BYTES = OFF_CU + W * (int)sizeof(T);
     // 16 * odd bytes per record: a quarter warp of 128-bit stores then covers all 32 banks.
     static constexpr int REC_BYTES = ((RAW_BYTES / 16) % 2 == 0) ? RAW_BYTES + 16 : RAW_BYTES;
-    // Flush queue: a lane whose whole column leaves the window parks its W accumulators here ({grid element offset,
-    // pair value}) instead of issuing W*PP reductions alone while 31 lanes idle; the warp drains the queue with all
-    // lanes at the end of the round.
-    static constexpr int QENT_BYTES = sizeof(T) == 4 ? 16 : 32;
-    static constexpr int QCAP = 6 * W * PP;                                       // six column flushes per round
-    static constexpr int OFF_QUEUE = 32 * REC_BYTES;
-    static constexpr int OFF_QCOUNT = OFF_QUEUE + QCAP * QENT_BYTES;
-    static constexpr int WARP_BYTES = OFF_QCOUNT + 16;
+    static constexpr int WARP_BYTES = 32 * REC_BYTES;
 };
 
 constexpr int kSameFlag = 1;   // record idx.w: this sample has the same (plane, uc, vc) as the item's previous one
@@ -291,12 +284,6 @@ std_grid_track_kernel(StdParams p)
 #pragma unroll
     for (int ip = 0; ip < PP; ++ip) plane_off[ip] = 0;
 
-    bool fresh = false;        // my column was parked in the flush queue: the next sample overwrites the accumulators
-    int *qcount = reinterpret_cast<int *>(wbuf + Cfg::OFF_QCOUNT);
-    unsigned char *queue = wbuf + Cfg::OFF_QUEUE;
-    if (lane == 0) *qcount = 0;
-    __syncwarp();
-
     // flush accumulator j (grid cell (u, v) of the current plane) with native reductions.  Accumulators are cleared
     // only inside the non-zero test: unconditional writes in this divergent path make ptxas keep copies of them.
     auto flush_one = [&](int j, int u, int v) {
@@ -328,85 +315,6 @@ std_grid_track_kernel(StdParams p)
         const int u = my_column();
 #pragma unroll
         for (int j = 0; j < W; ++j) flush_one(j, u, lo_v + ((j - lo_v) & (W - 1)));
-    };
-
-    // Column leaves the window in the middle of a round (divergent path, usually ONE lane of the warp): park the
-    // accumulators in the queue -- no zero tests, no clearing (the next sample overwrites them, see `fresh`).
-    auto park_column = [&]() {
-        const int slot = atomicAdd(qcount, W * PP);   // shared-memory integer atomic (native ATOMS.ADD)
-        if (slot + W * PP > Cfg::QCAP) {              // queue full: reduce directly
-            for (int e = slot; e < Cfg::QCAP; ++e)    // the part of the reservation inside the queue stays empty
-                *reinterpret_cast<long long *>(queue + e * Cfg::QENT_BYTES) = -1;
-            flush_column();
-            return;
-        }
-        const int u = my_column();
-        unsigned char *q = queue + slot * Cfg::QENT_BYTES;
-#pragma unroll
-        for (int ip = 0; ip < PP; ++ip) {
-            const long long base = plane_off[ip] + (long long)u * p.n_v;
-#pragma unroll
-            for (int j = 0; j < W; ++j) {
-                const long long off = (ip < npol) ? base + lo_v + ((j - lo_v) & (W - 1)) : -1;
-                unsigned char *e = q + (ip * W + j) * Cfg::QENT_BYTES;
-                if (CPLX) {
-                    if (sizeof(T) == 4) {
-                        *reinterpret_cast<int4 *>(e) = make_int4((int)(off & 0xffffffffll), (int)(off >> 32),
-                                                                 __float_as_int((float)acc[j][ip].x), __float_as_int((float)acc[j][ip].y));
-                    } else {
-                        *reinterpret_cast<long long *>(e) = off;
-                        *reinterpret_cast<double2 *>(e + 16) = make_double2((double)acc[j][ip].x, (double)acc[j][ip].y);
-                    }
-                } else {
-                    const T v1 = (ip & 1) ? acc[j][ip / 2].y : acc[j][ip / 2].x;
-                    if (sizeof(T) == 4) {
-                        *reinterpret_cast<int4 *>(e) = make_int4((int)(off & 0xffffffffll), (int)(off >> 32), __float_as_int((float)v1), 0);
-                    } else {
-                        *reinterpret_cast<long long *>(e) = off;
-                        *reinterpret_cast<double2 *>(e + 16) = make_double2((double)v1, 0.0);
-                    }
-                }
-            }
-        }
-        fresh = true;
-    };
-    // all 32 lanes, converged: one queue entry per lane per pass
-    auto drain = [&]() {
-        __syncwarp();
-        const int n = min(*qcount, Cfg::QCAP);
-        for (int e0 = 0; e0 < n; e0 += 32) {
-            const int ei = e0 + lane;
-            if (ei < n) {
-                const unsigned char *e = queue + ei * Cfg::QENT_BYTES;
-                long long off;
-                T re, im;
-                if (sizeof(T) == 4) {
-                    const int4 x = *reinterpret_cast<const int4 *>(e);
-                    off = ((long long)x.y << 32) | (long long)(unsigned)x.x;
-                    re = (T)__int_as_float(x.z);
-                    im = (T)__int_as_float(x.w);
-                } else {
-                    off = *reinterpret_cast<const long long *>(e);
-                    const double2 x = *reinterpret_cast<const double2 *>(e + 16);
-                    re = (T)x.x;
-                    im = (T)x.y;
-                }
-                if (off >= 0) {
-                    if (CPLX) {
-                        if (re != (T)0 || im != (T)0) {
-                            CT val;
-                            val.x = re;
-                            val.y = im;
-                            red_add((CT *)p.grid + off, val);
-                        }
-                    } else if (re != (T)0) {
-                        red_add((T *)p.grid + off, re);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) *qcount = 0;
     };
 
     // ---- raw sample registers (software prefetch: loads of round n+1 fly during phase 2 of round n) --
@@ -616,37 +524,25 @@ std_grid_track_kernel(StdParams p)
                     else if (need_v + S > lo_v + W) new_v = need_v + S - W;
                     if (new_u != lo_u) {   // my column leaves iff it is outside the new column range
                         const int u = my_column();
-                        if (u < new_u || u >= new_u + W) park_column();
+                        if (u < new_u || u >= new_u + W) flush_column();
                         lo_u = new_u;
                     }
-                    if (new_v != lo_v) {   // rows outside the new row range leave (nothing to do if the column just went)
-                        if (!fresh) {
-                            const int u = my_column();
+                    if (new_v != lo_v) {   // rows outside the new row range leave (cleared already if the column went)
+                        const int u = my_column();
 #pragma unroll
-                            for (int j = 0; j < W; ++j) {
-                                const int v = lo_v + ((j - lo_v) & (W - 1));
-                                if (v < new_v || v >= new_v + W) flush_one(j, u, v);
-                            }
+                        for (int j = 0; j < W; ++j) {
+                            const int v = lo_v + ((j - lo_v) & (W - 1));
+                            if (v < new_v || v >= new_v + W) flush_one(j, u, v);
                         }
                         lo_v = new_v;
                     }
                 }
             }
-            if (fresh) {   // first sample of a column whose previous content was parked: overwrite
 #pragma unroll
-                for (int n = 0; n < NV; ++n) {
-                    const P2 t = pk_mul(wd[n], cu);
+            for (int n = 0; n < NV; ++n) {
+                const P2 t = pk_mul(wd[n], cu);
 #pragma unroll
-                    for (int j = 0; j < W; ++j) acc[j][n] = pk_mul(t, cv[j]);
-                }
-                fresh = false;
-            } else {
-#pragma unroll
-                for (int n = 0; n < NV; ++n) {
-                    const P2 t = pk_mul(wd[n], cu);
-#pragma unroll
-                    for (int j = 0; j < W; ++j) pk_fma_acc(acc[j][n], t, cv[j]);
-                }
+                for (int j = 0; j < W; ++j) pk_fma_acc(acc[j][n], t, cv[j]);
             }
         }
     };
@@ -658,7 +554,7 @@ std_grid_track_kernel(StdParams p)
         __syncwarp();
         if (t0 + spr < t_hi) load_raw(t0 + spr);
         consume();
-        drain();
+        __syncwarp();
     }
     if (cur_plane >= 0) flush_column();
 
