@@ -176,24 +176,8 @@ template <typename T, bool CPLX, int S, int PP> struct TrackCfg {
     static constexpr int RAW_BYTES = OFF_CU + W * (int)sizeof(T);
     // 16 * odd bytes per record: a quarter warp of 128-bit stores then covers all 32 banks.
     static constexpr int REC_BYTES = ((RAW_BYTES / 16) % 2 == 0) ? RAW_BYTES + 16 : RAW_BYTES;
-    static constexpr int OFF_SW = 32 * REC_BYTES;               // per-lane sum_weight partials (PP doubles) + carry key
-    // raw sample slots filled by cp.async one round ahead: uvw (16 B) | vis (PP complex) | weight (PP real, padded to 16 B)
-    static constexpr int RAW_VIS = 16;
-    static constexpr int RAW_W = RAW_VIS + PP * 2 * (int)sizeof(T);
-    static constexpr int RAW_SLOT = (RAW_W + PP * (int)sizeof(T) + 15) / 16 * 16;
-    static constexpr int OFF_RAW = OFF_SW + 32 * (PP + 1) * 8;
-    static constexpr int WARP_BYTES = OFF_RAW + 32 * RAW_SLOT;
+    static constexpr int WARP_BYTES = 32 * REC_BYTES;
 };
-
-// cp.async (LDGSTS): global -> shared without staging registers; the data of round n+1 lands while round n is consumed
-template <int BYTES> __device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 
 constexpr int kSameFlag = 1;   // record idx.w: this sample has the same (plane, uc, vc) as the item's previous one
 
@@ -278,11 +262,10 @@ std_grid_track_kernel(StdParams p)
     bool chan_ok = c_fwd < c_end;
     const bool any_chan_ok = zigzag ? (c_fwd < c_end || c_bwd < c_end) : chan_ok;
     const int a_chan1 = chan_ok ? chan_of(p, c_fwd) : 0;   // zigzag only runs in continuum mode: plane 0 either way
-    double *sw_acc = reinterpret_cast<double *>(wbuf + Cfg::OFF_SW) + lane * (PP + 1);   // [PP] partial sums, then the carry key
+    double sw_acc[PP];
 #pragma unroll
     for (int ip = 0; ip < PP; ++ip) sw_acc[ip] = 0.0;
-    long long *carry_key_p = reinterpret_cast<long long *>(sw_acc + PP);   // key of the item's last sample of the previous round
-    *carry_key_p = -1;
+    long long carry_key = -1;   // key of the item's last sample of the previous round (lanes < IPW use it)
 
     // ---- phase-2 role: lane <-> (item, u residue mod W) ----------------------------------------------
     const int k2 = lane / W;
@@ -334,12 +317,12 @@ std_grid_track_kernel(StdParams p)
         for (int j = 0; j < W; ++j) flush_one(j, u, lo_v + ((j - lo_v) & (W - 1)));
     };
 
-    // ---- raw sample slots (asynchronous prefetch: the copies of round n+1 fly during phase 2 of round n) ----------
-    unsigned char *raw = wbuf + Cfg::OFF_RAW + lane * Cfg::RAW_SLOT;
+    // ---- raw sample registers (software prefetch: loads of round n+1 fly during phase 2 of round n) --
+    double raw_u = 0.0, raw_v = 0.0;
+    CT raw_vis[PP];
+    T raw_w[PP];
     unsigned raw_flag = 0;
     bool raw_ok = false;
-    // vector copies need the pol pair of a sample to be 16-byte (vis) / 8-byte (weight) aligned: even n_pol
-    const bool pair_copy = (PP == 2) && (npol == 2) && ((p.n_pol & 1) == 0);
     auto load_raw = [&](int t0) {
         const int t = t0 + row1;
         if (zigzag) {
@@ -350,17 +333,30 @@ std_grid_track_kernel(StdParams p)
         raw_flag = 0;
         if (raw_ok) {
             const long long tb = (long long)t * p.n_baseline + b;
-            cp_async<8>(raw, p.uvw + tb * 3);   // u, v (uvw rows are 24 bytes, so only 8-byte aligned)
-            cp_async<8>(raw + 8, p.uvw + tb * 3 + 1);
+            raw_u = p.uvw[tb * 3];
+            raw_v = p.uvw[tb * 3 + 1];
             const long long s = (tb * p.n_chan + c1) * p.n_pol + p0;
-            if (pair_copy) {
-                cp_async<2 * (int)sizeof(T)>(raw + Cfg::RAW_W, (const T *)p.weight + s);
+            if (PP == 2 && npol == 2 && (p.n_pol & 1) == 0) {   // 2 pols, aligned: one vector load each
+                const T *wp = (const T *)p.weight + s;
+                if (sizeof(T) == 4) {
+                    const float2 w2 = *reinterpret_cast<const float2 *>(wp);
+                    raw_w[0] = (T)w2.x;
+                    raw_w[PP - 1] = (T)w2.y;
+                } else {
+                    const double2 w2 = *reinterpret_cast<const double2 *>(wp);
+                    raw_w[0] = (T)w2.x;
+                    raw_w[PP - 1] = (T)w2.y;
+                }
                 if (!p.do_psf) {
                     if (sizeof(T) == 4) {
-                        cp_async<16>(raw + Cfg::RAW_VIS, (const CT *)p.vis + s);
+                        const float4 d = *reinterpret_cast<const float4 *>((const CT *)p.vis + s);
+                        raw_vis[0].x = (T)d.x;
+                        raw_vis[0].y = (T)d.y;
+                        raw_vis[PP - 1].x = (T)d.z;
+                        raw_vis[PP - 1].y = (T)d.w;
                     } else {
-                        cp_async<16>(raw + Cfg::RAW_VIS, (const CT *)p.vis + s);
-                        cp_async<16>(raw + Cfg::RAW_VIS + 16, (const CT *)p.vis + s + 1);
+                        raw_vis[0] = ((const CT *)p.vis)[s];
+                        raw_vis[PP - 1] = ((const CT *)p.vis)[s + 1];
                     }
                     if (p.flag) {
                         const uchar2 f2 = *reinterpret_cast<const uchar2 *>(p.flag + s);
@@ -371,18 +367,15 @@ std_grid_track_kernel(StdParams p)
 #pragma unroll
                 for (int ip = 0; ip < PP; ++ip) {
                     if (ip < npol) {
-                        cp_async<(int)sizeof(T)>(raw + Cfg::RAW_W + ip * (int)sizeof(T), (const T *)p.weight + s + ip);
+                        raw_w[ip] = ((const T *)p.weight)[s + ip];
                         if (!p.do_psf) {
-                            cp_async<8>(raw + Cfg::RAW_VIS + ip * 2 * (int)sizeof(T), (const CT *)p.vis + s + ip);
-                            if (sizeof(T) == 8)
-                                cp_async<8>(raw + Cfg::RAW_VIS + ip * 16 + 8, reinterpret_cast<const double *>((const CT *)p.vis + s + ip) + 1);
+                            raw_vis[ip] = ((const CT *)p.vis)[s + ip];
                             if (p.flag && p.flag[s + ip]) raw_flag |= 1u << ip;
                         }
                     }
                 }
             }
         }
-        cp_async_commit();
     };
 
     // ---- phase 1: locate, mask, look up taps, stage ------------------------------------------------
@@ -392,10 +385,7 @@ std_grid_track_kernel(StdParams p)
         long long key = -1;
         CellPos cp;
         bool ok = raw_ok;
-        if (ok) {
-            const double2 uv = *reinterpret_cast<const double2 *>(raw);
-            ok = locate_centre(uv.x, uv.y, scale[c1 - p.c_lo], scale[p.c_n + c1 - p.c_lo], p.n_u, p.n_v, cp);
-        }
+        if (ok) ok = locate_centre(raw_u, raw_v, scale[c1 - p.c_lo], scale[p.c_n + c1 - p.c_lo], p.n_u, p.n_v, cp);
         if (ok) ok = stamp_inside(cp.uc, cp.vc, HALF, p.n_u, p.n_v);
         if (ok) {
             T wd[Cfg::WD];
@@ -407,14 +397,13 @@ std_grid_track_kernel(StdParams p)
             for (int ip = 0; ip < PP; ++ip) {
                 wsel[ip] = 0.0;
                 if (ip < npol) {
-                    const T w = reinterpret_cast<const T *>(raw + Cfg::RAW_W)[ip];
+                    const T w = raw_w[ip];
                     T wre = w, wim = (T)0;
                     bool use;
                     if (p.do_psf) {
                         use = !(isnan(w) || w == (T)0);
                     } else {
-                        const CT vz = reinterpret_cast<const CT *>(raw + Cfg::RAW_VIS)[ip];
-                        const T a = vz.x, bq = vz.y;
+                        const T a = raw_vis[ip].x, bq = raw_vis[ip].y;
                         const bool flagged = (raw_flag >> ip) & 1u;
                         if (sizeof(T) == 4 && isfinite(a) && isfinite(bq) && isfinite(w)) {
                             // all finite: vis*w is NaN-free and is zero exactly when w == 0 or vis == 0, so the
@@ -478,8 +467,8 @@ std_grid_track_kernel(StdParams p)
         }
         // the item's previous sample is IPW slots back (or the last slot of the previous round)
         long long prev = __shfl_up_sync(FULL, key, IPW);
-        if (lane < IPW) prev = *carry_key_p;
-        *carry_key_p = __shfl_sync(FULL, key, 32 - IPW + k1);
+        if (lane < IPW) prev = carry_key;
+        carry_key = __shfl_sync(FULL, key, 32 - IPW + k1);
         if (key >= 0 && key == prev) idx.w |= kSameFlag;
         *reinterpret_cast<int4 *>(rec + Cfg::OFF_IDX) = idx;
     };
@@ -561,7 +550,6 @@ std_grid_track_kernel(StdParams p)
     // ---- main loop over rounds ---------------------------------------------------------------------
     load_raw(t_lo);
     for (int t0 = t_lo; t0 < t_hi; t0 += spr) {
-        cp_async_wait_all();   // this lane's own copies: a lane only ever reads the slot it filled
         stage();
         __syncwarp();
         if (t0 + spr < t_hi) load_raw(t0 + spr);
