@@ -381,7 +381,7 @@ std_grid_track_kernel(StdParams p)
     // ---- phase 1: locate, mask, look up taps, stage ------------------------------------------------
     auto stage = [&]() {
         unsigned char *rec = wbuf + lane * Cfg::REC_BYTES;
-        int4 idx = make_int4(-1, 0, 0, 0);
+        int2 idx = make_int2(-1, 0);   // {uc | vc << 16, plane << 8 | flags}; -1 = no sample
         long long key = -1;
         CellPos cp;
         bool ok = raw_ok;
@@ -434,18 +434,31 @@ std_grid_track_kernel(StdParams p)
             if (any) {
                 const int uoff = oversample_offset(cp.uc, cp.u_pos, p.oversampling);
                 const int voff = oversample_offset(cp.vc, cp.v_pos, p.oversampling);
-                T *rcu = reinterpret_cast<T *>(rec + Cfg::OFF_CU);
-                T *rcv = reinterpret_cast<T *>(rec + Cfg::OFF_CV);
-                // taps go to slot (cell mod W); the W - S slots outside the stamp get a zero tap
+                // Taps are produced directly in slot order (slot = cell mod W), so they leave as 128-bit stores; slots
+                // outside the stamp (the W - S spare columns / rows) get a zero tap.  A scatter of scalar stores here
+                // cost 4-way bank conflicts (lanes L, L+8, L+16, L+24 share banks at this record stride).
+                const int bu = (cp.uc - HALF) & (W - 1), bv = (cp.vc - HALF) & (W - 1);
+                T tu[W], tv[W];
 #pragma unroll
-                for (int q = 0; q < W; ++q) {
-                    T tu = (T)0, tv = (T)0;
-                    if (q < S) {
-                        tu = table[abs(p.oversampling * (q - HALF) + uoff)];
-                        tv = table[abs(p.oversampling * (q - HALF) + voff)];
+                for (int sl = 0; sl < W; ++sl) {
+                    const int qu = (sl - bu) & (W - 1), qv = (sl - bv) & (W - 1);   // position of this slot in the stamp
+                    const T au = table[min(abs(p.oversampling * (qu - HALF) + uoff), p.table_len - 1)];
+                    const T av = table[min(abs(p.oversampling * (qv - HALF) + voff), p.table_len - 1)];
+                    tu[sl] = qu < S ? au : (T)0;
+                    tv[sl] = qv < S ? av : (T)0;
+                }
+                if (sizeof(T) == 4) {
+#pragma unroll
+                    for (int q = 0; q < W; q += 4) {
+                        *reinterpret_cast<float4 *>(rec + Cfg::OFF_CU + q * 4) = make_float4(tu[q], tu[q + 1], tu[q + 2], tu[q + 3]);
+                        *reinterpret_cast<float4 *>(rec + Cfg::OFF_CV + q * 4) = make_float4(tv[q], tv[q + 1], tv[q + 2], tv[q + 3]);
                     }
-                    rcu[(cp.uc - HALF + q) & (W - 1)] = tu;
-                    rcv[(cp.vc - HALF + q) & (W - 1)] = tv;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < W; q += 2) {
+                        *reinterpret_cast<double2 *>(rec + Cfg::OFF_CU + q * 8) = make_double2(tu[q], tu[q + 1]);
+                        *reinterpret_cast<double2 *>(rec + Cfg::OFF_CV + q * 8) = make_double2(tv[q], tv[q + 1]);
+                    }
                 }
                 const int o0 = p.oversampling / 2 + 1;
                 const double norm = tapsum[uoff + o0] * tapsum[voff + o0];   // == sum over the stamp of cu*cv
@@ -461,7 +474,7 @@ std_grid_track_kernel(StdParams p)
                     for (int i = 0; i < Cfg::WD; i += 2)
                         *reinterpret_cast<double2 *>(rwd + i) = make_double2(wd[i], wd[i + 1]);
                 }
-                idx = make_int4(cp.uc, cp.vc, a_chan1, 0);
+                idx = make_int2(cp.uc | (cp.vc << 16), a_chan1 << 8);
                 key = ((long long)a_chan1 * p.n_u + cp.uc) * p.n_v + cp.vc;
             }
         }
@@ -469,8 +482,8 @@ std_grid_track_kernel(StdParams p)
         long long prev = __shfl_up_sync(FULL, key, IPW);
         if (lane < IPW) prev = carry_key;
         carry_key = __shfl_sync(FULL, key, 32 - IPW + k1);
-        if (key >= 0 && key == prev) idx.w |= kSameFlag;
-        *reinterpret_cast<int4 *>(rec + Cfg::OFF_IDX) = idx;
+        if (key >= 0 && key == prev) idx.y |= kSameFlag;
+        *reinterpret_cast<int2 *>(rec + Cfg::OFF_IDX) = idx;
     };
 
     // ---- phase 2: consume ----------------------------------------------------------------------------
@@ -478,7 +491,7 @@ std_grid_track_kernel(StdParams p)
 #pragma unroll 2
         for (int i = 0; i < ITER; ++i) {
             const unsigned char *rec = wbuf + (i * IPW + k2) * Cfg::REC_BYTES;
-            const int4 idx = *reinterpret_cast<const int4 *>(rec + Cfg::OFF_IDX);
+            const int2 idx = *reinterpret_cast<const int2 *>(rec + Cfg::OFF_IDX);
             // taps and data are fetched together with the cell ids (before the branches below), so an iteration
             // exposes one shared-memory latency instead of two
             const T cu = reinterpret_cast<const T *>(rec + Cfg::OFF_CU)[r2];
@@ -507,14 +520,15 @@ std_grid_track_kernel(StdParams p)
                     wd[q / 2].x = x.x, wd[q / 2].y = x.y;
                 }
             }
-            if (idx.x < 0) continue;
-            if (!(idx.w & kSameFlag)) {   // the stamp moved (or first sample): does it still fit the register window?
-                const int need_u = idx.x - HALF, need_v = idx.y - HALF;   // lowest column / row the stamp touches
-                if (idx.z != cur_plane) {
+            if (idx.x == -1) continue;
+            if (!(idx.y & kSameFlag)) {   // the stamp moved (or first sample): does it still fit the register window?
+                const int need_u = (idx.x & 0xffff) - HALF, need_v = (int)((unsigned)idx.x >> 16) - HALF;   // lowest column / row
+                const int plane = idx.y >> 8;
+                if (plane != cur_plane) {
                     if (cur_plane >= 0) flush_column();
 #pragma unroll
-                    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)idx.z * p.n_ip + apol[ip]) * plane_cells;
-                    cur_plane = idx.z, lo_u = need_u, lo_v = need_v;
+                    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)plane * p.n_ip + apol[ip]) * plane_cells;
+                    cur_plane = plane, lo_u = need_u, lo_v = need_v;
                 } else {
                     // slide the window by the least amount that makes the stamp fit (hysteresis of W - S cells)
                     int new_u = lo_u, new_v = lo_v;
@@ -715,11 +729,12 @@ template <typename T, bool CPLX> static int dispatch(StdParams p, const cngi_std
 #else
     int algo = a->algorithm;
     const bool track_ok = (a->support == 3 || a->support == 5 || a->support == 7 || a->support == 9) &&
-                          a->oversampling >= 1 && p.table_len <= 8192;
+                          a->oversampling >= 1 && p.table_len <= 8192 && a->n_u < 65536 && a->n_v < 65536 &&
+                          a->n_imag_chan < (1 << 23);   // staged records pack (uc, vc) into 16 bits each
     if (algo == CNGI_ALGO_AUTO) algo = track_ok ? CNGI_ALGO_TRACK : CNGI_ALGO_NAIVE;
     if (algo == CNGI_ALGO_TRACK) {
         if (!track_ok) {
-            set_error("standard_grid: track kernel supports support in {3,5,7,9} (got %d)", a->support);
+            set_error("standard_grid: track kernel needs support in {3,5,7,9} (got %d) and a grid side below 65536", a->support);
             return CNGI_ERR_UNSUPPORTED;
         }
         switch (a->support) {
