@@ -184,6 +184,9 @@ constexpr int kSameFlag = 1;   // record idx.w: this sample has the same (plane,
 #ifndef CNGI_TRACK_MINB128
 #define CNGI_TRACK_MINB128 4   // min resident blocks per SM asked of ptxas (caps registers/thread); tuned on B200
 #endif
+#ifndef CNGI_TRACK_UNROLL
+#define CNGI_TRACK_UNROLL 1   // consume-loop unroll; larger values overflow the instruction cache (stall_no_inst)
+#endif
 #ifndef CNGI_TRACK_MINB256
 #define CNGI_TRACK_MINB256 2
 #endif
@@ -488,7 +491,7 @@ std_grid_track_kernel(StdParams p)
 
     // ---- phase 2: consume ----------------------------------------------------------------------------
     auto consume = [&]() {
-#pragma unroll 2
+#pragma unroll CNGI_TRACK_UNROLL
         for (int i = 0; i < ITER; ++i) {
             const unsigned char *rec = wbuf + (i * IPW + k2) * Cfg::REC_BYTES;
             const int2 idx = *reinterpret_cast<const int2 *>(rec + Cfg::OFF_IDX);
@@ -524,33 +527,32 @@ std_grid_track_kernel(StdParams p)
             if (!(idx.y & kSameFlag)) {   // the stamp moved (or first sample): does it still fit the register window?
                 const int need_u = (idx.x & 0xffff) - HALF, need_v = (int)((unsigned)idx.x >> 16) - HALF;   // lowest column / row
                 const int plane = idx.y >> 8;
-                if (plane != cur_plane) {
-                    if (cur_plane >= 0) flush_column();
+                // slide the window by the least amount that makes the stamp fit (hysteresis of W - S cells); a new
+                // plane starts a new window.  One call site per flush loop keeps the code (instruction cache) small.
+                const bool new_plane = plane != cur_plane;
+                int new_u = lo_u, new_v = lo_v;
+                if (new_plane || need_u < lo_u) new_u = need_u;
+                else if (need_u + S > lo_u + W) new_u = need_u + S - W;
+                if (new_plane || need_v < lo_v) new_v = need_v;
+                else if (need_v + S > lo_v + W) new_v = need_v + S - W;
+                const int u = my_column();
+                // my column leaves iff it is outside the new column range (or the plane changes)
+                const bool col_leaves = new_plane ? (cur_plane >= 0) : (u < new_u || u >= new_u + W);
+                if (col_leaves) {
+                    flush_column();
+                } else if (new_v != lo_v) {   // rows outside the new row range leave
 #pragma unroll
-                    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)plane * p.n_ip + apol[ip]) * plane_cells;
-                    cur_plane = plane, lo_u = need_u, lo_v = need_v;
-                } else {
-                    // slide the window by the least amount that makes the stamp fit (hysteresis of W - S cells)
-                    int new_u = lo_u, new_v = lo_v;
-                    if (need_u < lo_u) new_u = need_u;
-                    else if (need_u + S > lo_u + W) new_u = need_u + S - W;
-                    if (need_v < lo_v) new_v = need_v;
-                    else if (need_v + S > lo_v + W) new_v = need_v + S - W;
-                    if (new_u != lo_u) {   // my column leaves iff it is outside the new column range
-                        const int u = my_column();
-                        if (u < new_u || u >= new_u + W) flush_column();
-                        lo_u = new_u;
-                    }
-                    if (new_v != lo_v) {   // rows outside the new row range leave (cleared already if the column went)
-                        const int u = my_column();
-#pragma unroll
-                        for (int j = 0; j < W; ++j) {
-                            const int v = lo_v + ((j - lo_v) & (W - 1));
-                            if (v < new_v || v >= new_v + W) flush_one(j, u, v);
-                        }
-                        lo_v = new_v;
+                    for (int j = 0; j < W; ++j) {
+                        const int v = lo_v + ((j - lo_v) & (W - 1));
+                        if (v < new_v || v >= new_v + W) flush_one(j, u, v);
                     }
                 }
+                if (new_plane) {
+#pragma unroll
+                    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)plane * p.n_ip + apol[ip]) * plane_cells;
+                    cur_plane = plane;
+                }
+                lo_u = new_u, lo_v = new_v;
             }
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
