@@ -187,6 +187,7 @@ constexpr int kSameFlag = 1;   // record idx.w: this sample has the same (plane,
 #ifndef CNGI_TRACK_UNROLL
 #define CNGI_TRACK_UNROLL 1   // consume-loop unroll; larger values overflow the instruction cache (stall_no_inst)
 #endif
+constexpr int kConsumeUnroll = CNGI_TRACK_UNROLL;
 #ifndef CNGI_TRACK_MINB256
 #define CNGI_TRACK_MINB256 2
 #endif
@@ -491,7 +492,7 @@ std_grid_track_kernel(StdParams p)
 
     // ---- phase 2: consume ----------------------------------------------------------------------------
     auto consume = [&]() {
-#pragma unroll CNGI_TRACK_UNROLL
+#pragma unroll(kConsumeUnroll)
         for (int i = 0; i < ITER; ++i) {
             const unsigned char *rec = wbuf + (i * IPW + k2) * Cfg::REC_BYTES;
             const int2 idx = *reinterpret_cast<const int2 *>(rec + Cfg::OFF_IDX);
