@@ -193,7 +193,7 @@ constexpr int kConsumeUnroll = CNGI_TRACK_UNROLL;
 #endif
 
 template <typename T, bool CPLX, int S, int PP, int BLK>
-__global__ void __launch_bounds__(BLK, (sizeof(T) == 4 ? (BLK == 128 ? CNGI_TRACK_MINB128 : CNGI_TRACK_MINB256) : 1))
+__global__ void __launch_bounds__(BLK, (sizeof(T) == 4 ? (BLK == 128 ? CNGI_TRACK_MINB128 : CNGI_TRACK_MINB256) : (BLK == 128 ? 3 : 1)))
 std_grid_track_kernel(StdParams p)
 {
     using Cfg = TrackCfg<T, CPLX, S, PP>;
