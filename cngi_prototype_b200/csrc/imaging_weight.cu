@@ -40,10 +40,13 @@ __device__ __forceinline__ int iw_chan_of(const IwParams &p, int c)
 // thread <-> (time segment, baseline, group of G consecutive channels); group index fastest, so a warp reads
 // 32*G consecutive channels of one row (coalesced).  The thread walks time (outer) and its G channels (inner,
 // boustrophedon so consecutive samples stay neighbours in the uv plane) and run-length accumulates while the
-// (plane, cell, conjugate cell) key is unchanged.  With G > 1 (channels sharing an image plane, i.e. continuum)
-// this removes most same-address reductions: neighbouring channels of a baseline fall into the same cell.
-template <typename T, int G> __global__ void __launch_bounds__(256) iw_grid_kernel(IwParams p)
+// (plane, cell, conjugate cell) key is unchanged.  G > 1 is only used when all channels share ONE image plane
+// (continuum): neighbouring channels of a baseline then fall into the same cell, which removes most same-address
+// reductions.  NP = compile-time pol count (1 / 2 with the identity pol_map), 0 = generic.
+template <typename T, int G, int NP> __global__ void __launch_bounds__(256) iw_grid_kernel(IwParams p)
 {
+    const int n_pol = NP ? NP : p.n_pol;
+    const long long plane_cells = (long long)p.n_u * p.n_v;
     const int n_cg = (p.n_chan + G - 1) / G;
     const long long n_items = (long long)p.n_seg * p.n_baseline * n_cg;
     long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,33 +59,31 @@ template <typename T, int G> __global__ void __launch_bounds__(256) iw_grid_kern
     const int t_lo = seg * p.seg_len, t_hi = in_range ? min(p.n_time, t_lo + p.seg_len) : t_lo;
     const int c0 = cg * G;
     const int ng = min(G, p.n_chan - c0);
-    double us[G], vs[G];
-    int a_chan[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const int c = min(c0 + g, p.n_chan - 1);
-        const double f = p.freq[c];
-        us[g] = uv_scale_of(f, p.dl, p.n_u);
-        vs[g] = uv_scale_of(f, p.dm, p.n_v);
-        a_chan[g] = iw_chan_of(p, c);
-    }
-    const bool average = p.n_pol >= 2;               // (n_pol >= 2) and do_imaging_weight, :328-330
+    const int plane = (G > 1) ? 0 : iw_chan_of(p, c0);   // G > 1 <=> continuum
+    double *const plane_base = p.density + (long long)plane * p.n_ip * plane_cells;
+    const bool average = n_pol >= 2;               // (n_pol >= 2) and do_imaging_weight, :328-330
     const double mid_u = (double)(p.n_u / 2), mid_v = (double)(p.n_v / 2);
+    const double *us = p.scale + c0, *vs = p.scale + p.n_chan + c0;   // uv_scale table (L1 resident)
 
-    int cur_plane = -1, cur_u = 0, cur_v = 0, cur_cu = 0, cur_cv = 0;
-    double acc = 0.0;
-    double sw[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) sw[g] = 0.0;
+    int cur_u = -1, cur_v = 0, cur_cu = 0, cur_cv = 0;
+    double acc = 0.0, sw = 0.0;
 
     auto flush = [&]() {
-        if (cur_plane < 0 || acc == 0.0) return;
+        if (cur_u < 0 || acc == 0.0) return;
         const bool conj_ok = cur_cu >= 0 && cur_cu < p.n_u && cur_cv >= 0 && cur_cv < p.n_v;
-        for (int ip = 0; ip < p.n_pol; ++ip) {
-            const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
-            double *plane = p.density + ((long long)cur_plane * p.n_ip + a_pol) * p.n_u * (long long)p.n_v;
-            atomicAdd(plane + (long long)cur_u * p.n_v + cur_v, acc);
-            if (conj_ok) atomicAdd(plane + (long long)cur_cu * p.n_v + cur_cv, acc);
+        const int cell = cur_u * p.n_v + cur_v, ccell = cur_cu * p.n_v + cur_cv;   // n_u * n_v < 2^31 (checked by the launcher)
+        if (NP) {
+#pragma unroll
+            for (int ip = 0; ip < (NP ? NP : 1); ++ip) {
+                atomicAdd(plane_base + ip * plane_cells + cell, acc);
+                if (conj_ok) atomicAdd(plane_base + ip * plane_cells + ccell, acc);
+            }
+        } else {
+            for (int ip = 0; ip < n_pol; ++ip) {
+                const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
+                atomicAdd(plane_base + a_pol * plane_cells + cell, acc);
+                if (conj_ok) atomicAdd(plane_base + a_pol * plane_cells + ccell, acc);
+            }
         }
         acc = 0.0;
     };
@@ -90,7 +91,7 @@ template <typename T, int G> __global__ void __launch_bounds__(256) iw_grid_kern
     for (int t = t_lo; t < t_hi; ++t) {
         const long long tb = (long long)t * p.n_baseline + b;
         const double uu = p.uvw[tb * 3], vv = p.uvw[tb * 3 + 1];
-        const T *wrow = (const T *)p.weight + (tb * p.n_chan + c0) * p.n_pol;
+        const T *wrow = (const T *)p.weight + (tb * p.n_chan + c0) * n_pol;
         double wd[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {   // issue all loads of the row before the dependent math
@@ -98,7 +99,7 @@ template <typename T, int G> __global__ void __launch_bounds__(256) iw_grid_kern
             if (g < ng) {
                 if (average) {
                     double w0, w1;
-                    if (p.n_pol == 2) {
+                    if (n_pol == 2) {
                         if (sizeof(T) == 4) {
                             const float2 w2 = *reinterpret_cast<const float2 *>(wrow + g * 2);
                             w0 = (double)w2.x, w1 = (double)w2.y;
@@ -107,51 +108,46 @@ template <typename T, int G> __global__ void __launch_bounds__(256) iw_grid_kern
                             w0 = w2.x, w1 = w2.y;
                         }
                     } else {
-                        w0 = (double)wrow[g * p.n_pol], w1 = (double)wrow[g * p.n_pol + 1];
+                        w0 = (double)wrow[g * n_pol], w1 = (double)wrow[g * n_pol + 1];
                     }
-                    wd[g] = __dmul_rn(__dadd_rn(w0, w1), 0.5)   /* == /2.0 exactly */;
+                    wd[g] = __dmul_rn(__dadd_rn(w0, w1), 0.5);   // == /2.0 exactly
                 } else {
                     wd[g] = (double)wrow[g];
                 }
             }
         }
-#pragma unroll
-        for (int gi = 0; gi < G; ++gi) {
-            const int g = (t & 1) ? G - 1 - gi : gi;
-            if (g >= ng) continue;
+        // g is a compile-time constant in both unrolled loops below (a run-time index would push wd[] to local memory)
+        auto sample = [&](int g, double w) {
+            if (g >= ng) return;
             CellPos cp;
-            if (!locate_centre(uu, vv, us[g], vs[g], p.n_u, p.n_v, cp)) continue;
-            if (!stamp_inside(cp.uc, cp.vc, 0, p.n_u, p.n_v)) continue;
-            const double w = wd[g];
-            if (isnan(w) || w == 0.0) continue;
+            const double su = us[g], sv = vs[g];
+            if (!locate_centre(uu, vv, su, sv, p.n_u, p.n_v, cp)) return;
+            if (!stamp_inside(cp.uc, cp.vc, 0, p.n_u, p.n_v)) return;
+            if (isnan(w) || w == 0.0) return;
             // conjugate cell: int(-u + centre + 0.5)   (:309-318)
-            const double un = -__dmul_rn(uu, us[g]), vn = -__dmul_rn(vv, vs[g]);
+            const double un = -__dmul_rn(uu, su), vn = -__dmul_rn(vv, sv);
             const int cu = __double2int_rz(__dadd_rn(__dadd_rn(un, mid_u), 0.5));
             const int cv = __double2int_rz(__dadd_rn(__dadd_rn(vn, mid_v), 0.5));
-            if (a_chan[g] != cur_plane || cp.uc != cur_u || cp.vc != cur_v || cu != cur_cu || cv != cur_cv) {
+            if (cp.uc != cur_u || cp.vc != cur_v || cu != cur_cu || cv != cur_cv) {
                 flush();
-                cur_plane = a_chan[g], cur_u = cp.uc, cur_v = cp.vc, cur_cu = cu, cur_cv = cv;
+                cur_u = cp.uc, cur_v = cp.vc, cur_cu = cu, cur_cv = cv;
             }
             acc += w;
-            sw[g] += w + w;   // sum_weight gets sel_weight*norm twice (:366-369), norm == cgk_1D[0] == 1
+            sw += w + w;   // sum_weight gets sel_weight*norm twice (:366-369), norm == cgk_1D[0] == 1
+        };
+        if (t & 1) {   // boustrophedon
+#pragma unroll
+            for (int gi = 0; gi < G; ++gi) sample(G - 1 - gi, wd[G - 1 - gi]);
+        } else {
+#pragma unroll
+            for (int gi = 0; gi < G; ++gi) sample(gi, wd[gi]);
         }
     }
     flush();
-    // sum_weight: fold channels of the same plane inside the thread, then one reduction per plane per warp
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        bool first = true;   // no earlier channel of this thread maps to the same plane
-#pragma unroll
-        for (int h = 0; h < G; ++h)
-            if (h < g && a_chan[h] == a_chan[g]) first = false;
-        double v = 0.0;
-#pragma unroll
-        for (int h = 0; h < G; ++h)
-            if (first && h >= g && h < ng && a_chan[h] == a_chan[g]) v += sw[h];
-        for (int ip = 0; ip < p.n_pol; ++ip) {   // n_pol is uniform, so the warp stays converged
-            const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
-            warp_grouped_add(p.sum_weight, a_chan[g] * p.n_ip + a_pol, v, in_range && g < ng && v != 0.0);
-        }
+    // sum_weight: one reduction per plane per warp (all of a thread's channels share its plane)
+    for (int ip = 0; ip < n_pol; ++ip) {   // n_pol is uniform, so the warp stays converged
+        const int a_pol = (!NP && p.pol_map) ? (int)p.pol_map[ip] : ip;
+        warp_grouped_add(p.sum_weight, plane * p.n_ip + a_pol, sw, in_range && sw != 0.0);
     }
 }
 
@@ -191,41 +187,86 @@ __global__ void iw_briggs_finalize_kernel(double *bf, const double *sum_weight, 
     }
 }
 
-template <typename T> __global__ void __launch_bounds__(256) iw_degrid_kernel(IwParams p)
+// block = (CX channels) x (256 / CX rows); thread <-> one (row, chan) sample, all pols.  No integer division, the uvw
+// row is a warp-wide broadcast load, weights and outputs are coalesced along the channel axis.
+template <typename T, int NP> __global__ void __launch_bounds__(256) iw_degrid_kernel(IwParams p)
 {
-    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % p.n_chan);
-    const long long tb = idx / p.n_chan;
-    T *out = (T *)p.out + idx * p.n_pol;
-    const T *nat = (const T *)p.weight + idx * p.n_pol;
+    const int n_pol = NP ? NP : p.n_pol;
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    const long long tb = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    if (c >= p.n_chan || tb >= (long long)p.n_time * p.n_baseline) return;
+    const long long idx = tb * p.n_chan + c;
+    T *out = (T *)p.out + idx * n_pol;
+    const T *nat = (const T *)p.weight + idx * n_pol;
+    T natv[NP ? NP : 1];
+    if (NP == 2) {   // one 8/16-byte load for the pol pair
+        if (sizeof(T) == 4) {
+            const float2 w2 = *reinterpret_cast<const float2 *>(nat);
+            natv[0] = (T)w2.x, natv[NP - 1] = (T)w2.y;
+        } else {
+            const double2 w2 = *reinterpret_cast<const double2 *>(nat);
+            natv[0] = (T)w2.x, natv[NP - 1] = (T)w2.y;
+        }
+    } else if (NP == 1) {
+        natv[0] = nat[0];
+    }
     CellPos cp;
     bool ok = locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], p.scale[c], p.scale[p.n_chan + c], p.n_u, p.n_v, cp);
     if (ok) ok = stamp_inside(cp.uc, cp.vc, 0, p.n_u, p.n_v);
+    T res[NP ? NP : 1];
     if (!ok) {   // off-grid or NaN uv: output stays 0 (:460,493,502)
-        for (int ip = 0; ip < p.n_pol; ++ip) out[ip] = (T)0;
-        return;
-    }
-    const int a_chan = iw_chan_of(p, c);
-    const double avg = p.n_pol == 2 ? __dmul_rn(__dadd_rn((double)nat[0], (double)nat[1]), 0.5)   /* == /2.0 exactly */ : 0.0;
-    for (int ip = 0; ip < p.n_pol; ++ip) {
-        const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
-        double iw = p.n_pol == 2 ? avg : (double)nat[ip];   // :508-511
-        const double w = (double)nat[ip];
-        if (!isnan(w) && w != 0.0) {
-            const double rho = p.density[cp.uc * p.ds_u + cp.vc * p.ds_v + a_chan * p.ds_c + a_pol * p.ds_p];
-            if (!isnan(rho) && rho != 0.0) {
-                const double f0 = p.bf[a_chan * p.n_ip + a_pol];
-                const double f1 = p.bf[((long long)p.n_ic + a_chan) * p.n_ip + a_pol];
-                const double den = __dadd_rn(__dmul_rn(f0, rho), f1);   // :515-516
-                if (sizeof(T) == 4)
-                    iw = (double)__fdiv_rn((float)iw, (float)den);   // result is stored as fp32 anyway
-                else
-                    iw = __ddiv_rn(iw, den);
-            }
+        if (NP) {
+#pragma unroll
+            for (int ip = 0; ip < (NP ? NP : 1); ++ip) res[ip] = (T)0;
+        } else {
+            for (int ip = 0; ip < n_pol; ++ip) out[ip] = (T)0;
+            return;
         }
-        out[ip] = (T)iw;
+    } else {
+        const int a_chan = iw_chan_of(p, c);
+        const long long cell = cp.uc * p.ds_u + cp.vc * p.ds_v + a_chan * p.ds_c;
+        if (NP) {
+            const double avg = NP == 2 ? __dmul_rn(__dadd_rn((double)natv[0], (double)natv[NP - 1]), 0.5) : 0.0;   // == /2.0
+#pragma unroll
+            for (int ip = 0; ip < (NP ? NP : 1); ++ip) {
+                double iw = NP == 2 ? avg : (double)natv[ip];   // :508-511
+                const double w = (double)natv[ip];
+                if (!isnan(w) && w != 0.0) {
+                    const double rho = p.density[cell + ip * p.ds_p];
+                    if (!isnan(rho) && rho != 0.0) {
+                        const double den = __dadd_rn(__dmul_rn(p.bf[a_chan * p.n_ip + ip], rho),
+                                                     p.bf[((long long)p.n_ic + a_chan) * p.n_ip + ip]);   // :515-516
+                        iw = sizeof(T) == 4 ? (double)__fdiv_rn((float)iw, (float)den) : __ddiv_rn(iw, den);
+                    }
+                }
+                res[ip] = (T)iw;
+            }
+        } else {
+            const double avg = n_pol == 2 ? __dmul_rn(__dadd_rn((double)nat[0], (double)nat[1]), 0.5) : 0.0;
+            for (int ip = 0; ip < n_pol; ++ip) {
+                const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
+                double iw = n_pol == 2 ? avg : (double)nat[ip];
+                const double w = (double)nat[ip];
+                if (!isnan(w) && w != 0.0) {
+                    const double rho = p.density[cell + a_pol * p.ds_p];
+                    if (!isnan(rho) && rho != 0.0) {
+                        const double den = __dadd_rn(__dmul_rn(p.bf[a_chan * p.n_ip + a_pol], rho),
+                                                     p.bf[((long long)p.n_ic + a_chan) * p.n_ip + a_pol]);
+                        iw = sizeof(T) == 4 ? (double)__fdiv_rn((float)iw, (float)den) : __ddiv_rn(iw, den);
+                    }
+                }
+                out[ip] = (T)iw;
+            }
+            return;
+        }
+    }
+    if (NP == 2) {
+        if (sizeof(T) == 4)
+            *reinterpret_cast<float2 *>(out) = make_float2((float)res[0], (float)res[NP - 1]);
+        else
+            *reinterpret_cast<double2 *>(out) = make_double2((double)res[0], (double)res[NP - 1]);
+    } else if (NP == 1) {
+        out[0] = res[0];
     }
 }
 
@@ -240,6 +281,7 @@ extern "C" int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *a, void *s
     CNGI_REQUIRE(a->n_u > 0 && a->n_v > 0 && a->n_u < (1 << 24) && a->n_v < (1 << 24), "imaging_weight_grid: bad grid size");
     CNGI_REQUIRE(a->chan_mode != CNGI_CHAN_GENERAL || a->chan_map, "imaging_weight_grid: chan_map is null");
     CNGI_REQUIRE(a->n_time * a->n_baseline < (1LL << 31), "imaging_weight_grid: too many rows");
+    CNGI_REQUIRE(a->n_u * a->n_v < (1LL << 31), "imaging_weight_grid: n_u*n_v overflows int32");
     if (a->n_time == 0 || a->n_baseline == 0 || a->n_chan == 0 || a->n_pol == 0) return CNGI_OK;
     IwParams p{};
     p.n_time = (int)a->n_time, p.n_baseline = (int)a->n_baseline, p.n_chan = (int)a->n_chan, p.n_pol = (int)a->n_pol;
@@ -249,7 +291,7 @@ extern "C" int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *a, void *s
     p.chan_mode = a->chan_mode;
     // channels per thread: only useful when neighbouring channels share a plane
     int G = 1;
-    if (p.chan_mode != CNGI_CHAN_CUBE)
+    if (p.chan_mode == CNGI_CHAN_CONTINUUM)
         while (G < 8 && G * 2 <= p.n_chan) G *= 2;
     const long long per_seg = (long long)p.n_baseline * ceil_div(p.n_chan, G);
     long long n_seg = ceil_div((long long)sm_count() * 2048 * 2, per_seg);   // ~2 waves of full occupancy
@@ -260,7 +302,20 @@ extern "C" int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *a, void *s
     const long long blocks = ceil_div(per_seg * p.n_seg, 256);
     CNGI_REQUIRE(blocks < (1LL << 31), "imaging_weight_grid: too many work items");
     cudaStream_t st = (cudaStream_t)stream;
-#define CNGI_IW_LAUNCH(TT, GG) iw_grid_kernel<TT, GG><<<(unsigned)blocks, 256, 0, st>>>(p)
+    double *scale = nullptr;
+    {
+        int rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
+        if (rc != CNGI_OK) return rc;
+        p.scale = scale;
+    }
+    // compile-time pol count when the pol_map is the identity (the reference's wrappers always pass arange)
+    const int np = (!a->pol_map && (p.n_pol == 1 || p.n_pol == 2)) ? p.n_pol : 0;
+#define CNGI_IW_LAUNCH(TT, GG)                                                      \
+    do {                                                                            \
+        if (np == 2) iw_grid_kernel<TT, GG, 2><<<(unsigned)blocks, 256, 0, st>>>(p); \
+        else if (np == 1) iw_grid_kernel<TT, GG, 1><<<(unsigned)blocks, 256, 0, st>>>(p); \
+        else iw_grid_kernel<TT, GG, 0><<<(unsigned)blocks, 256, 0, st>>>(p);          \
+    } while (0)
     if (a->precision == CNGI_F32) {
         switch (G) {
             case 1: CNGI_IW_LAUNCH(float, 1); break;
@@ -277,7 +332,9 @@ extern "C" int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *a, void *s
         }
     }
 #undef CNGI_IW_LAUNCH
-    CNGI_CUDA_TRY(cudaGetLastError());
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scale, st);
+    CNGI_CUDA_TRY(e);
     return CNGI_OK;
 }
 
@@ -322,17 +379,30 @@ extern "C" int cngi_b200_imaging_weight_degrid(const cngi_iw_degrid_args *a, voi
     p.density = const_cast<double *>(a->density), p.dl = a->delta_lm[0], p.dm = a->delta_lm[1], p.chan_mode = a->chan_mode;
     p.bf = a->briggs_factors, p.out = a->imaging_weight;
     p.ds_u = a->density_stride[0], p.ds_v = a->density_stride[1], p.ds_c = a->density_stride[2], p.ds_p = a->density_stride[3];
-    const long long blocks = ceil_div(total, 256);
-    CNGI_REQUIRE(blocks < (1LL << 31), "imaging_weight_degrid: too many samples");
+    int cx = 1;
+    while (cx < 128 && cx < p.n_chan) cx <<= 1;   // channels per block (power of two), 256 / cx rows per block
+    const dim3 block(cx, 256 / cx);
+    const long long rows = (long long)p.n_time * p.n_baseline;
+    const long long gx = ceil_div(rows, block.y), gy = ceil_div(p.n_chan, cx);
+    CNGI_REQUIRE(gx < (1LL << 31) && gy < 65536, "imaging_weight_degrid: too many samples");
+    const dim3 grid((unsigned)gx, (unsigned)gy);
+    const int np = (!a->pol_map && (p.n_pol == 1 || p.n_pol == 2)) ? p.n_pol : 0;
     cudaStream_t st = (cudaStream_t)stream;
     double *scale = nullptr;
     int rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
     if (rc != CNGI_OK) return rc;
     p.scale = scale;
+#define CNGI_DG_LAUNCH(TT)                                                      \
+    do {                                                                        \
+        if (np == 2) iw_degrid_kernel<TT, 2><<<grid, block, 0, st>>>(p);        \
+        else if (np == 1) iw_degrid_kernel<TT, 1><<<grid, block, 0, st>>>(p);   \
+        else iw_degrid_kernel<TT, 0><<<grid, block, 0, st>>>(p);                \
+    } while (0)
     if (a->precision == CNGI_F32)
-        iw_degrid_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(p);
+        CNGI_DG_LAUNCH(float);
     else
-        iw_degrid_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(p);
+        CNGI_DG_LAUNCH(double);
+#undef CNGI_DG_LAUNCH
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scale, st);
     CNGI_CUDA_TRY(e);

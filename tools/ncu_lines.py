@@ -6,7 +6,8 @@ import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
+kern = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep] + kern + ["--page", "source", "--print-source", "cuda,sass", "--csv"],
                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, fname, lines = None, "", []
