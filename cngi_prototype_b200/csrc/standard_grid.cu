@@ -49,6 +49,7 @@ struct StdParams {
     // track kernel decomposition
     int G, log2G, seg_len, n_seg, n_cspan, n_pgrp;
     int c_lo, c_n;         // channel window handled by this launch (bounds the shared-memory channel table)
+    int use_rot;           // 1: shared memory holds tap rows pre-rotated into slot order (see the kernel)
     long long n_tasks;
     const double *scale;   // naive kernel: [2, n_chan] uv_scale table
 };
@@ -204,15 +205,31 @@ std_grid_track_kernel(StdParams p)
     const unsigned FULL = 0xffffffffu;
 
     extern __shared__ __align__(16) unsigned char smem[];
+    // Tap table.  use_rot: rows of W taps already rotated into slot order, rot[b][off][slot] = tap of the stamp position
+    // q = (slot - b) mod W for oversampling offset `off` (zero for the W - S spare slots), so phase 1 fetches a sample's
+    // W u-taps (and W v-taps) with two 128-bit loads and no arithmetic.  Otherwise (table too large for shared memory):
+    // the plain half-kernel table cgk_1D, taps looked up one by one.
     T *table = reinterpret_cast<T *>(smem);
-    const int table_bytes = (p.table_len * (int)sizeof(T) + 15) / 16 * 16;
+    const int n_off = p.oversampling + 3;
+    const int table_elems = p.use_rot ? W * n_off * W : p.table_len;
+    const int table_bytes = (table_elems * (int)sizeof(T) + 15) / 16 * 16;
     double *scale = reinterpret_cast<double *>(smem + table_bytes);   // uv_scale[0][c], uv_scale[1][c] of the window
     const int scale_bytes = 2 * p.c_n * (int)sizeof(double);
     // tapsum[off + os/2 + 1] = sum over the S taps of the stamp for oversampling offset `off`
     double *tapsum = reinterpret_cast<double *>(smem + table_bytes + scale_bytes);
-    const int n_off = p.oversampling + 3;
     const int tapsum_bytes = (n_off * (int)sizeof(double) + 15) / 16 * 16;
-    for (int i = threadIdx.x; i < p.table_len; i += blockDim.x) table[i] = (T)p.cgk[i];
+    if (p.use_rot) {
+        for (int e = threadIdx.x; e < table_elems; e += blockDim.x) {
+            const int sl = e & (W - 1);
+            const int o = (e / W) % n_off;
+            const int bq = e / (W * n_off);
+            const int q = (sl - bq) & (W - 1);
+            const int k = min(abs(p.oversampling * (q - HALF) + o - p.oversampling / 2 - 1), p.table_len - 1);
+            table[e] = q < S ? (T)p.cgk[k] : (T)0;
+        }
+    } else {
+        for (int i = threadIdx.x; i < p.table_len; i += blockDim.x) table[i] = (T)p.cgk[i];
+    }
     for (int i = threadIdx.x; i < p.c_n; i += blockDim.x) {
         const double f = p.freq[p.c_lo + i];
         scale[i] = uv_scale_of(f, p.dl, p.n_u);
@@ -231,9 +248,10 @@ std_grid_track_kernel(StdParams p)
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const long long task = (long long)blockIdx.x * (BLK / 32) + warp;
-    if (task >= p.n_tasks) return;   // no block-wide barrier after this point
     unsigned char *wbuf = smem + table_bytes + scale_bytes + tapsum_bytes + warp * Cfg::WARP_BYTES;
+    // Persistent warps: the grid is sized to the machine and every warp strides over the work items, so the tables
+    // above are built once per resident block.  No block-wide barrier after this point.
+    for (long long task = (long long)blockIdx.x * (BLK / 32) + warp; task < p.n_tasks; task += (long long)gridDim.x * (BLK / 32)) {
 
     // ---- task decode: (time segment, baseline, pol group, channel span), channel span fastest ------
     const int cspan = (int)(task % p.n_cspan);
@@ -442,14 +460,34 @@ std_grid_track_kernel(StdParams p)
                 // outside the stamp (the W - S spare columns / rows) get a zero tap.  A scatter of scalar stores here
                 // cost 4-way bank conflicts (lanes L, L+8, L+16, L+24 share banks at this record stride).
                 const int bu = (cp.uc - HALF) & (W - 1), bv = (cp.vc - HALF) & (W - 1);
+                const int o0 = p.oversampling / 2 + 1;
                 T tu[W], tv[W];
+                if (p.use_rot) {
+                    const T *ru = table + ((bu * n_off) + uoff + o0) * W, *rv = table + ((bv * n_off) + voff + o0) * W;
+                    if (sizeof(T) == 4) {
 #pragma unroll
-                for (int sl = 0; sl < W; ++sl) {
-                    const int qu = (sl - bu) & (W - 1), qv = (sl - bv) & (W - 1);   // position of this slot in the stamp
-                    const T au = table[min(abs(p.oversampling * (qu - HALF) + uoff), p.table_len - 1)];
-                    const T av = table[min(abs(p.oversampling * (qv - HALF) + voff), p.table_len - 1)];
-                    tu[sl] = qu < S ? au : (T)0;
-                    tv[sl] = qv < S ? av : (T)0;
+                        for (int q = 0; q < W; q += 4) {
+                            const float4 x = *reinterpret_cast<const float4 *>(ru + q), y = *reinterpret_cast<const float4 *>(rv + q);
+                            tu[q] = x.x, tu[q + 1] = x.y, tu[q + 2] = x.z, tu[q + 3] = x.w;
+                            tv[q] = y.x, tv[q + 1] = y.y, tv[q + 2] = y.z, tv[q + 3] = y.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < W; q += 2) {
+                            const double2 x = *reinterpret_cast<const double2 *>(ru + q), y = *reinterpret_cast<const double2 *>(rv + q);
+                            tu[q] = x.x, tu[q + 1] = x.y;
+                            tv[q] = y.x, tv[q + 1] = y.y;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int sl = 0; sl < W; ++sl) {
+                        const int qu = (sl - bu) & (W - 1), qv = (sl - bv) & (W - 1);   // position of this slot in the stamp
+                        const T au = table[min(abs(p.oversampling * (qu - HALF) + uoff), p.table_len - 1)];
+                        const T av = table[min(abs(p.oversampling * (qv - HALF) + voff), p.table_len - 1)];
+                        tu[sl] = qu < S ? au : (T)0;
+                        tv[sl] = qv < S ? av : (T)0;
+                    }
                 }
                 if (sizeof(T) == 4) {
 #pragma unroll
@@ -464,7 +502,6 @@ std_grid_track_kernel(StdParams p)
                         *reinterpret_cast<double2 *>(rec + Cfg::OFF_CV + q * 8) = make_double2(tv[q], tv[q + 1]);
                     }
                 }
-                const int o0 = p.oversampling / 2 + 1;
                 const double norm = tapsum[uoff + o0] * tapsum[voff + o0];   // == sum over the stamp of cu*cv
 #pragma unroll
                 for (int ip = 0; ip < PP; ++ip) sw_acc[ip] += wsel[ip] * norm;
@@ -584,6 +621,8 @@ std_grid_track_kernel(StdParams p)
         const bool lead = (lane < span) && any_chan_ok && (ip < npol);
         warp_grouped_add(p.sum_weight, a_chan1 * p.n_ip + apol[ip], v, lead);
     }
+    __syncwarp();   // the next work item reuses this warp's staging buffer
+    }   // work-item loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -660,6 +699,11 @@ static int launch_track_blk(StdParams p, long long blocks, size_t smem, cudaStre
 {
     auto kern = std_grid_track_kernel<T, CPLX, S, PP, BLK>;
     CNGI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;   // resident blocks per SM for this kernel / shared-memory size
+    CNGI_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLK, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long resident = (long long)sm_count() * per_sm;
+    if (blocks > resident) blocks = resident;   // persistent warps stride over the work items
     kern<<<(unsigned)blocks, BLK, smem, st>>>(p);
     CNGI_CUDA_TRY(cudaGetLastError());
     return CNGI_OK;
@@ -708,7 +752,10 @@ static int launch_track(StdParams p, const cngi_std_grid_args *a, cudaStream_t s
         const int wpb = blk / 32;
         const long long blocks = ceil_div(p.n_tasks, wpb);
         CNGI_REQUIRE(blocks < (1LL << 31), "standard_grid: too many work items for one launch");
-        const size_t smem = (size_t)((p.table_len * (int)sizeof(T) + 15) / 16 * 16) + (size_t)2 * p.c_n * sizeof(double) +
+        const size_t rot_bytes = (size_t)Cfg::W * (p.oversampling + 3) * Cfg::W * sizeof(T);
+        p.use_rot = rot_bytes <= 56 * 1024;
+        const size_t tab_elems = p.use_rot ? rot_bytes / sizeof(T) : (size_t)p.table_len;
+        const size_t smem = (size_t)((tab_elems * sizeof(T) + 15) / 16 * 16) + (size_t)2 * p.c_n * sizeof(double) +
                             (size_t)(((p.oversampling + 3) * (int)sizeof(double) + 15) / 16 * 16) +
                             (size_t)wpb * Cfg::WARP_BYTES;
         CNGI_REQUIRE(smem <= 227 * 1024, "standard_grid: CF table too large for shared memory (%zu bytes)", smem);
