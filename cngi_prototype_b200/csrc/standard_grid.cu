@@ -49,7 +49,6 @@ struct StdParams {
     // track kernel decomposition
     int G, log2G, seg_len, n_seg, n_cspan, n_pgrp;
     int c_lo, c_n;         // channel window handled by this launch (bounds the shared-memory channel table)
-    int use_rot;           // 1: shared memory holds tap rows pre-rotated into slot order (see the kernel)
     long long n_tasks;
     const double *scale;   // naive kernel: [2, n_chan] uv_scale table
 };
@@ -185,16 +184,12 @@ constexpr int kSameFlag = 1;   // record idx.w: this sample has the same (plane,
 #ifndef CNGI_TRACK_MINB128
 #define CNGI_TRACK_MINB128 4   // min resident blocks per SM asked of ptxas (caps registers/thread); tuned on B200
 #endif
-#ifndef CNGI_TRACK_UNROLL
-#define CNGI_TRACK_UNROLL 1   // consume-loop unroll; larger values overflow the instruction cache (stall_no_inst)
-#endif
-constexpr int kConsumeUnroll = CNGI_TRACK_UNROLL;
 #ifndef CNGI_TRACK_MINB256
 #define CNGI_TRACK_MINB256 2
 #endif
 
 template <typename T, bool CPLX, int S, int PP, int BLK>
-__global__ void __launch_bounds__(BLK, (sizeof(T) == 4 ? (BLK == 128 ? CNGI_TRACK_MINB128 : CNGI_TRACK_MINB256) : (BLK == 128 ? 3 : 1)))
+__global__ void __launch_bounds__(BLK, (sizeof(T) == 4 ? (BLK == 128 ? CNGI_TRACK_MINB128 : CNGI_TRACK_MINB256) : 1))
 std_grid_track_kernel(StdParams p)
 {
     using Cfg = TrackCfg<T, CPLX, S, PP>;
@@ -205,31 +200,15 @@ std_grid_track_kernel(StdParams p)
     const unsigned FULL = 0xffffffffu;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    // Tap table.  use_rot: rows of W taps already rotated into slot order, rot[b][off][slot] = tap of the stamp position
-    // q = (slot - b) mod W for oversampling offset `off` (zero for the W - S spare slots), so phase 1 fetches a sample's
-    // W u-taps (and W v-taps) with two 128-bit loads and no arithmetic.  Otherwise (table too large for shared memory):
-    // the plain half-kernel table cgk_1D, taps looked up one by one.
     T *table = reinterpret_cast<T *>(smem);
-    const int n_off = p.oversampling + 3;
-    const int table_elems = p.use_rot ? W * n_off * W : p.table_len;
-    const int table_bytes = (table_elems * (int)sizeof(T) + 15) / 16 * 16;
+    const int table_bytes = (p.table_len * (int)sizeof(T) + 15) / 16 * 16;
     double *scale = reinterpret_cast<double *>(smem + table_bytes);   // uv_scale[0][c], uv_scale[1][c] of the window
     const int scale_bytes = 2 * p.c_n * (int)sizeof(double);
     // tapsum[off + os/2 + 1] = sum over the S taps of the stamp for oversampling offset `off`
     double *tapsum = reinterpret_cast<double *>(smem + table_bytes + scale_bytes);
+    const int n_off = p.oversampling + 3;
     const int tapsum_bytes = (n_off * (int)sizeof(double) + 15) / 16 * 16;
-    if (p.use_rot) {
-        for (int e = threadIdx.x; e < table_elems; e += blockDim.x) {
-            const int sl = e & (W - 1);
-            const int o = (e / W) % n_off;
-            const int bq = e / (W * n_off);
-            const int q = (sl - bq) & (W - 1);
-            const int k = min(abs(p.oversampling * (q - HALF) + o - p.oversampling / 2 - 1), p.table_len - 1);
-            table[e] = q < S ? (T)p.cgk[k] : (T)0;
-        }
-    } else {
-        for (int i = threadIdx.x; i < p.table_len; i += blockDim.x) table[i] = (T)p.cgk[i];
-    }
+    for (int i = threadIdx.x; i < p.table_len; i += blockDim.x) table[i] = (T)p.cgk[i];
     for (int i = threadIdx.x; i < p.c_n; i += blockDim.x) {
         const double f = p.freq[p.c_lo + i];
         scale[i] = uv_scale_of(f, p.dl, p.n_u);
@@ -248,10 +227,9 @@ std_grid_track_kernel(StdParams p)
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * (BLK / 32) + warp;
+    if (task >= p.n_tasks) return;   // no block-wide barrier after this point
     unsigned char *wbuf = smem + table_bytes + scale_bytes + tapsum_bytes + warp * Cfg::WARP_BYTES;
-    // Persistent warps: the grid is sized to the machine and every warp strides over the work items, so the tables
-    // above are built once per resident block.  No block-wide barrier after this point.
-    for (long long task = (long long)blockIdx.x * (BLK / 32) + warp; task < p.n_tasks; task += (long long)gridDim.x * (BLK / 32)) {
 
     // ---- task decode: (time segment, baseline, pol group, channel span), channel span fastest ------
     const int cspan = (int)(task % p.n_cspan);
@@ -403,7 +381,7 @@ std_grid_track_kernel(StdParams p)
     // ---- phase 1: locate, mask, look up taps, stage ------------------------------------------------
     auto stage = [&]() {
         unsigned char *rec = wbuf + lane * Cfg::REC_BYTES;
-        int2 idx = make_int2(-1, 0);   // {uc | vc << 16, plane << 8 | flags}; -1 = no sample
+        int4 idx = make_int4(-1, 0, 0, 0);
         long long key = -1;
         CellPos cp;
         bool ok = raw_ok;
@@ -456,52 +434,20 @@ std_grid_track_kernel(StdParams p)
             if (any) {
                 const int uoff = oversample_offset(cp.uc, cp.u_pos, p.oversampling);
                 const int voff = oversample_offset(cp.vc, cp.v_pos, p.oversampling);
-                // Taps are produced directly in slot order (slot = cell mod W), so they leave as 128-bit stores; slots
-                // outside the stamp (the W - S spare columns / rows) get a zero tap.  A scatter of scalar stores here
-                // cost 4-way bank conflicts (lanes L, L+8, L+16, L+24 share banks at this record stride).
-                const int bu = (cp.uc - HALF) & (W - 1), bv = (cp.vc - HALF) & (W - 1);
+                T *rcu = reinterpret_cast<T *>(rec + Cfg::OFF_CU);
+                T *rcv = reinterpret_cast<T *>(rec + Cfg::OFF_CV);
+                // taps go to slot (cell mod W); the W - S slots outside the stamp get a zero tap
+#pragma unroll
+                for (int q = 0; q < W; ++q) {
+                    T tu = (T)0, tv = (T)0;
+                    if (q < S) {
+                        tu = table[abs(p.oversampling * (q - HALF) + uoff)];
+                        tv = table[abs(p.oversampling * (q - HALF) + voff)];
+                    }
+                    rcu[(cp.uc - HALF + q) & (W - 1)] = tu;
+                    rcv[(cp.vc - HALF + q) & (W - 1)] = tv;
+                }
                 const int o0 = p.oversampling / 2 + 1;
-                T tu[W], tv[W];
-                if (p.use_rot) {
-                    const T *ru = table + ((bu * n_off) + uoff + o0) * W, *rv = table + ((bv * n_off) + voff + o0) * W;
-                    if (sizeof(T) == 4) {
-#pragma unroll
-                        for (int q = 0; q < W; q += 4) {
-                            const float4 x = *reinterpret_cast<const float4 *>(ru + q), y = *reinterpret_cast<const float4 *>(rv + q);
-                            tu[q] = x.x, tu[q + 1] = x.y, tu[q + 2] = x.z, tu[q + 3] = x.w;
-                            tv[q] = y.x, tv[q + 1] = y.y, tv[q + 2] = y.z, tv[q + 3] = y.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < W; q += 2) {
-                            const double2 x = *reinterpret_cast<const double2 *>(ru + q), y = *reinterpret_cast<const double2 *>(rv + q);
-                            tu[q] = x.x, tu[q + 1] = x.y;
-                            tv[q] = y.x, tv[q + 1] = y.y;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int sl = 0; sl < W; ++sl) {
-                        const int qu = (sl - bu) & (W - 1), qv = (sl - bv) & (W - 1);   // position of this slot in the stamp
-                        const T au = table[min(abs(p.oversampling * (qu - HALF) + uoff), p.table_len - 1)];
-                        const T av = table[min(abs(p.oversampling * (qv - HALF) + voff), p.table_len - 1)];
-                        tu[sl] = qu < S ? au : (T)0;
-                        tv[sl] = qv < S ? av : (T)0;
-                    }
-                }
-                if (sizeof(T) == 4) {
-#pragma unroll
-                    for (int q = 0; q < W; q += 4) {
-                        *reinterpret_cast<float4 *>(rec + Cfg::OFF_CU + q * 4) = make_float4(tu[q], tu[q + 1], tu[q + 2], tu[q + 3]);
-                        *reinterpret_cast<float4 *>(rec + Cfg::OFF_CV + q * 4) = make_float4(tv[q], tv[q + 1], tv[q + 2], tv[q + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < W; q += 2) {
-                        *reinterpret_cast<double2 *>(rec + Cfg::OFF_CU + q * 8) = make_double2(tu[q], tu[q + 1]);
-                        *reinterpret_cast<double2 *>(rec + Cfg::OFF_CV + q * 8) = make_double2(tv[q], tv[q + 1]);
-                    }
-                }
                 const double norm = tapsum[uoff + o0] * tapsum[voff + o0];   // == sum over the stamp of cu*cv
 #pragma unroll
                 for (int ip = 0; ip < PP; ++ip) sw_acc[ip] += wsel[ip] * norm;
@@ -515,7 +461,7 @@ std_grid_track_kernel(StdParams p)
                     for (int i = 0; i < Cfg::WD; i += 2)
                         *reinterpret_cast<double2 *>(rwd + i) = make_double2(wd[i], wd[i + 1]);
                 }
-                idx = make_int2(cp.uc | (cp.vc << 16), a_chan1 << 8);
+                idx = make_int4(cp.uc, cp.vc, a_chan1, 0);
                 key = ((long long)a_chan1 * p.n_u + cp.uc) * p.n_v + cp.vc;
             }
         }
@@ -523,16 +469,16 @@ std_grid_track_kernel(StdParams p)
         long long prev = __shfl_up_sync(FULL, key, IPW);
         if (lane < IPW) prev = carry_key;
         carry_key = __shfl_sync(FULL, key, 32 - IPW + k1);
-        if (key >= 0 && key == prev) idx.y |= kSameFlag;
-        *reinterpret_cast<int2 *>(rec + Cfg::OFF_IDX) = idx;
+        if (key >= 0 && key == prev) idx.w |= kSameFlag;
+        *reinterpret_cast<int4 *>(rec + Cfg::OFF_IDX) = idx;
     };
 
     // ---- phase 2: consume ----------------------------------------------------------------------------
     auto consume = [&]() {
-#pragma unroll(kConsumeUnroll)
+#pragma unroll 2
         for (int i = 0; i < ITER; ++i) {
             const unsigned char *rec = wbuf + (i * IPW + k2) * Cfg::REC_BYTES;
-            const int2 idx = *reinterpret_cast<const int2 *>(rec + Cfg::OFF_IDX);
+            const int4 idx = *reinterpret_cast<const int4 *>(rec + Cfg::OFF_IDX);
             // taps and data are fetched together with the cell ids (before the branches below), so an iteration
             // exposes one shared-memory latency instead of two
             const T cu = reinterpret_cast<const T *>(rec + Cfg::OFF_CU)[r2];
@@ -561,36 +507,36 @@ std_grid_track_kernel(StdParams p)
                     wd[q / 2].x = x.x, wd[q / 2].y = x.y;
                 }
             }
-            if (idx.x == -1) continue;
-            if (!(idx.y & kSameFlag)) {   // the stamp moved (or first sample): does it still fit the register window?
-                const int need_u = (idx.x & 0xffff) - HALF, need_v = (int)((unsigned)idx.x >> 16) - HALF;   // lowest column / row
-                const int plane = idx.y >> 8;
-                // slide the window by the least amount that makes the stamp fit (hysteresis of W - S cells); a new
-                // plane starts a new window.  One call site per flush loop keeps the code (instruction cache) small.
-                const bool new_plane = plane != cur_plane;
-                int new_u = lo_u, new_v = lo_v;
-                if (new_plane || need_u < lo_u) new_u = need_u;
-                else if (need_u + S > lo_u + W) new_u = need_u + S - W;
-                if (new_plane || need_v < lo_v) new_v = need_v;
-                else if (need_v + S > lo_v + W) new_v = need_v + S - W;
-                const int u = my_column();
-                // my column leaves iff it is outside the new column range (or the plane changes)
-                const bool col_leaves = new_plane ? (cur_plane >= 0) : (u < new_u || u >= new_u + W);
-                if (col_leaves) {
-                    flush_column();
-                } else if (new_v != lo_v) {   // rows outside the new row range leave
+            if (idx.x < 0) continue;
+            if (!(idx.w & kSameFlag)) {   // the stamp moved (or first sample): does it still fit the register window?
+                const int need_u = idx.x - HALF, need_v = idx.y - HALF;   // lowest column / row the stamp touches
+                if (idx.z != cur_plane) {
+                    if (cur_plane >= 0) flush_column();
 #pragma unroll
-                    for (int j = 0; j < W; ++j) {
-                        const int v = lo_v + ((j - lo_v) & (W - 1));
-                        if (v < new_v || v >= new_v + W) flush_one(j, u, v);
+                    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)idx.z * p.n_ip + apol[ip]) * plane_cells;
+                    cur_plane = idx.z, lo_u = need_u, lo_v = need_v;
+                } else {
+                    // slide the window by the least amount that makes the stamp fit (hysteresis of W - S cells)
+                    int new_u = lo_u, new_v = lo_v;
+                    if (need_u < lo_u) new_u = need_u;
+                    else if (need_u + S > lo_u + W) new_u = need_u + S - W;
+                    if (need_v < lo_v) new_v = need_v;
+                    else if (need_v + S > lo_v + W) new_v = need_v + S - W;
+                    if (new_u != lo_u) {   // my column leaves iff it is outside the new column range
+                        const int u = my_column();
+                        if (u < new_u || u >= new_u + W) flush_column();
+                        lo_u = new_u;
+                    }
+                    if (new_v != lo_v) {   // rows outside the new row range leave (cleared already if the column went)
+                        const int u = my_column();
+#pragma unroll
+                        for (int j = 0; j < W; ++j) {
+                            const int v = lo_v + ((j - lo_v) & (W - 1));
+                            if (v < new_v || v >= new_v + W) flush_one(j, u, v);
+                        }
+                        lo_v = new_v;
                     }
                 }
-                if (new_plane) {
-#pragma unroll
-                    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)plane * p.n_ip + apol[ip]) * plane_cells;
-                    cur_plane = plane;
-                }
-                lo_u = new_u, lo_v = new_v;
             }
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
@@ -621,8 +567,6 @@ std_grid_track_kernel(StdParams p)
         const bool lead = (lane < span) && any_chan_ok && (ip < npol);
         warp_grouped_add(p.sum_weight, a_chan1 * p.n_ip + apol[ip], v, lead);
     }
-    __syncwarp();   // the next work item reuses this warp's staging buffer
-    }   // work-item loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -699,11 +643,6 @@ static int launch_track_blk(StdParams p, long long blocks, size_t smem, cudaStre
 {
     auto kern = std_grid_track_kernel<T, CPLX, S, PP, BLK>;
     CNGI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;   // resident blocks per SM for this kernel / shared-memory size
-    CNGI_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLK, smem));
-    if (per_sm < 1) per_sm = 1;
-    const long long resident = (long long)sm_count() * per_sm;
-    if (blocks > resident) blocks = resident;   // persistent warps stride over the work items
     kern<<<(unsigned)blocks, BLK, smem, st>>>(p);
     CNGI_CUDA_TRY(cudaGetLastError());
     return CNGI_OK;
@@ -752,10 +691,7 @@ static int launch_track(StdParams p, const cngi_std_grid_args *a, cudaStream_t s
         const int wpb = blk / 32;
         const long long blocks = ceil_div(p.n_tasks, wpb);
         CNGI_REQUIRE(blocks < (1LL << 31), "standard_grid: too many work items for one launch");
-        const size_t rot_bytes = (size_t)Cfg::W * (p.oversampling + 3) * Cfg::W * sizeof(T);
-        p.use_rot = rot_bytes <= 56 * 1024;
-        const size_t tab_elems = p.use_rot ? rot_bytes / sizeof(T) : (size_t)p.table_len;
-        const size_t smem = (size_t)((tab_elems * sizeof(T) + 15) / 16 * 16) + (size_t)2 * p.c_n * sizeof(double) +
+        const size_t smem = (size_t)((p.table_len * (int)sizeof(T) + 15) / 16 * 16) + (size_t)2 * p.c_n * sizeof(double) +
                             (size_t)(((p.oversampling + 3) * (int)sizeof(double) + 15) / 16 * 16) +
                             (size_t)wpb * Cfg::WARP_BYTES;
         CNGI_REQUIRE(smem <= 227 * 1024, "standard_grid: CF table too large for shared memory (%zu bytes)", smem);
@@ -779,12 +715,11 @@ template <typename T, bool CPLX> static int dispatch(StdParams p, const cngi_std
 #else
     int algo = a->algorithm;
     const bool track_ok = (a->support == 3 || a->support == 5 || a->support == 7 || a->support == 9) &&
-                          a->oversampling >= 1 && p.table_len <= 8192 && a->n_u < 65536 && a->n_v < 65536 &&
-                          a->n_imag_chan < (1 << 23);   // staged records pack (uc, vc) into 16 bits each
+                          a->oversampling >= 1 && p.table_len <= 8192;
     if (algo == CNGI_ALGO_AUTO) algo = track_ok ? CNGI_ALGO_TRACK : CNGI_ALGO_NAIVE;
     if (algo == CNGI_ALGO_TRACK) {
         if (!track_ok) {
-            set_error("standard_grid: track kernel needs support in {3,5,7,9} (got %d) and a grid side below 65536", a->support);
+            set_error("standard_grid: track kernel supports support in {3,5,7,9} (got %d)", a->support);
             return CNGI_ERR_UNSUPPORTED;
         }
         switch (a->support) {
