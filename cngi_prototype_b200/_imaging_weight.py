@@ -13,8 +13,11 @@ from ._devutil import (torch, is_torch, chan_mode, precision_of, torch_dtypes, d
                        back)
 
 
-def imaging_weight_grid(uvw, weight, freq_chan, grid_parms, grid=None, sum_weight=None):
-    """Density grid rho (n_imag_chan, n_pol, n_u, n_v) float64 and sum_weight (n_imag_chan, n_pol)."""
+def imaging_weight_grid(uvw, weight, freq_chan, grid_parms, grid=None, sum_weight=None, first_pol_only=False):
+    """Density grid rho (n_imag_chan, n_pol, n_u, n_v) float64 and sum_weight (n_imag_chan, n_pol).
+
+    first_pol_only (n_pol >= 2): all pol planes are identical by construction (pol-averaged weights,
+    _standard_grid.py:328-330); update plane 0 only and let the caller replicate it (`replicate_pol_planes`)."""
     L = _lib.lib()
     like_torch = is_torch(weight)
     dev = device_of(weight, uvw)
@@ -36,10 +39,18 @@ def imaging_weight_grid(uvw, weight, freq_chan, grid_parms, grid=None, sum_weigh
     a.density, a.sum_weight = ptr(grid), ptr(sum_weight)
     cell = grid_parms["cell_size"]
     a.delta_lm[0], a.delta_lm[1] = float(cell[0]), float(cell[1])
-    a.precision, a.chan_mode = precision, chan_mode(grid_parms)
+    a.precision, a.chan_mode, a.first_pol_only = precision, chan_mode(grid_parms), int(bool(first_pol_only))
     with torch.cuda.device(dev):
         _lib.check(L.cngi_b200_imaging_weight_grid(C.byref(a), stream()), "cngi_b200_imaging_weight_grid")
     return back(grid, like_torch), back(sum_weight, like_torch)
+
+
+def replicate_pol_planes(density, sum_weight):
+    """Copies pol plane 0 (and its sum_weight) into the other pol planes -- the second half of first_pol_only."""
+    if density.shape[1] > 1:
+        density[:, 1:] = density[:, :1]
+        sum_weight[:, 1:] = sum_weight[:, :1]
+    return density, sum_weight
 
 
 def calculate_briggs_parms(grid_of_imaging_weights, sum_weight, imaging_weights_parms):

@@ -35,7 +35,7 @@ class IwGridArgs(C.Structure):
         ("weight", vp), ("uvw", vp), ("freq_chan", vp), ("chan_map", vp), ("pol_map", vp),
         ("density", vp), ("sum_weight", vp),
         ("delta_lm", f64 * 2),
-        ("precision", i32), ("chan_mode", i32),
+        ("precision", i32), ("chan_mode", i32), ("first_pol_only", i32), ("reserved", i32),
     ]
 
 

@@ -28,6 +28,7 @@ struct IwParams {
     long long ds_u, ds_v, ds_c, ds_p;
     void *out;
     const double *scale;   // [2, n_chan] uv_scale table
+    int n_pol_out;         // pol planes updated by iw_grid (1 when first_pol_only)
 };
 
 __device__ __forceinline__ int iw_chan_of(const IwParams &p, int c)
@@ -75,11 +76,13 @@ template <typename T, int G, int NP> __global__ void __launch_bounds__(256) iw_g
         if (NP) {
 #pragma unroll
             for (int ip = 0; ip < (NP ? NP : 1); ++ip) {
-                atomicAdd(plane_base + ip * plane_cells + cell, acc);
-                if (conj_ok) atomicAdd(plane_base + ip * plane_cells + ccell, acc);
+                if (ip < p.n_pol_out) {
+                    atomicAdd(plane_base + ip * plane_cells + cell, acc);
+                    if (conj_ok) atomicAdd(plane_base + ip * plane_cells + ccell, acc);
+                }
             }
         } else {
-            for (int ip = 0; ip < n_pol; ++ip) {
+            for (int ip = 0; ip < p.n_pol_out; ++ip) {
                 const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
                 atomicAdd(plane_base + a_pol * plane_cells + cell, acc);
                 if (conj_ok) atomicAdd(plane_base + a_pol * plane_cells + ccell, acc);
@@ -145,7 +148,7 @@ template <typename T, int G, int NP> __global__ void __launch_bounds__(256) iw_g
     }
     flush();
     // sum_weight: one reduction per plane per warp (all of a thread's channels share its plane)
-    for (int ip = 0; ip < n_pol; ++ip) {   // n_pol is uniform, so the warp stays converged
+    for (int ip = 0; ip < p.n_pol_out; ++ip) {   // uniform trip count, so the warp stays converged
         const int a_pol = (!NP && p.pol_map) ? (int)p.pol_map[ip] : ip;
         warp_grouped_add(p.sum_weight, plane * p.n_ip + a_pol, sw, in_range && sw != 0.0);
     }
@@ -289,6 +292,7 @@ extern "C" int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *a, void *s
     p.weight = a->weight, p.uvw = a->uvw, p.freq = a->freq_chan, p.chan_map = a->chan_map, p.pol_map = a->pol_map;
     p.density = a->density, p.sum_weight = a->sum_weight, p.dl = a->delta_lm[0], p.dm = a->delta_lm[1];
     p.chan_mode = a->chan_mode;
+    p.n_pol_out = (a->first_pol_only && p.n_pol >= 2) ? 1 : p.n_pol;
     // channels per thread: only useful when neighbouring channels share a plane
     int G = 1;
     if (p.chan_mode == CNGI_CHAN_CONTINUUM)

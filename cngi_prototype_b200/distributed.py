@@ -101,6 +101,87 @@ def continuum_imaging_step(ops, d, gp, gp_iw, iw_parms, cgk, bufs, grid_hook=Non
     return iw
 
 
+class ContinuumPipeline:
+    """Software-pipelined sequence of time-sharded continuum steps (one per chunk / dataset).
+
+    A step is  A: density grid -> all-reduce(density)      B: Briggs -> weight degrid -> gridding -> reduce(grid).
+    Both collectives have a consumer right behind them, so inside ONE step they cannot be hidden; across steps they
+    can: step k+1's stage A is issued before step k's stage B, so all-reduce(k+1) runs under gridding(k), and
+    reduce(k) runs under A(k+2)/B(k+1).  Accumulators are double-buffered; a buffer is reused only after the
+    collective that reads it has finished.  With world_size 1 the same kernels run in the same order, minus the
+    collectives.  The density all-reduce moves pol plane 0 only (all pol planes are identical when n_pol >= 2).
+
+        pipe = ContinuumPipeline(ops, gp, gp_iw, iw_parms, cgk, make_bufs)
+        for d in chunks: pipe.step(d)
+        pipe.flush()            # results of the last step: pipe.last (grid, gsw valid on rank 0)
+    """
+
+    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs):
+        self.ops, self.gp, self.gp_iw, self.iw_parms, self.cgk = ops, gp, gp_iw, iw_parms, cgk
+        self.bufs = [make_bufs(), make_bufs()]
+        self.pend_density = [[], []]
+        self.pend_grid = [[], []]
+        self.k = 0
+        self.prev = None
+        self.last = None
+
+    @staticmethod
+    def _wait(works):
+        for w in works:
+            w.wait()
+        del works[:]
+
+    def _stage_a(self, d, slot):
+        b = self.bufs[slot]
+        b.density.zero_()
+        b.dsw.zero_()
+        n_pol = b.density.shape[1]
+        self.ops.imaging_weight_grid(d["uvw"], d["weight"], d["freq_chan"], self.gp_iw, grid=b.density, sum_weight=b.dsw,
+                                     first_pol_only=n_pol >= 2)
+        if world()[1] > 1:   # every rank needs the full density for its own degrid; plane 0 carries all the information
+            first = b.density[:, :1] if n_pol >= 2 else b.density
+            self.pend_density[slot] = [dist.all_reduce(first, async_op=True), dist.all_reduce(b.dsw, async_op=True)]
+
+    def _stage_b(self, d, slot, grid_hook):
+        b = self.bufs[slot]
+        self._wait(self.pend_density[slot])
+        if b.density.shape[1] >= 2:
+            b.density[:, 1:] = b.density[:, :1]
+            b.dsw[:, 1:] = b.dsw[:, :1]
+        bf = self.ops.briggs(b.density, b.dsw, self.iw_parms)
+        iw = self.ops.degrid(b.density, d["uvw"], d["weight"], bf, d["freq_chan"], self.gp_iw)
+        self._wait(self.pend_grid[slot])   # the reduce that last read this grid buffer
+        b.grid.zero_()
+        b.gsw.zero_()
+        if grid_hook is not None:
+            grid_hook("begin")
+        self.ops.standard_grid(d["vis"], d["uvw"], iw, d["freq_chan"], self.cgk, self.gp, grid=b.grid, sum_weight=b.gsw)
+        if grid_hook is not None:
+            grid_hook("end")
+        if world()[1] > 1:   # partial uv-grids -> the rank that runs the FFT
+            self.pend_grid[slot] = [dist.reduce(_as_real(b.grid), 0, async_op=True), dist.reduce(b.gsw, 0, async_op=True)]
+        self.last = b
+        return iw
+
+    def step(self, d, grid_hook=None):
+        slot = self.k & 1
+        self._stage_a(d, slot)
+        if self.prev is not None:
+            self._stage_b(*self.prev)
+        self.prev = (d, slot, grid_hook)
+        self.k += 1
+
+    def flush(self):
+        iw = None
+        if self.prev is not None:
+            iw = self._stage_b(*self.prev)
+            self.prev = None
+        for slot in (0, 1):
+            self._wait(self.pend_density[slot])
+            self._wait(self.pend_grid[slot])
+        return iw
+
+
 def cuda_ops():
     """The product operators (libcngi_b200.so through the Python mirror) in the shape continuum_imaging_step expects."""
     from ._standard_grid import standard_grid

@@ -109,6 +109,10 @@ typedef struct cngi_iw_grid_args {
     double delta_lm[2];
     int32_t precision;
     int32_t chan_mode;
+    int32_t first_pol_only;     /* n_pol >= 2 only: every pol plane receives the same (pol-averaged) weights, so update
+                                   plane pol_map[0] and sum_weight[.., pol_map[0]] only; the caller replicates the plane
+                                   (halves the reductions here and the bytes of a multi-GPU all-reduce)             */
+    int32_t reserved;
 } cngi_iw_grid_args;
 
 int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *args, void *stream);

@@ -19,8 +19,11 @@ IW = dict(weighting="briggs", robust=0.5)
 
 
 def oracle_ops():
-    def iw_grid(uvw, w, freq, gp_iw, grid=None, sum_weight=None):
+    def iw_grid(uvw, w, freq, gp_iw, grid=None, sum_weight=None, first_pol_only=False):
         g, s = O._standard_grid_psf_numpy_wrap(uvw.numpy(), w.numpy(), freq.numpy(), np.ones(1), gp_iw)
+        if first_pol_only:   # the CUDA operator updates plane 0 only; mimic that so the replicate step is exercised
+            g[:, 1:] = 0
+            s[:, 1:] = 0
         grid += torch.from_numpy(g)
         sum_weight += torch.from_numpy(s)
 
@@ -61,13 +64,22 @@ def main():
     bufs = SimpleNamespace(density=torch.zeros((1, 2, n, n), dtype=torch.float64), dsw=torch.zeros((1, 2), dtype=torch.float64),
                            grid=torch.zeros((1, 2, n, n), dtype=torch.complex128), gsw=torch.zeros((1, 2), dtype=torch.float64))
     iw = D.continuum_imaging_step(oracle_ops(), shard, gp, gp_iw, IW, cgk, bufs)
+    # the software-pipelined driver (collectives overlapped across steps) must give the same result every step
+    def make_bufs():
+        return SimpleNamespace(density=torch.zeros((1, 2, n, n), dtype=torch.float64), dsw=torch.zeros((1, 2), dtype=torch.float64),
+                               grid=torch.zeros((1, 2, n, n), dtype=torch.complex128), gsw=torch.zeros((1, 2), dtype=torch.float64))
+    pipe = D.ContinuumPipeline(oracle_ops(), gp, gp_iw, IW, cgk, make_bufs)
+    for _ in range(3):
+        pipe.step(shard)
+    iw_pipe = pipe.flush()
+    pipe_grid, pipe_gsw = pipe.last.grid.numpy().copy(), pipe.last.gsw.numpy().copy()
     # cube: channel sharding, no exchange; gather the owned planes only to check them
     gpc = dict(gp, chan_mode="cube")
     cs = D.channel_shard(full, rank, ws)
     gc, sc = O._standard_grid_numpy_wrap(cs["vis"].numpy(), cs["uvw"].numpy(), cs["weight"].numpy(), cs["freq_chan"].numpy(),
                                          cgk, gpc)
     np.savez(os.path.join(out, "rank%d.npz" % rank), grid=bufs.grid.numpy(), gsw=bufs.gsw.numpy(), iw=iw.numpy(),
-             density=bufs.density.numpy(), cube_grid=gc, cube_sw=sc, chan_range=np.array(D.shard_range(6, rank, ws)),
+             density=bufs.density.numpy(), pipe_grid=pipe_grid, pipe_gsw=pipe_gsw, iw_pipe=iw_pipe.numpy(), cube_grid=gc, cube_sw=sc, chan_range=np.array(D.shard_range(6, rank, ws)),
              time_range=np.array(D.shard_range(24, rank, ws)))
     dist.barrier()
     dist.destroy_process_group()

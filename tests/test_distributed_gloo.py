@@ -49,6 +49,14 @@ def test_sharded_step_matches_single_process(tmp_path, oracle, world_size):
     assert np.array_equal(ranks[0]["grid"] != 0, g != 0)
     assert np.max(np.abs(ranks[0]["grid"] - g)) <= 1e-12 * np.max(np.abs(g))
     assert np.max(np.abs(ranks[0]["gsw"] - s)) <= 1e-12 * np.max(np.abs(s))
+    # pipelined driver: same grid on rank 0 after three overlapped steps, same imaging weights
+    assert np.max(np.abs(ranks[0]["pipe_grid"] - g)) <= 1e-12 * np.max(np.abs(g))
+    assert np.max(np.abs(ranks[0]["pipe_gsw"] - s)) <= 1e-12 * np.max(np.abs(s))
+    for rk in ranks:   # (summation order inside the all-reduce may differ between the two drivers: tolerance, not bits)
+        a, b = rk["iw_pipe"], rk["iw"]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        fin = np.isfinite(b)
+        assert np.max(np.abs(a[fin] - b[fin])) <= 1e-12 * np.max(np.abs(b[fin]))
     # imaging weights of the shards concatenate to the full set
     iw_cat = np.concatenate([rk["iw"] for rk in ranks], axis=0)
     assert iw_cat.shape == iw.shape
