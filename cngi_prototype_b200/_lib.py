@@ -140,5 +140,12 @@ def check(rc, what):
         raise CngiError("%s failed (status %d): %s" % (what, rc, msg.decode() if msg else "?"))
 
 
+_device_ok = False
+
+
 def require_device():
-    check(lib().cngi_b200_check_device(), "cngi_b200_check_device")
+    """Raises unless an sm_100 device is usable (checked once per process; there is no fallback)."""
+    global _device_ok
+    if not _device_ok:
+        check(lib().cngi_b200_check_device(), "cngi_b200_check_device")
+        _device_ok = True
