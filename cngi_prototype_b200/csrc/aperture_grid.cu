@@ -7,13 +7,18 @@
 // on the fly for exactly the taps a sample reads, so the CF stack (real, L2 resident) and the per-field
 // phase gradients are only ever read.
 //
-// A5: one thread per (time, baseline, chan) sample, S_u x S_v reductions per polarisation (REDG.F32x2 /
-//     2 x REDG.F64).
+// A5: the oversampled CF is first re-laid out per call into OFFSET-MAJOR order and pre-multiplied by the phase gradient,
+//     taps[field][cf][u offset][v offset][iu][iv] (complex), so the Su x Sv taps a sample needs are one contiguous block
+//     instead of a stride-`oversampling` gather through a 160 x 160 array.  The gridding kernel then gives LW lanes to a
+//     sample, lane j <-> grid column vc + iv_j (the fastest axis): per stamp row the lanes read one contiguous run of
+//     taps and issue one contiguous run of reductions (REDG.F32x2 / 2 x REDG.F64), 4 cells per 32-byte L2 sector.
+//     The fp64 cell / offset arithmetic is done once per sample (lane L <-> sample L) and handed out with shuffles.
 // A6: every sample stamps the SAME Su x Sv cells at the grid centre, so weights are first summed per
 //     (field, cf_baseline, cf_chan, cf_pol, image plane) bucket (warp-aggregated REDG into a small table) and a
 //     second tiny kernel multiplies each bucket by its CF*PG taps -- O(n_samples) + O(n_buckets * S^2)
 //     instead of O(n_samples * S^2) colliding atomics.
 #include "common.cuh"
+#include <algorithm>
 
 namespace cngi {
 
@@ -34,6 +39,8 @@ struct ApParams {
     int n_field, n_cfb, n_cfc, n_cfp, n_cu, n_cv;
     int os_u, os_v, max_support, do_psf, chan_mode;
     const double *scale;   // [2, n_chan] uv_scale table
+    const void *taps;      // A5: offset-major pre-multiplied taps (see aperture_build_taps_kernel)
+    int smax, n_off_u, n_off_v;
     double *buckets;       // A6: [n_field, n_cfb, n_cfc, n_cfp, n_ic, n_ip] weight sums
 };
 
@@ -62,60 +69,144 @@ __device__ __forceinline__ bool ap_locate(const ApParams &p, long long tb, int c
     return stamp_inside(cp.uc, cp.vc, p.max_support, p.n_u, p.n_v);
 }
 
-template <typename T> __global__ void __launch_bounds__(256) aperture_grid_kernel(ApParams p)
+// taps[(((field * n_cf + cf) * n_off_u + ou) * n_off_v + ov) * smax + iu_t) * smax + iv_t]
+//   = CF[cf][os_u * (iu_t - smax/2) + (ou - os_u/2 - 1) + n_cu/2][os_v * (iv_t - smax/2) + (ov - os_v/2 - 1) + n_cv/2] * PG[field][same]
+// i.e. exactly the element _aperture_grid_jit reads for stamp position (iu, iv) at oversampling offset (ou, ov)
+// (_aperture_grid.py:448-451,484-499), as (k + 0j) * pg like the reference's conv_kernel * phase_gradient (:429).
+template <typename T> __global__ void aperture_build_taps_kernel(ApParams p, typename Cplx<T>::type *taps, long long n_elems)
 {
     using CT = typename Cplx<T>::type;
-    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % p.n_chan);
-    const long long tb = idx / p.n_chan;
-    const int b = (int)(tb % p.n_baseline);
-    int field_indx;
-    CellPos cp;
-    if (!ap_locate(p, tb, c, field_indx, cp)) return;
-    const int u_off = oversample_offset(cp.uc, cp.u_pos, p.os_u) + p.n_cu / 2;   // :448-451
-    const int v_off = oversample_offset(cp.vc, cp.v_pos, p.os_v) + p.n_cv / 2;
-    const int cf_b = (int)p.cf_b_map[b], cf_c = (int)p.cf_c_map[c];
-    const int a_chan = ap_chan_of(p, c);
-    const double2 *pg = p.pg + (long long)field_indx * p.n_cu * p.n_cv;
-    for (int ip = 0; ip < p.n_pol; ++ip) {
-        const long long s = idx * p.n_pol + ip;
-        const double w = (double)((const T *)p.weight)[s];
-        double wre = w, wim = 0.0;
-        if (!p.do_psf) {
-            const CT d = ((const CT *)p.vis)[s];
-            weighted_vis((double)d.x, (double)d.y, w, wre, wim);
-            if (p.flag && p.flag[s]) wre = nan("");
+    const int n_cf = p.n_cfb * p.n_cfc * p.n_cfp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += (long long)gridDim.x * blockDim.x) {
+        long long r = e;
+        const int iv_t = (int)(r % p.smax);
+        r /= p.smax;
+        const int iu_t = (int)(r % p.smax);
+        r /= p.smax;
+        const int ov = (int)(r % p.n_off_v);
+        r /= p.n_off_v;
+        const int ou = (int)(r % p.n_off_u);
+        r /= p.n_off_u;
+        const int cf = (int)(r % n_cf);
+        const int field = (int)(r / n_cf);
+        const int cf_u = p.os_u * (iu_t - p.smax / 2) + (ou - p.os_u / 2 - 1) + p.n_cu / 2;
+        const int cf_v = p.os_v * (iv_t - p.smax / 2) + (ov - p.os_v / 2 - 1) + p.n_cv / 2;
+        CT out;
+        out.x = out.y = (T)0;
+        if (cf_u >= 0 && cf_u < p.n_cu && cf_v >= 0 && cf_v < p.n_cv) {
+            const double k = p.ck[((long long)cf * p.n_cu + cf_u) * p.n_cv + cf_v];
+            const double2 g = p.pg[((long long)field * p.n_cu + cf_u) * p.n_cv + cf_v];
+            out.x = (T)(k * g.x);
+            out.y = (T)(k * g.y);
         }
-        if (masked(wre, wim)) continue;
-        const int cf_p = (int)p.cf_p_map[ip];
-        const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
-        const long long cf = ((long long)cf_b * p.n_cfc + cf_c) * p.n_cfp + cf_p;
-        const int su = (int)p.support[cf * 2], sv = (int)p.support[cf * 2 + 1];
-        const double *ck = p.ck + cf * p.n_cu * p.n_cv;
-        CT *plane = (CT *)p.grid + ((long long)a_chan * p.n_ip + a_pol) * p.n_u * (long long)p.n_v;
-        double nre = 0.0, nim = 0.0;
-        for (int iu = -(su / 2); iu < su - su / 2; ++iu) {          // u outer: consecutive iv are contiguous in CF and grid
-            const int cf_u = p.os_u * iu + u_off;
-            CT *rowp = plane + (long long)(cp.uc + iu) * p.n_v + cp.vc;
-            for (int iv = -(sv / 2); iv < sv - sv / 2; ++iv) {
-                const int cf_v = p.os_v * iv + v_off;
-                const double k = ck[(long long)cf_u * p.n_cv + cf_v];
-                const double2 g = pg[(long long)cf_u * p.n_cv + cf_v];
-                const double cr = k * g.x, ci = k * g.y;                     // (k + 0j) * pg
-                CT val;
-                val.x = (T)(cr * wre - ci * wim);
-                val.y = (T)(cr * wim + ci * wre);
-                red_add(rowp + iv, val);
-                nre += cr;
-                nim += ci;
+        taps[e] = out;
+    }
+}
+
+template <typename T, int LW> __global__ void __launch_bounds__(256) aperture_grid_kernel(ApParams p)
+{
+    using CT = typename Cplx<T>::type;
+    constexpr int SPW = 32 / LW;
+    const unsigned FULL = 0xffffffffu;
+    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LW, lj = lane % LW;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long plane_cells = (long long)p.n_u * p.n_v;
+    const int n_cf = p.n_cfb * p.n_cfc * p.n_cfp;
+    const int shalf = p.smax / 2;
+    const int iv = lj - shalf;                      // stamp column of this lane
+    // running sum_weight of this lane group (one reduction when the image plane changes / at the end)
+    double sw_acc = 0.0;
+    int sw_slot = -1;
+
+    for (long long base = warp0 * 32; base < total; base += n_warps * 32) {
+        // ---- step 1: lane L locates sample base + L ------------------------------------------------------------------
+        const long long mine = base + lane;
+        int pk_cell = -1, pk_off = 0, pk_cf = 0, pk_plane = 0;
+        if (mine < total) {
+            const int c = (int)(mine % p.n_chan);
+            const long long tb = mine / p.n_chan;
+            int field_indx;
+            CellPos cp;
+            if (ap_locate(p, tb, c, field_indx, cp)) {
+                const int ou = oversample_offset(cp.uc, cp.u_pos, p.os_u) + p.os_u / 2 + 1;   // :448-451 (centre folded into the table)
+                const int ov = oversample_offset(cp.vc, cp.v_pos, p.os_v) + p.os_v / 2 + 1;
+                pk_cell = cp.uc | (cp.vc << 16);
+                pk_off = ou | (ov << 16);
+                pk_cf = ((int)p.cf_b_map[tb % p.n_baseline] * p.n_cfc + (int)p.cf_c_map[c]) | (field_indx << 20);
+                pk_plane = ap_chan_of(p, c);
             }
         }
-        // psf: w * Re(norm); image: w * Re(norm^2)   (:508-511)
-        const double sw = p.do_psf ? w * nre : w * (nre * nre - nim * nim);
-        atomicAdd(p.sum_weight + a_chan * p.n_ip + a_pol, sw);
+        // ---- step 2: LW lanes per sample, lane lj <-> stamp column iv ------------------------------------------------------
+#pragma unroll 1
+        for (int it = 0; it < LW; ++it) {
+            const int src = it * SPW + sub;
+            const int q_cell = __shfl_sync(FULL, pk_cell, src);
+            const int q_off = __shfl_sync(FULL, pk_off, src);
+            const int q_cf = __shfl_sync(FULL, pk_cf, src);
+            const int a_chan = __shfl_sync(FULL, pk_plane, src);
+            const long long idx = base + src;
+            const bool ok = q_cell != -1;
+            const int uc = q_cell & 0xffff, vc = (int)((unsigned)q_cell >> 16);
+            const int ou = q_off & 0xffff, ov = (int)((unsigned)q_off >> 16);
+            const int cf_bc = q_cf & 0xfffff, field_indx = q_cf >> 20;
+            for (int ip = 0; ip < p.n_pol; ++ip) {   // uniform trip count: shuffles below
+                double w = 0.0, wre = 0.0, wim = 0.0;
+                bool use = ok;
+                if (use) {
+                    const long long s = idx * p.n_pol + ip;
+                    w = (double)((const T *)p.weight)[s];
+                    wre = w;
+                    if (!p.do_psf) {
+                        const CT d = ((const CT *)p.vis)[s];
+                        weighted_vis((double)d.x, (double)d.y, w, wre, wim);
+                        if (p.flag && p.flag[s]) wre = nan("");
+                    }
+                    use = !masked(wre, wim);
+                }
+                const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
+                T nre = (T)0, nim = (T)0;
+                if (use) {
+                    const int cf = cf_bc * p.n_cfp + (int)p.cf_p_map[ip];
+                    const int su = (int)p.support[cf * 2], sv = (int)p.support[cf * 2 + 1];
+                    if (iv >= -(sv / 2) && iv < sv - sv / 2) {
+                        const CT *tp = (const CT *)p.taps +
+                                       ((((long long)field_indx * n_cf + cf) * p.n_off_u + ou) * p.n_off_v + ov) * p.smax * p.smax + lj;
+                        CT *col = (CT *)p.grid + ((long long)a_chan * p.n_ip + a_pol) * plane_cells + vc + iv;
+                        const T dre = (T)wre, dim = (T)wim;
+                        for (int iu = -(su / 2); iu < su - su / 2; ++iu) {
+                            const CT t = tp[(iu + shalf) * p.smax];
+                            CT val;
+                            val.x = t.x * dre - t.y * dim;
+                            val.y = t.x * dim + t.y * dre;
+                            red_add(col + (long long)(uc + iu) * p.n_v, val);
+                            nre += t.x;
+                            nim += t.y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = LW / 2; o > 0; o >>= 1) {
+                    nre += __shfl_xor_sync(FULL, nre, o);
+                    nim += __shfl_xor_sync(FULL, nim, o);
+                }
+                if (lj == 0 && use) {   // psf: w * Re(norm); image: w * Re(norm^2)   (:508-511)
+                    const double nr = (double)nre, ni = (double)nim;
+                    const double term = p.do_psf ? w * nr : w * (nr * nr - ni * ni);
+                    const int slot = a_chan * p.n_ip + a_pol;
+                    if (slot != sw_slot) {
+                        if (sw_slot >= 0 && sw_acc != 0.0) atomicAdd(p.sum_weight + sw_slot, sw_acc);
+                        sw_slot = slot;
+                        sw_acc = 0.0;
+                    }
+                    sw_acc += term;
+                }
+            }
+        }
     }
+    if (sw_slot >= 0 && sw_acc != 0.0) atomicAdd(p.sum_weight + sw_slot, sw_acc);
 }
 
 // A6 pass 1: bucket the weights
@@ -217,6 +308,48 @@ static int fill(ApParams &p, const cngi_aperture_grid_args *a, const char *who, 
     return CNGI_OK;
 }
 
+template <typename T> static int launch_aperture(ApParams p, cudaStream_t st)
+{
+    using CT = typename Cplx<T>::type;
+    const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
+    p.smax = p.max_support;
+    p.n_off_u = p.os_u + 3, p.n_off_v = p.os_v + 3;
+    const int n_cf = p.n_cfb * p.n_cfc * p.n_cfp;
+    const long long n_elems = (long long)p.n_field * n_cf * p.n_off_u * p.n_off_v * p.smax * p.smax;
+    CNGI_REQUIRE(p.smax <= 32, "aperture_grid: max support above 32 is not supported (got %d)", p.smax);
+    CNGI_REQUIRE(p.n_u < 65536 && p.n_v < 65536 && p.n_off_u < 65536 && p.n_off_v < 65536, "aperture_grid: grid side / oversampling too large");
+    CNGI_REQUIRE(p.n_cfb * p.n_cfc < (1 << 20) && p.n_field < (1 << 11), "aperture_grid: too many convolution functions / fields");
+    CNGI_REQUIRE(n_elems * (long long)sizeof(CT) < (8LL << 30), "aperture_grid: offset-major tap table would need %lld MB",
+                 n_elems * (long long)sizeof(CT) >> 20);
+    double *scale = nullptr;
+    int rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
+    if (rc != CNGI_OK) return rc;
+    p.scale = scale;
+    CT *taps = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&taps, (size_t)n_elems * sizeof(CT), st);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(scale, st);
+        set_error("aperture_grid: cudaMallocAsync of the tap table failed: %s", cudaGetErrorString(e));
+        return CNGI_ERR_CUDA;
+    }
+    aperture_build_taps_kernel<T><<<(unsigned)std::min<long long>(ceil_div(n_elems, 256), (long long)sm_count() * 16), 256, 0, st>>>(p, taps, n_elems);
+    p.taps = taps;
+    long long blocks = ceil_div(ceil_div(total, 32) * 32, 256);
+    const long long cap = (long long)sm_count() * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    if (p.smax <= 8)
+        aperture_grid_kernel<T, 8><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else if (p.smax <= 16)
+        aperture_grid_kernel<T, 16><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else
+        aperture_grid_kernel<T, 32><<<(unsigned)blocks, 256, 0, st>>>(p);
+    e = cudaGetLastError();
+    cudaFreeAsync(taps, st);
+    cudaFreeAsync(scale, st);
+    CNGI_CUDA_TRY(e);
+    return CNGI_OK;
+}
+
 }  // namespace cngi
 
 extern "C" int cngi_b200_aperture_grid(const cngi_aperture_grid_args *a, void *stream)
@@ -228,21 +361,7 @@ extern "C" int cngi_b200_aperture_grid(const cngi_aperture_grid_args *a, void *s
     if (p.do_psf) p.flag = nullptr;
     const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
     if (total == 0 || p.n_pol == 0) return CNGI_OK;
-    const long long blocks = ceil_div(total, 256);
-    CNGI_REQUIRE(blocks < (1LL << 31), "aperture_grid: too many samples");
-    cudaStream_t st = (cudaStream_t)stream;
-    double *scale = nullptr;
-    rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
-    if (rc != CNGI_OK) return rc;
-    p.scale = scale;
-    if (a->precision == CNGI_F32)
-        aperture_grid_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(p);
-    else
-        aperture_grid_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(p);
-    cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(scale, st);
-    CNGI_CUDA_TRY(e);
-    return CNGI_OK;
+    return a->precision == CNGI_F32 ? launch_aperture<float>(p, (cudaStream_t)stream) : launch_aperture<double>(p, (cudaStream_t)stream);
 }
 
 extern "C" int cngi_b200_aperture_weight_grid(const cngi_aperture_grid_args *a, void *stream)
