@@ -19,6 +19,7 @@
 //     instead of O(n_samples * S^2) colliding atomics.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace cngi {
 
@@ -41,6 +42,9 @@ struct ApParams {
     const double *scale;   // [2, n_chan] uv_scale table
     const void *taps;      // A5: offset-major pre-multiplied taps (see aperture_build_taps_kernel)
     int smax, n_off_u, n_off_v;
+    const double2 *tapnorm; // track kernel: sum of the taps of each (field, cf, ou, ov) block
+    int G, log2G, seg_len, n_seg, n_cspan, n_pgrp;
+    long long n_tasks;
     double *buckets;       // A6: [n_field, n_cfb, n_cfc, n_cfp, n_ic, n_ip] weight sums
 };
 
@@ -209,6 +213,291 @@ template <typename T, int LW> __global__ void __launch_bounds__(256) aperture_gr
     if (sw_slot >= 0 && sw_acc != 0.0) atomicAdd(p.sum_weight + sw_slot, sw_acc);
 }
 
+// ------------------------------------------------------------------------------------------------
+//  A5 track kernel: the aperture gridder with the standard gridder's register-window scheme
+// ------------------------------------------------------------------------------------------------
+// Same decomposition as std_grid_track_kernel (standard_grid.cu): a work item walks one baseline through time (and G
+// channels in continuum mode), W lanes per item, lane r owns the grid column u == r (mod W) of a W x W register window
+// and keeps W accumulators (rows v == s (mod W)) per polarisation; cells are reduced into the grid (REDG) only when
+// they leave the window.  W = 16 covers supports up to 15 with one spare column / row of hysteresis.
+// The CF is not separable, so taps are not staged: every lane fetches its W taps per sample straight from the
+// block-major tap table tapsW[block][iv][iu] (block = (field, cf, u offset, v offset), zero outside the CF's own
+// support), where the W lanes of an item read one contiguous 128-byte row per load.  The per-block tap sum needed by
+// sum_weight (_aperture_grid.py:508-511) is tabulated once per call (tapnorm).
+template <typename T, int W> __global__ void aperture_build_blocks_kernel(ApParams p, typename Cplx<T>::type *tapsW, double2 *tapnorm)
+{
+    using CT = typename Cplx<T>::type;
+    const int n_cf = p.n_cfb * p.n_cfc * p.n_cfp;
+    long long r = blockIdx.x;                       // one CUDA block per tap block
+    const int ov = (int)(r % p.n_off_v);
+    r /= p.n_off_v;
+    const int ou = (int)(r % p.n_off_u);
+    r /= p.n_off_u;
+    const int cf = (int)(r % n_cf);
+    const int field = (int)(r / n_cf);
+    const int su = (int)p.support[cf * 2], sv = (int)p.support[cf * 2 + 1];
+    const int shalf = p.smax / 2;
+    double sre = 0.0, sim = 0.0;
+    for (int e = threadIdx.x; e < W * W; e += blockDim.x) {
+        const int iv_t = e / W, iu_t = e % W;       // [iv][iu]: the lanes of an item (iu) are contiguous
+        const int iu = iu_t - shalf, iv = iv_t - shalf;
+        CT out;
+        out.x = out.y = (T)0;
+        if (iu >= -(su / 2) && iu < su - su / 2 && iv >= -(sv / 2) && iv < sv - sv / 2) {
+            const int cf_u = p.os_u * iu + (ou - p.os_u / 2 - 1) + p.n_cu / 2;
+            const int cf_v = p.os_v * iv + (ov - p.os_v / 2 - 1) + p.n_cv / 2;
+            if (cf_u >= 0 && cf_u < p.n_cu && cf_v >= 0 && cf_v < p.n_cv) {
+                const double k = p.ck[((long long)cf * p.n_cu + cf_u) * p.n_cv + cf_v];
+                const double2 g = p.pg[((long long)field * p.n_cu + cf_u) * p.n_cv + cf_v];
+                out.x = (T)(k * g.x);
+                out.y = (T)(k * g.y);
+                sre += (double)out.x;
+                sim += (double)out.y;
+            }
+        }
+        tapsW[(long long)blockIdx.x * W * W + e] = out;
+    }
+    __shared__ double red[2][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sre += __shfl_xor_sync(0xffffffffu, sre, o);
+        sim += __shfl_xor_sync(0xffffffffu, sim, o);
+    }
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = sre, red[1][threadIdx.x >> 5] = sim;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) a += red[0][i], b += red[1][i];
+        tapnorm[blockIdx.x] = make_double2(a, b);
+    }
+}
+
+template <typename T, int W, int PP> struct ApTrackCfg {
+    static constexpr int IPW = 32 / W;
+    static constexpr int ITER = W;
+    // record: {uc | vc << 16, plane << 8 | flags} | tap block index | pad | PP (re, im) pairs of weighted data
+    static constexpr int OFF_WD = 16;
+    static constexpr int RAW = OFF_WD + PP * 2 * (int)sizeof(T);
+    static constexpr int R16 = (RAW + 15) / 16;
+    static constexpr int REC_BYTES = 16 * (R16 % 2 == 0 ? R16 + 1 : R16);   // 16 * odd: conflict-free 128-bit stores
+    static constexpr int WARP_BYTES = 32 * REC_BYTES;
+};
+
+template <typename T, int W, int PP> __global__ void __launch_bounds__(128) aperture_track_kernel(ApParams p)
+{
+    using Cfg = ApTrackCfg<T, W, PP>;
+    using CT = typename Cplx<T>::type;
+    constexpr int IPW = Cfg::IPW, ITER = Cfg::ITER;
+    const unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (task >= p.n_tasks) return;
+    unsigned char *wbuf = smem + warp * Cfg::WARP_BYTES;
+    const int S = p.smax, shalf = p.smax / 2;
+    const int n_cf = p.n_cfb * p.n_cfc * p.n_cfp;
+
+    const int cspan = (int)(task % p.n_cspan);
+    long long rest = task / p.n_cspan;
+    const int pgrp = (int)(rest % p.n_pgrp);
+    rest /= p.n_pgrp;
+    const int b = (int)(rest % p.n_baseline);
+    const int seg = (int)(rest / p.n_baseline);
+    const int t_lo = seg * p.seg_len, t_hi = min(p.n_time, t_lo + p.seg_len);
+    const int G = p.G, spr = ITER >> p.log2G;
+    const int c_base = cspan * IPW * G;
+    const int p0 = pgrp * PP, npol = min(PP, p.n_pol - p0);
+    const long long plane_cells = (long long)p.n_u * p.n_v;
+    const int cf_b = (int)p.cf_b_map[b];
+
+    // ---- phase-1 role: lane <-> staged sample ----
+    const int k1 = lane % IPW, q1 = lane / IPW;
+    const int g1 = q1 & (G - 1), row1 = q1 >> p.log2G;
+    const int c1 = c_base + k1 * G + g1;
+    const bool chan_ok = c1 < p.n_chan;
+    const int a_chan1 = chan_ok ? ap_chan_of(p, c1) : 0;
+    int cf1[PP];   // CF of each polarisation of the group (they usually coincide: cf_pol_map is often all zero)
+#pragma unroll
+    for (int ip = 0; ip < PP; ++ip)
+        cf1[ip] = (chan_ok && ip < npol) ? (cf_b * p.n_cfc + (int)p.cf_c_map[c1]) * p.n_cfp + (int)p.cf_p_map[p0 + ip] : 0;
+    const double us1 = chan_ok ? p.scale[c1] : 0.0, vs1 = chan_ok ? p.scale[p.n_chan + c1] : 0.0;
+    double sw_acc[PP];
+#pragma unroll
+    for (int ip = 0; ip < PP; ++ip) sw_acc[ip] = 0.0;
+    long long carry_key = -1;
+
+    // ---- phase-2 role: lane <-> (item, u residue mod W) ----
+    const int k2 = lane / W, r2 = lane & (W - 1);
+    int apol[PP];
+#pragma unroll
+    for (int ip = 0; ip < PP; ++ip) apol[ip] = (ip < npol) ? (p.pol_map ? (int)p.pol_map[p0 + ip] : p0 + ip) : 0;
+    CT acc[W][PP];
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+#pragma unroll
+        for (int ip = 0; ip < PP; ++ip) acc[j][ip].x = acc[j][ip].y = (T)0;
+    int cur_plane = -1, lo_u = 0, lo_v = 0;
+    long long plane_off[PP];
+#pragma unroll
+    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = 0;
+
+    auto flush_one = [&](int j, int u, int v) {
+        const int cell = u * p.n_v + v;
+#pragma unroll
+        for (int ip = 0; ip < PP; ++ip) {
+            if (ip < npol && (acc[j][ip].x != (T)0 || acc[j][ip].y != (T)0)) {
+                red_add((CT *)p.grid + plane_off[ip] + cell, acc[j][ip]);
+                acc[j][ip].x = acc[j][ip].y = (T)0;   // clear only what was flushed (see standard_grid.cu)
+            }
+        }
+    };
+    auto my_column = [&]() { return lo_u + ((r2 - lo_u) & (W - 1)); };
+    auto flush_column = [&]() {
+        const int u = my_column();
+#pragma unroll
+        for (int j = 0; j < W; ++j) flush_one(j, u, lo_v + ((j - lo_v) & (W - 1)));
+    };
+
+    for (int t0 = t_lo; t0 < t_hi; t0 += spr) {
+        // ---- phase 1 ----
+        {
+            unsigned char *rec = wbuf + lane * Cfg::REC_BYTES;
+            int2 idx = make_int2(-1, 0);
+            int blk[2] = {0, 0};
+            long long key = -1;
+            const int t = t0 + row1;
+            if (chan_ok && t < t_hi) {
+                const long long tb = (long long)t * p.n_baseline + b;
+                const long long f = p.field[tb];
+                const int field_indx = f > -1 ? ap_find_field(p, f) : -1;
+                CellPos cp;
+                bool ok = field_indx >= 0 && locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], us1, vs1, p.n_u, p.n_v, cp);
+                if (ok) ok = stamp_inside(cp.uc, cp.vc, p.max_support, p.n_u, p.n_v);
+                if (ok) {
+                    const long long s = (tb * p.n_chan + c1) * p.n_pol + p0;
+                    T wd[PP * 2];
+                    double wsel[PP];
+                    bool any = false;
+#pragma unroll
+                    for (int ip = 0; ip < PP; ++ip) {
+                        wd[2 * ip] = wd[2 * ip + 1] = (T)0;
+                        wsel[ip] = 0.0;
+                        if (ip < npol) {
+                            const double w = (double)((const T *)p.weight)[s + ip];
+                            double wre = w, wim = 0.0;
+                            if (!p.do_psf) {
+                                const CT d = ((const CT *)p.vis)[s + ip];
+                                weighted_vis((double)d.x, (double)d.y, w, wre, wim);
+                                if (p.flag && p.flag[s + ip]) wre = nan("");
+                            }
+                            if (!masked(wre, wim)) {
+                                any = true;
+                                wsel[ip] = w;
+                                wd[2 * ip] = (T)wre, wd[2 * ip + 1] = (T)wim;
+                            }
+                        }
+                    }
+                    if (any) {
+                        const int ou = oversample_offset(cp.uc, cp.u_pos, p.os_u) + p.os_u / 2 + 1;
+                        const int ov = oversample_offset(cp.vc, cp.v_pos, p.os_v) + p.os_v / 2 + 1;
+#pragma unroll
+                        for (int ip = 0; ip < PP; ++ip) {
+                            blk[ip] = (((field_indx * n_cf) + cf1[ip]) * p.n_off_u + ou) * p.n_off_v + ov;
+                            const double2 tn = p.tapnorm[blk[ip]];
+                            // psf: w * Re(norm); image: w * Re(norm^2)   (_aperture_grid.py:508-511)
+                            sw_acc[ip] += wsel[ip] * (p.do_psf ? tn.x : (tn.x * tn.x - tn.y * tn.y));
+                        }
+#pragma unroll
+                        for (int ip = 0; ip < PP; ++ip) {
+                            CT v2;
+                            v2.x = wd[2 * ip], v2.y = wd[2 * ip + 1];
+                            reinterpret_cast<CT *>(rec + Cfg::OFF_WD)[ip] = v2;
+                        }
+                        idx = make_int2(cp.uc | (cp.vc << 16), a_chan1 << 8);
+                        key = ((long long)a_chan1 * p.n_u + cp.uc) * p.n_v + cp.vc;
+                    }
+                }
+            }
+            long long prev = __shfl_up_sync(FULL, key, IPW);
+            if (lane < IPW) prev = carry_key;
+            carry_key = __shfl_sync(FULL, key, 32 - IPW + k1);
+            if (key >= 0 && key == prev) idx.y |= 1;
+            *reinterpret_cast<int4 *>(rec) = make_int4(idx.x, idx.y, blk[0], blk[PP - 1]);
+        }
+        __syncwarp();
+        // ---- phase 2 ----
+#pragma unroll 1
+        for (int i = 0; i < ITER; ++i) {
+            const unsigned char *rec = wbuf + (i * IPW + k2) * Cfg::REC_BYTES;
+            const int4 idx = *reinterpret_cast<const int4 *>(rec);
+            if (idx.x == -1) continue;
+            CT wd[PP];
+#pragma unroll
+            for (int ip = 0; ip < PP; ++ip) wd[ip] = reinterpret_cast<const CT *>(rec + Cfg::OFF_WD)[ip];
+            const int uc = idx.x & 0xffff, vc = (int)((unsigned)idx.x >> 16);
+            if (!(idx.y & 1)) {
+                const int need_u = uc - shalf, need_v = vc - shalf;
+                const int plane = idx.y >> 8;
+                const bool new_plane = plane != cur_plane;
+                int new_u = lo_u, new_v = lo_v;
+                if (new_plane || need_u < lo_u) new_u = need_u;
+                else if (need_u + S > lo_u + W) new_u = need_u + S - W;
+                if (new_plane || need_v < lo_v) new_v = need_v;
+                else if (need_v + S > lo_v + W) new_v = need_v + S - W;
+                const int u = my_column();
+                const bool col_leaves = new_plane ? (cur_plane >= 0) : (u < new_u || u >= new_u + W);
+                if (col_leaves) {
+                    flush_column();
+                } else if (new_v != lo_v) {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) {
+                        const int v = lo_v + ((j - lo_v) & (W - 1));
+                        if (v < new_v || v >= new_v + W) flush_one(j, u, v);
+                    }
+                }
+                if (new_plane) {
+#pragma unroll
+                    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)plane * p.n_ip + apol[ip]) * plane_cells;
+                    cur_plane = plane;
+                }
+                lo_u = new_u, lo_v = new_v;
+            }
+            // taps: slot s of this lane's column <-> stamp row q = (s - bv) mod W, stamp column qu = (r2 - bu) mod W
+            const int bu = (uc - shalf) & (W - 1), bv = (vc - shalf) & (W - 1);
+            const CT *tp = (const CT *)p.taps + (long long)idx.z * (W * W) + ((r2 - bu) & (W - 1));
+            const CT *tp1 = (const CT *)p.taps + (long long)idx.w * (W * W) + ((r2 - bu) & (W - 1));
+            const bool same_cf = idx.z == idx.w;
+            CT d0[PP], d1[PP];   // acc += t.x * (dr, di) + t.y * (-di, dr)
+#pragma unroll
+            for (int ip = 0; ip < PP; ++ip) {
+                d0[ip] = wd[ip];
+                d1[ip].x = -wd[ip].y, d1[ip].y = wd[ip].x;
+            }
+#pragma unroll
+            for (int sl = 0; sl < W; ++sl) {
+                const int row = ((sl - bv) & (W - 1)) * W;
+                CT tap = tp[row];
+#pragma unroll
+                for (int ip = 0; ip < PP; ++ip) {
+                    if (ip > 0 && !same_cf) tap = tp1[row];
+                    pair_fma(acc[sl][ip], d0[ip], tap.x);
+                    pair_fma(acc[sl][ip], d1[ip], tap.y);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (cur_plane >= 0) flush_column();
+
+    const int span = IPW * G;
+#pragma unroll
+    for (int ip = 0; ip < PP; ++ip) {
+        double v = sw_acc[ip];
+        for (int o = span; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+        warp_grouped_add(p.sum_weight, a_chan1 * p.n_ip + apol[ip], v, (lane < span) && chan_ok && (ip < npol));
+    }
+}
+
 // A6 pass 1: bucket the weights
 template <typename T> __global__ void __launch_bounds__(256) aperture_weight_bucket_kernel(ApParams p)
 {
@@ -308,7 +597,65 @@ static int fill(ApParams &p, const cngi_aperture_grid_args *a, const char *who, 
     return CNGI_OK;
 }
 
-template <typename T> static int launch_aperture(ApParams p, cudaStream_t st)
+template <typename T, int W, int PP> static int launch_aperture_track(ApParams p, cudaStream_t st)
+{
+    using CT = typename Cplx<T>::type;
+    using Cfg = ApTrackCfg<T, W, PP>;
+    p.smax = p.max_support;
+    p.n_off_u = p.os_u + 3, p.n_off_v = p.os_v + 3;
+    const int n_cf = p.n_cfb * p.n_cfc * p.n_cfp;
+    const long long n_blocks = (long long)p.n_field * n_cf * p.n_off_u * p.n_off_v;
+    CNGI_REQUIRE(n_blocks < (1LL << 31) && n_blocks * W * W * (long long)sizeof(CT) < (8LL << 30),
+                 "aperture_grid: tap table of %lld blocks is too large", n_blocks);
+    double *scale = nullptr;
+    CT *taps = nullptr;
+    double2 *tapnorm = nullptr;
+    int rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
+    if (rc != CNGI_OK) return rc;
+    cudaError_t e = cudaMallocAsync((void **)&taps, (size_t)n_blocks * W * W * sizeof(CT), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&tapnorm, (size_t)n_blocks * sizeof(double2), st);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(scale, st);
+        if (taps) cudaFreeAsync(taps, st);
+        set_error("aperture_grid: cudaMallocAsync of the tap table failed: %s", cudaGetErrorString(e));
+        return CNGI_ERR_CUDA;
+    }
+    p.scale = scale, p.taps = taps, p.tapnorm = tapnorm;
+    aperture_build_blocks_kernel<T, W><<<(unsigned)n_blocks, W * W < 256 ? W * W : 256, 0, st>>>(p, taps, tapnorm);
+    // work decomposition (as the standard track kernel)
+    int G = (p.chan_mode == CNGI_CHAN_CONTINUUM) ? 8 : 1;
+    if (G > Cfg::ITER) G = Cfg::ITER;
+    while (G > 1 && (Cfg::IPW * G / 2) >= p.n_chan) G >>= 1;
+    int log2G = 0;
+    while ((1 << (log2G + 1)) <= G) ++log2G;
+    p.G = 1 << log2G, p.log2G = log2G;
+    const int spr = Cfg::ITER / p.G;
+    p.n_cspan = (int)ceil_div(p.n_chan, Cfg::IPW * p.G);
+    p.n_pgrp = (int)ceil_div(p.n_pol, PP);
+    const long long per_seg = (long long)p.n_baseline * p.n_cspan * p.n_pgrp;
+    long long n_seg = ceil_div((long long)sm_count() * 16 * 12, per_seg);
+    if (n_seg < 1) n_seg = 1;
+    int seg_len = (int)ceil_div(p.n_time, n_seg);
+    if (seg_len < 8 * spr) seg_len = 8 * spr;
+    seg_len = (int)(ceil_div(seg_len, spr) * spr);
+    p.seg_len = seg_len, p.n_seg = (int)ceil_div(p.n_time, seg_len);
+    p.n_tasks = per_seg * p.n_seg;
+    const int wpb = 4;
+    const long long blocks = ceil_div(p.n_tasks, wpb);
+    if (blocks >= (1LL << 31)) {
+        cudaFreeAsync(taps, st), cudaFreeAsync(tapnorm, st), cudaFreeAsync(scale, st);
+        set_error("aperture_grid: too many work items for one launch");
+        return CNGI_ERR_INVALID;
+    }
+    aperture_track_kernel<T, W, PP><<<(unsigned)blocks, wpb * 32, wpb * Cfg::WARP_BYTES, st>>>(p);
+    e = cudaGetLastError();
+    cudaFreeAsync(taps, st), cudaFreeAsync(tapnorm, st), cudaFreeAsync(scale, st);
+    CNGI_CUDA_TRY(e);
+    return CNGI_OK;
+}
+
+// fallback for supports above 15: offset-major taps, column-parallel lanes, reductions per tap
+template <typename T> static int launch_aperture_rows(ApParams p, cudaStream_t st)
 {
     using CT = typename Cplx<T>::type;
     const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
@@ -317,8 +664,6 @@ template <typename T> static int launch_aperture(ApParams p, cudaStream_t st)
     const int n_cf = p.n_cfb * p.n_cfc * p.n_cfp;
     const long long n_elems = (long long)p.n_field * n_cf * p.n_off_u * p.n_off_v * p.smax * p.smax;
     CNGI_REQUIRE(p.smax <= 32, "aperture_grid: max support above 32 is not supported (got %d)", p.smax);
-    CNGI_REQUIRE(p.n_u < 65536 && p.n_v < 65536 && p.n_off_u < 65536 && p.n_off_v < 65536, "aperture_grid: grid side / oversampling too large");
-    CNGI_REQUIRE(p.n_cfb * p.n_cfc < (1 << 20) && p.n_field < (1 << 11), "aperture_grid: too many convolution functions / fields");
     CNGI_REQUIRE(n_elems * (long long)sizeof(CT) < (8LL << 30), "aperture_grid: offset-major tap table would need %lld MB",
                  n_elems * (long long)sizeof(CT) >> 20);
     double *scale = nullptr;
@@ -350,6 +695,18 @@ template <typename T> static int launch_aperture(ApParams p, cudaStream_t st)
     return CNGI_OK;
 }
 
+template <typename T> static int launch_aperture(ApParams p, cudaStream_t st, int algorithm)
+{
+    CNGI_REQUIRE(p.n_u < 65536 && p.n_v < 65536 && p.os_u < 65000 && p.os_v < 65000, "aperture_grid: grid side / oversampling too large");
+    CNGI_REQUIRE(p.n_cfb * p.n_cfc < (1 << 20) && p.n_field < (1 << 11), "aperture_grid: too many convolution functions / fields");
+    CNGI_REQUIRE((long long)p.n_u * p.n_v < (1LL << 31), "aperture_grid: n_u*n_v overflows int32");
+    const bool track = algorithm != CNGI_ALGO_NAIVE && p.max_support <= 15 && p.n_ic < (1 << 23);
+    if (!track) return launch_aperture_rows<T>(p, st);
+    if (p.max_support <= 7)
+        return p.n_pol == 1 ? launch_aperture_track<T, 8, 1>(p, st) : launch_aperture_track<T, 8, 2>(p, st);
+    return p.n_pol == 1 ? launch_aperture_track<T, 16, 1>(p, st) : launch_aperture_track<T, 16, 2>(p, st);
+}
+
 }  // namespace cngi
 
 extern "C" int cngi_b200_aperture_grid(const cngi_aperture_grid_args *a, void *stream)
@@ -361,7 +718,9 @@ extern "C" int cngi_b200_aperture_grid(const cngi_aperture_grid_args *a, void *s
     if (p.do_psf) p.flag = nullptr;
     const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
     if (total == 0 || p.n_pol == 0) return CNGI_OK;
-    return a->precision == CNGI_F32 ? launch_aperture<float>(p, (cudaStream_t)stream) : launch_aperture<double>(p, (cudaStream_t)stream);
+    const int algo = getenv("CNGI_APERTURE_NAIVE") ? CNGI_ALGO_NAIVE : CNGI_ALGO_AUTO;   // development knob
+    return a->precision == CNGI_F32 ? launch_aperture<float>(p, (cudaStream_t)stream, algo)
+                                    : launch_aperture<double>(p, (cudaStream_t)stream, algo);
 }
 
 extern "C" int cngi_b200_aperture_weight_grid(const cngi_aperture_grid_args *a, void *stream)

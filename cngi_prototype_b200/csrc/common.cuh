@@ -97,6 +97,20 @@ __device__ __forceinline__ void red_add(double2 *p, double2 v)
     atomicAdd(&p->y, v.y);
 }
 
+// ---- packed pair arithmetic: acc(x, y) += a(x, y) * s.  fp32: one FFMA2 (fma.rn.f32x2), fp64: two DFMAs ----------------
+__device__ __forceinline__ void pair_fma(float2 &acc, float2 a, float s)
+{
+    float2 b = make_float2(s, s);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(*reinterpret_cast<unsigned long long *>(&acc))
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+}
+__device__ __forceinline__ void pair_fma(double2 &acc, double2 a, double s)
+{
+    acc.x = fma(a.x, s, acc.x);
+    acc.y = fma(a.y, s, acc.y);
+}
+
 // Adds `val` into base[index] with one reduction per distinct index in the warp when the warp hits at
 // most two distinct indices (continuum imaging: every lane hits the same sum_weight slot).
 __device__ __forceinline__ void warp_grouped_add(double *base, int index, double val, bool active)

@@ -36,11 +36,14 @@ def test_aperture_golden(ap, name):
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_mosaic_vs_oracle(ap, oracle, prec):
-    """Config-3 shape at reduced size: 7 pointings, CF 160x160 (oversampling 10, max support 15), variable supports."""
+@pytest.mark.parametrize("max_support,n_cf_pol", [(15, 1), (7, 1), (17, 1), (11, 2)])
+def test_mosaic_vs_oracle(ap, oracle, prec, max_support, n_cf_pol):
+    """Config-3 shape at reduced size: 7 pointings, CF 160x160 (oversampling 10, max support 15), variable supports.
+    max_support 7 -> 8-wide register windows, 15 -> 16-wide, 17 -> the per-tap fallback kernel; n_cf_pol 2 -> the two
+    polarisations use different convolution functions."""
     from cngi_prototype_b200 import synth
     d = synth.make_vis_set(10, 28, 6, 2, 345e9, 347e9, 300.0, 6.0, seed=31, dtype=prec)
-    gcf = synth.make_mosaic_gcf(d["n_baseline"], 6, 2, n_field=7)
+    gcf = synth.make_mosaic_gcf(d["n_baseline"], 6, 2, n_field=7, max_support=(max_support, max_support), n_cf_pol=n_cf_pol)
     fld = synth.mosaic_field_column(28, d["n_baseline"], gcf["field_id"])
     tol = 1e-12 if prec == "f64" else 1e-5
     for mode in ("cube", "continuum"):
