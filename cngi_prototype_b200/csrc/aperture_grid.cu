@@ -502,23 +502,29 @@ template <typename T, int W, int PP> __global__ void __launch_bounds__(128) aper
 template <typename T> __global__ void __launch_bounds__(256) aperture_weight_bucket_kernel(ApParams p)
 {
     const long long total = (long long)p.n_time * p.n_baseline * p.n_chan;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+    const long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = idx0 < total;   // no early return: the warp aggregates its bucket updates together
+    const long long idx = in_range ? idx0 : 0;
     const int c = (int)(idx % p.n_chan);
     const long long tb = idx / p.n_chan;
     const int b = (int)(tb % p.n_baseline);
-    int field_indx;
+    int field_indx = 0;
     CellPos cp;
-    if (!ap_locate(p, tb, c, field_indx, cp)) return;
+    const bool ok = in_range && ap_locate(p, tb, c, field_indx, cp);
     const int cf_b = (int)p.cf_b_map[b], cf_c = (int)p.cf_c_map[c];
     const int a_chan = ap_chan_of(p, c);
-    for (int ip = 0; ip < p.n_pol; ++ip) {
-        const double w = (double)((const T *)p.weight)[idx * p.n_pol + ip];
-        if (isnan(w) || w == 0.0) continue;
+    for (int ip = 0; ip < p.n_pol; ++ip) {   // uniform trip count
+        double w = 0.0;
+        bool use = ok;
+        if (use) {
+            w = (double)((const T *)p.weight)[idx * p.n_pol + ip];
+            use = !(isnan(w) || w == 0.0);
+        }
         const int cf_p = (int)p.cf_p_map[ip];
         const int a_pol = p.pol_map ? (int)p.pol_map[ip] : ip;
         const long long cf = (((long long)field_indx * p.n_cfb + cf_b) * p.n_cfc + cf_c) * p.n_cfp + cf_p;
-        atomicAdd(p.buckets + (cf * p.n_ic + a_chan) * p.n_ip + a_pol, w);
+        // neighbouring channels of a row share their bucket: one reduction per distinct bucket per warp
+        warp_grouped_add(p.buckets, (int)((cf * p.n_ic + a_chan) * p.n_ip + a_pol), w, use);
     }
 }
 

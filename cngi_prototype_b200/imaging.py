@@ -1,0 +1,165 @@
+"""API layer: make_imaging_weight / make_grid / make_psf / make_image on plain-mapping visibility datasets.
+
+Mirrors the flat, stateless API functions of /root/reference/ngcasa/imaging (make_imaging_weight.py:20,
+make_grid.py, make_psf.py:27, make_image.py:27) and their parameter handling
+(_imaging_utils/_check_imaging_parms.py:22-41,123-146).  xarray and dask do not exist in this environment, so a
+"vis dataset" here is any mapping with
+
+    DATA (n_time, n_baseline, n_chan, n_pol) complex, UVW (n_time, n_baseline, 3), WEIGHT (like DATA, real),
+    optional FLAG (bool/uint8, like DATA), optional IMAGING_WEIGHT, and chan (n_chan,) frequencies in Hz,
+
+with numpy arrays or torch CUDA tensors as values (an xarray Dataset's ``.values`` drop in unchanged).  Where the
+reference builds a lazy dask graph of per-chunk tasks plus a tree-sum (_standard_grid.py:58-98), these functions loop
+over time chunks and accumulate into ONE device-resident grid -- the chunk operators are the same ones the dask graph
+would call (cngi_prototype_b200._standard_grid etc.).  Results are returned as a dict of arrays of the input kind.
+"""
+import copy
+import numbers
+
+import numpy as np
+
+from ._devutil import torch, is_torch, device_of
+from ._gridding_convolutional_kernels import _create_prolate_spheroidal_kernel_1D, correcting_function_1D
+from ._standard_grid import standard_grid
+from ._imaging_weight import (imaging_weight_grid, calculate_briggs_parms,
+                              _standard_imaging_weight_degrid_numpy_wrap)
+from ._fft import grid_to_image
+
+ARCSEC_TO_RAD = np.pi / (3600 * 180)
+
+
+def _check_grid_parms(grid_parms):
+    """Defaults / validation / unit conversion of grid_parms, in place (_check_imaging_parms.py:22-41).
+
+    image_size [nx, ny] ints; cell_size [x, y] arcsec -> radians with x negated; fft_padding in [1, 10] default 1.2;
+    chan_mode 'cube' (default) | 'continuum'; derives image_size_padded = int(fft_padding * image_size).
+    """
+    ok = True
+    def bad(msg):
+        nonlocal ok
+        print("######### Parameter checking error: ", msg)
+        ok = False
+    if "image_size" not in grid_parms or len(grid_parms["image_size"]) != 2:
+        bad("image_size must be a list of two ints")
+    if "cell_size" not in grid_parms or len(grid_parms["cell_size"]) != 2 or \
+            not all(isinstance(x, numbers.Number) for x in grid_parms["cell_size"]):
+        bad("cell_size must be a list of two numbers (arcsec)")
+    grid_parms.setdefault("fft_padding", 1.2)
+    if not (isinstance(grid_parms["fft_padding"], numbers.Number) and 1 <= grid_parms["fft_padding"] <= 10):
+        bad("fft_padding must be a number in [1, 10]")
+    grid_parms.setdefault("chan_mode", "cube")
+    if grid_parms["chan_mode"] not in ("cube", "continuum"):
+        bad("chan_mode must be 'cube' or 'continuum'")
+    if ok:
+        grid_parms["image_size"] = np.array(grid_parms["image_size"]).astype(int)
+        grid_parms.setdefault("image_center", grid_parms["image_size"] // 2)
+        grid_parms["image_size_padded"] = (grid_parms["fft_padding"] * grid_parms["image_size"]).astype(int)
+        grid_parms["image_center"] = np.array(grid_parms["image_center"])
+        grid_parms["cell_size"] = ARCSEC_TO_RAD * np.array(grid_parms["cell_size"], dtype=np.float64)
+        grid_parms["cell_size"][0] = -grid_parms["cell_size"][0]
+    return ok
+
+
+def _check_imaging_weights_parms(parms):
+    """_check_imaging_parms.py:123-146: weighting natural (default) | uniform | briggs | briggs_abs, robust in [-2, 2]."""
+    parms.setdefault("weighting", "natural")
+    if parms["weighting"] not in ("natural", "uniform", "briggs", "briggs_abs"):
+        print("######### Parameter checking error: weighting must be natural, uniform, briggs or briggs_abs")
+        return False
+    if parms["weighting"] in ("briggs", "briggs_abs"):
+        parms.setdefault("robust", 0.5)
+        if not (isinstance(parms["robust"], numbers.Number) and -2 <= parms["robust"] <= 2):
+            print("######### Parameter checking error: robust must be a number in [-2, 2]")
+            return False
+    if parms["weighting"] == "briggs_abs":
+        parms.setdefault("briggs_abs_noise", 1.0)
+    return True
+
+
+def _time_chunks(n_time, time_chunk):
+    step = int(time_chunk) if time_chunk else n_time
+    return [slice(t, min(n_time, t + step)) for t in range(0, n_time, max(step, 1))]
+
+
+def _dev(ds, key, device, dtype=None):
+    x = ds[key]
+    t = x if is_torch(x) else torch.as_tensor(np.ascontiguousarray(x))
+    return t.to(device=device, dtype=dtype) if dtype is not None else t.to(device=device)
+
+
+def _out(t, like_torch):
+    return t if like_torch else t.cpu().numpy()
+
+
+def make_imaging_weight(vis_dataset, imaging_weights_parms, grid_parms, time_chunk=0):
+    """Adds IMAGING_WEIGHT to a copy of the dataset (natural: aliases WEIGHT; uniform / briggs: density grid on the
+    UNPADDED image size, Briggs factors, degrid -- make_imaging_weight.py:95-104,144-247)."""
+    _iw = copy.deepcopy(imaging_weights_parms)
+    _gp = copy.deepcopy(grid_parms)
+    assert _check_imaging_weights_parms(_iw), "######### ERROR: imaging_weights_parms checking failed"
+    out = dict(vis_dataset)
+    if _iw["weighting"] == "natural":
+        out["IMAGING_WEIGHT"] = vis_dataset["WEIGHT"]
+        return out
+    assert _check_grid_parms(_gp), "######### ERROR: grid_parms checking failed"
+    _gp["image_size_padded"] = _gp["image_size"]          # no padding: no FFT follows (:153)
+    _gp.update(oversampling=0, support=1, do_psf=True, complex_grid=False, do_imaging_weight=True)
+    like_torch = is_torch(vis_dataset["WEIGHT"])
+    dev = device_of(vis_dataset["WEIGHT"], vis_dataset["UVW"])
+    w, uvw, freq = _dev(vis_dataset, "WEIGHT", dev), _dev(vis_dataset, "UVW", dev, torch.float64), \
+        _dev(vis_dataset, "chan", dev, torch.float64)
+    density = sw = None
+    for sl in _time_chunks(w.shape[0], time_chunk):        # the reference's chunk loop + tree sum, on one device grid
+        density, sw = imaging_weight_grid(uvw[sl], w[sl], freq, _gp, grid=density, sum_weight=sw)
+    bf = calculate_briggs_parms(density, sw, _iw)
+    iw = _standard_imaging_weight_degrid_numpy_wrap(density, uvw, w, bf, freq, _gp, kernel_side_layout=True)
+    out["IMAGING_WEIGHT"] = _out(iw, like_torch)
+    return out
+
+
+def _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key):
+    _gp = copy.deepcopy(grid_parms)
+    assert _check_grid_parms(_gp), "######### ERROR: grid_parms checking failed"
+    _gp["oversampling"], _gp["support"] = 100, 7          # make_image.py:106-107
+    _gp["complex_grid"], _gp["do_psf"], _gp["do_imaging_weight"] = (not do_psf), do_psf, False
+    cgk_1D = _create_prolate_spheroidal_kernel_1D(_gp["oversampling"], _gp["support"])
+    wkey = weight_key if weight_key in vis_dataset else "WEIGHT"
+    dev = device_of(vis_dataset[wkey], vis_dataset["UVW"])
+    w, uvw, freq = _dev(vis_dataset, wkey, dev), _dev(vis_dataset, "UVW", dev, torch.float64), \
+        _dev(vis_dataset, "chan", dev, torch.float64)
+    vis = None if do_psf else _dev(vis_dataset, "DATA", dev)
+    flag = _dev(vis_dataset, "FLAG", dev, torch.uint8) if (not do_psf and "FLAG" in vis_dataset) else None
+    grid = sw = None
+    for sl in _time_chunks(w.shape[0], time_chunk):
+        grid, sw = standard_grid(None if do_psf else vis[sl], uvw[sl], w[sl], freq, cgk_1D, _gp, do_psf, not do_psf,
+                                 flag=None if flag is None else flag[sl], grid=grid, sum_weight=sw)
+    return grid, sw, _gp
+
+
+def make_grid(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT"):
+    """GRID (u, v, chan, pol) complex and SUM_WEIGHT (chan, pol): make_grid.py:112-137 (stops after gridding)."""
+    like_torch = is_torch(vis_dataset["DATA"])
+    grid, sw, _ = _grid(vis_dataset, grid_parms, False, time_chunk, weight_key)
+    return {"GRID": _out(grid.permute(2, 3, 0, 1), like_torch), "SUM_WEIGHT": _out(sw, like_torch)}
+
+
+def _image(vis_dataset, grid_parms, do_psf, time_chunk, weight_key):
+    grid, sw, gp = _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key)
+    cu, cv = correcting_function_1D(gp["image_size_padded"], gp["image_size"])
+    return grid_to_image(grid, gp["image_size"], sum_weight=sw, corr_u=cu, corr_v=cv), sw
+
+
+def make_psf(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT"):
+    """PSF (l, m, chan, pol) and PSF_SUM_WEIGHT (chan, pol): real PS gridding of the weights, inverse FFT, crop,
+    / sum_weight / PS correcting image (make_psf.py:105-130).  The Gaussian beam fit (fit_gaussian) is out of scope."""
+    like_torch = is_torch(vis_dataset["UVW"])
+    img, sw = _image(vis_dataset, grid_parms, True, time_chunk, weight_key)
+    return {"PSF": _out(img, like_torch), "PSF_SUM_WEIGHT": _out(sw, like_torch)}
+
+
+def make_image(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT"):
+    """IMAGE (l, m, chan, pol) and SUM_WEIGHT (chan, pol): complex PS gridding of DATA * weight (FLAG honoured as NaN,
+    cngi/vis/apply_flags.py:53), inverse FFT, crop, / sum_weight / PS correcting image (make_image.py:106-130)."""
+    like_torch = is_torch(vis_dataset["DATA"])
+    img, sw = _image(vis_dataset, grid_parms, False, time_chunk, weight_key)
+    return {"IMAGE": _out(img, like_torch), "SUM_WEIGHT": _out(sw, like_torch)}

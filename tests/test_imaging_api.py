@@ -1,0 +1,79 @@
+"""API layer (cngi_prototype_b200/imaging.py): parameter handling on CPU, full chains against the oracle on the GPU."""
+import numpy as np
+import pytest
+
+from _util import rel_err
+
+
+def test_check_grid_parms_mirrors_reference_conventions():
+    """_check_imaging_parms.py:22-41: arcsec -> rad, x negated, padded size = int(fft_padding * size), defaults."""
+    from cngi_prototype_b200.imaging import _check_grid_parms, _check_imaging_weights_parms
+    gp = {"image_size": [200, 400], "cell_size": [0.08, 0.08]}
+    assert _check_grid_parms(gp)
+    assert gp["chan_mode"] == "cube" and gp["fft_padding"] == 1.2
+    assert list(gp["image_size_padded"]) == [240, 480]
+    assert list(gp["image_center"]) == [100, 200]
+    rad = 0.08 * np.pi / (3600 * 180)
+    assert gp["cell_size"][0] == -rad and gp["cell_size"][1] == rad
+    assert list(_check_grid_parms_padded([4096, 4096], 1.2)) == [4915, 4915]     # 5 * 983: odd
+    assert not _check_grid_parms({"image_size": [10, 10], "cell_size": [1, 1], "fft_padding": 0.5})
+    assert not _check_grid_parms({"image_size": [10, 10], "cell_size": [1, 1], "chan_mode": "mfs"})
+    iw = {}
+    assert _check_imaging_weights_parms(iw) and iw["weighting"] == "natural"
+    iw = {"weighting": "briggs"}
+    assert _check_imaging_weights_parms(iw) and iw["robust"] == 0.5
+    assert not _check_imaging_weights_parms({"weighting": "briggs", "robust": 3})
+
+
+def _check_grid_parms_padded(size, pad):
+    from cngi_prototype_b200.imaging import _check_grid_parms
+    gp = {"image_size": size, "cell_size": [1, 1], "fft_padding": pad}
+    assert _check_grid_parms(gp)
+    return gp["image_size_padded"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["cube", "continuum"])
+def test_weight_psf_image_chain_vs_oracle(oracle, mode):
+    """make_imaging_weight(briggs) -> make_psf -> make_image on a dict dataset, padded (odd padded size), time-chunked,
+    against the same chain through the oracle."""
+    from cngi_prototype_b200 import synth, imaging
+    d = synth.config_c1(n_time=36, n_chan=6)
+    cell_arcsec = d["cell"] / imaging.ARCSEC_TO_RAD * 1.3    # padded grid covers the same uv range
+    ds = {"DATA": d["vis"], "UVW": d["uvw"], "WEIGHT": d["weight"], "chan": d["freq_chan"]}
+    gp = {"image_size": [150, 135], "cell_size": [cell_arcsec, cell_arcsec], "fft_padding": 1.3, "chan_mode": mode}
+    iwp = {"weighting": "briggs", "robust": 0.5}
+    ds2 = imaging.make_imaging_weight(ds, iwp, gp, time_chunk=10)
+    psf = imaging.make_psf(ds2, gp, time_chunk=7)
+    img = imaging.make_image(ds2, gp, time_chunk=11)
+    # oracle chain
+    g = dict(gp)
+    assert imaging._check_grid_parms(g)
+    assert list(g["image_size_padded"]) == [195, 175]
+    gw = dict(g, image_size_padded=g["image_size"], oversampling=0, support=1, do_psf=True, complex_grid=False,
+              do_imaging_weight=True)
+    rho, sw = oracle._standard_grid_psf_numpy_wrap(d["uvw"], d["weight"], d["freq_chan"], np.ones(1), gw)
+    bf = oracle._calculate_briggs_parms(rho, sw, iwp)
+    iw = oracle._standard_imaging_weight_degrid_numpy_wrap(np.moveaxis(rho, (0, 1), (2, 3)), d["uvw"], d["weight"], bf,
+                                                           d["freq_chan"], gw)
+    m = np.isfinite(iw)
+    assert np.array_equal(np.isnan(ds2["IMAGING_WEIGHT"]), np.isnan(iw))
+    assert np.max(np.abs(ds2["IMAGING_WEIGHT"][m] - iw[m])) <= 1e-12 * np.max(np.abs(iw[m]))
+    cgk = oracle._create_prolate_spheroidal_kernel_1D(100, 7)
+    gi = dict(g, oversampling=100, support=7, do_psf=False, complex_grid=True, do_imaging_weight=False)
+    corr = oracle._remove_padding(oracle._create_prolate_spheroidal_image_2D(g["image_size_padded"]), g["image_size"])
+    gg, ss = oracle._standard_grid_numpy_wrap(d["vis"], d["uvw"], iw, d["freq_chan"], cgk, gi)
+    ref_img = oracle.correct_image(oracle.grid_to_uncorrected_image(gg, g["image_size"]), ss, corr)
+    gpp, sp = oracle._standard_grid_psf_numpy_wrap(d["uvw"], iw, d["freq_chan"], cgk, dict(gi, do_psf=True, complex_grid=False))
+    ref_psf = oracle.correct_image(oracle.grid_to_uncorrected_image(gpp, g["image_size"]), sp, corr)
+    assert img["IMAGE"].shape == ref_img.shape == (150, 135, 6 if mode == "cube" else 1, 2)
+    assert rel_err(img["IMAGE"], ref_img) <= 1e-11 and rel_err(img["SUM_WEIGHT"], ss) <= 1e-12
+    assert rel_err(psf["PSF"], ref_psf) <= 1e-11 and rel_err(psf["PSF_SUM_WEIGHT"], sp) <= 1e-12
+    # the PSF peaks at the image centre with value ~1 after normalisation
+    c = psf["PSF"][75, 67]
+    assert np.all(np.abs(c - 1.0) < 1e-3)
+    # natural weighting aliases WEIGHT, make_grid returns the API-side layout
+    assert imaging.make_imaging_weight(ds, {"weighting": "natural"}, gp)["IMAGING_WEIGHT"] is ds["WEIGHT"]
+    G = imaging.make_grid(ds2, gp)
+    assert G["GRID"].shape == (195, 175, 6 if mode == "cube" else 1, 2)
+    assert rel_err(np.moveaxis(G["GRID"], (2, 3), (0, 1)), gg) <= 1e-12
