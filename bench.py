@@ -123,44 +123,60 @@ def run_reference(a):
 #  GPU arm
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / throttle reasons / power DURING the timed region through NVML in a background thread
+    (an `nvidia-smi -lms` loop in a subprocess perturbs the measured GPU: +30 % step time at 50 ms sampling)."""
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index, period_s=0.1):
+        self.rows, self.gpu, self.period, self._stop, self.thread, self.h = [], gpu_index, period_s, False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:   # no NVML: fall back to one nvidia-smi query after the run
+            self.h, self.err = None, str(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip() != ""]
+            if self.gpu < len(ids) and ids[self.gpu].strip().isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                reasons = get(self.h)
+                power = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.perf_counter(), sm, reasons, power))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self, t_begin, t_end):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t_begin <= t <= t_end and len(r) >= 9] or \
-               [r for (_, r) in self.rows if len(r) >= 9]
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: %s" % getattr(self, "err", "?")]}
+        self._stop = True
+        self.thread.join(timeout=2)
+        nv = self.nv
+        rows = [r for r in self.rows if t_begin <= r[0] <= t_end] or self.rows
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
-        reasons = set()
-        for r in rows:
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
-                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+            return {"sm_mhz": None, "sm_max_mhz": float(self.max_sm), "reasons": ["no samples"]}
+        sm = sorted(r[1] for r in rows)
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(n for n, bit in names.items() if any(r[2] & bit for r in rows))
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.max_sm), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(r[3] for r in rows), "source": "NVML, %.0f ms period" % (self.period * 1e3)}
 
 
 def run_b200(a):
