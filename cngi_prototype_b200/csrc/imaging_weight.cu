@@ -273,6 +273,99 @@ template <typename T, int NP> __global__ void __launch_bounds__(256) iw_degrid_k
     }
 }
 
+// Fast path of A4 for the identity pol_map with 1 or 2 pols: R samples (rows tb, tb + stride, ...) per thread, written as
+// three passes so that all R uvw / weight loads, then all R density gathers, are in flight together -- the plain kernel
+// above is bound by its dependent uvw -> cell -> gather latency chain (63 % long-scoreboard stalls).
+template <typename T, int NP, int R> __global__ void __launch_bounds__(256) iw_degrid_mlp_kernel(IwParams p)
+{
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    const long long rows = (long long)p.n_time * p.n_baseline;
+    const long long row0 = ((long long)blockIdx.x * R) * blockDim.y + threadIdx.y;   // rows row0 + k * blockDim.y
+    if (c >= p.n_chan) return;
+    const double us = p.scale[c], vs = p.scale[p.n_chan + c];
+    const int a_chan = iw_chan_of(p, c);
+    double f0[NP], f1[NP];
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) {
+        f0[ip] = p.bf[a_chan * p.n_ip + ip];
+        f1[ip] = p.bf[((long long)p.n_ic + a_chan) * p.n_ip + ip];
+    }
+    double uu[R], vv[R];
+    T nat[R][NP];
+    bool live[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {   // pass 1: independent loads
+        const long long tb = row0 + (long long)k * blockDim.y;
+        live[k] = tb < rows;
+        uu[k] = vv[k] = 0.0;
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) nat[k][ip] = (T)0;
+        if (live[k]) {
+            uu[k] = p.uvw[tb * 3];
+            vv[k] = p.uvw[tb * 3 + 1];
+            const T *np_ = (const T *)p.weight + (tb * p.n_chan + c) * NP;
+            if (NP == 2) {
+                if (sizeof(T) == 4) {
+                    const float2 w2 = *reinterpret_cast<const float2 *>(np_);
+                    nat[k][0] = (T)w2.x, nat[k][NP - 1] = (T)w2.y;
+                } else {
+                    const double2 w2 = *reinterpret_cast<const double2 *>(np_);
+                    nat[k][0] = (T)w2.x, nat[k][NP - 1] = (T)w2.y;
+                }
+            } else {
+                nat[k][0] = np_[0];
+            }
+        }
+    }
+    double rho[R][NP];
+    bool ok[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {   // pass 2: cells, then the gathers
+        CellPos cp;
+        ok[k] = live[k] && locate_centre(uu[k], vv[k], us, vs, p.n_u, p.n_v, cp);
+        if (ok[k]) ok[k] = stamp_inside(cp.uc, cp.vc, 0, p.n_u, p.n_v);
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) rho[k][ip] = 0.0;
+        if (ok[k]) {
+            const long long cell = cp.uc * p.ds_u + cp.vc * p.ds_v + a_chan * p.ds_c;
+#pragma unroll
+            for (int ip = 0; ip < NP; ++ip) {
+                const double w = (double)nat[k][ip];
+                if (!isnan(w) && w != 0.0) rho[k][ip] = p.density[cell + ip * p.ds_p];   // rho is only used in that case
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {   // pass 3: Briggs division, stores
+        if (!live[k]) continue;
+        const long long tb = row0 + (long long)k * blockDim.y;
+        T res[NP];
+        const double avg = NP == 2 ? __dmul_rn(__dadd_rn((double)nat[k][0], (double)nat[k][NP - 1]), 0.5) : 0.0;   // == /2.0
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) {
+            double iw = 0.0;   // off-grid or NaN uv: 0 (:460,493,502)
+            if (ok[k]) {
+                iw = NP == 2 ? avg : (double)nat[k][ip];   // :508-511
+                const double w = (double)nat[k][ip], r = rho[k][ip];
+                if (!isnan(w) && w != 0.0 && !isnan(r) && r != 0.0) {
+                    const double den = __dadd_rn(__dmul_rn(f0[ip], r), f1[ip]);   // :515-516
+                    iw = sizeof(T) == 4 ? (double)__fdiv_rn((float)iw, (float)den) : __ddiv_rn(iw, den);
+                }
+            }
+            res[ip] = (T)iw;
+        }
+        T *out = (T *)p.out + (tb * p.n_chan + c) * NP;
+        if (NP == 2) {
+            if (sizeof(T) == 4)
+                *reinterpret_cast<float2 *>(out) = make_float2((float)res[0], (float)res[NP - 1]);
+            else
+                *reinterpret_cast<double2 *>(out) = make_double2((double)res[0], (double)res[NP - 1]);
+        } else {
+            out[0] = res[0];
+        }
+    }
+}
+
 }  // namespace cngi
 
 extern "C" int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *a, void *stream)
@@ -396,11 +489,13 @@ extern "C" int cngi_b200_imaging_weight_degrid(const cngi_iw_degrid_args *a, voi
     int rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
     if (rc != CNGI_OK) return rc;
     p.scale = scale;
-#define CNGI_DG_LAUNCH(TT)                                                      \
-    do {                                                                        \
-        if (np == 2) iw_degrid_kernel<TT, 2><<<grid, block, 0, st>>>(p);        \
-        else if (np == 1) iw_degrid_kernel<TT, 1><<<grid, block, 0, st>>>(p);   \
-        else iw_degrid_kernel<TT, 0><<<grid, block, 0, st>>>(p);                \
+    constexpr int kRows = 4;   // samples per thread in the fast path
+    const dim3 grid_mlp((unsigned)ceil_div(rows, (long long)block.y * kRows), (unsigned)gy);
+#define CNGI_DG_LAUNCH(TT)                                                                      \
+    do {                                                                                        \
+        if (np == 2) iw_degrid_mlp_kernel<TT, 2, kRows><<<grid_mlp, block, 0, st>>>(p);         \
+        else if (np == 1) iw_degrid_mlp_kernel<TT, 1, kRows><<<grid_mlp, block, 0, st>>>(p);    \
+        else iw_degrid_kernel<TT, 0><<<grid, block, 0, st>>>(p);                                \
     } while (0)
     if (a->precision == CNGI_F32)
         CNGI_DG_LAUNCH(float);
