@@ -24,42 +24,11 @@
 //      phase 2 (S lanes per item, IPW items per warp): each item consumes its staged samples in order,
 //        broadcast-reading the records, flushing on cell change, then S*PP FMAs per lane.
 //    Only __syncwarp() separates the phases; warps never wait for each other.
-#include "common.cuh"
+#include "standard_grid.cuh"
 #include <cstdlib>
 #include <algorithm>
 
 namespace cngi {
-
-struct StdParams {
-    int n_time, n_baseline, n_chan, n_pol;
-    int n_ic, n_ip, n_u, n_v;
-    const void *vis;
-    const void *weight;
-    const uint8_t *flag;
-    const double *uvw;
-    const double *freq;
-    const int64_t *chan_map;
-    const int64_t *pol_map;
-    const double *cgk;
-    void *grid;
-    double *sum_weight;
-    double dl, dm;
-    int support, oversampling, do_psf, chan_mode;
-    int table_len;
-    // track kernel decomposition
-    int G, log2G, seg_len, n_seg, n_cspan, n_pgrp;
-    int c_lo, c_n;         // channel window handled by this launch (bounds the shared-memory channel table)
-    long long n_tasks;
-    const double *scale;   // naive kernel: [2, n_chan] uv_scale table
-};
-
-__device__ __forceinline__ int chan_of(const StdParams &p, int c)
-{
-    if (p.chan_mode == CNGI_CHAN_CUBE) return c;
-    if (p.chan_mode == CNGI_CHAN_CONTINUUM) return 0;
-    return (int)p.chan_map[c];
-}
-__device__ __forceinline__ int pol_of(const StdParams &p, int ip) { return p.pol_map ? (int)p.pol_map[ip] : ip; }
 
 // ------------------------------------------------------------------------------------------------
 //  naive kernel
@@ -130,35 +99,6 @@ __global__ void __launch_bounds__(256) std_grid_naive_kernel(StdParams p)
 // ------------------------------------------------------------------------------------------------
 //  track kernel
 // ------------------------------------------------------------------------------------------------
-// Packed pair arithmetic.  Accumulators are (re, im) pairs (complex grid) or (pol0, pol1) pairs (real grid), so
-// that on sm_100a every fp32 update is one FFMA2 (fma.rn.f32x2: two FMAs per issue slot, the only way to reach
-// the full FP32 rate with three register operands).  fp64 uses two DFMAs.
-template <typename T> struct Pair;
-template <> struct Pair<float> { using type = float2; };
-template <> struct Pair<double> { using type = double2; };
-
-__device__ __forceinline__ void pk_fma_acc(float2 &c, float2 a, float s)   // c += a * (s, s); accumulator tied in place
-{
-    float2 b = make_float2(s, s);
-    asm("fma.rn.f32x2 %0, %1, %2, %0;"
-        : "+l"(*reinterpret_cast<unsigned long long *>(&c))
-        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
-}
-__device__ __forceinline__ float2 pk_mul(float2 a, float s)
-{
-    float2 b = make_float2(s, s), d;
-    asm("mul.rn.f32x2 %0, %1, %2;"
-        : "=l"(*reinterpret_cast<unsigned long long *>(&d))
-        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
-    return d;
-}
-__device__ __forceinline__ void pk_fma_acc(double2 &c, double2 a, double s)
-{
-    c.x = fma(a.x, s, c.x);
-    c.y = fma(a.y, s, c.y);
-}
-__device__ __forceinline__ double2 pk_mul(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
-
 template <typename T, bool CPLX, int S, int PP> struct TrackCfg {
     // The register window is W x W cells, W = the power of two above the support (8 for S = 7): one spare column /
     // row of hysteresis, so a stamp that jitters by a cell between samples (channels swept back and forth across a
@@ -716,7 +656,15 @@ template <typename T, bool CPLX> static int dispatch(StdParams p, const cngi_std
     int algo = a->algorithm;
     const bool track_ok = (a->support == 3 || a->support == 5 || a->support == 7 || a->support == 9) &&
                           a->oversampling >= 1 && p.table_len <= 8192;
+    const bool shift_ok = shift_kernel_supported(a, p.table_len);
     if (algo == CNGI_ALGO_AUTO) algo = track_ok ? CNGI_ALGO_TRACK : CNGI_ALGO_NAIVE;
+    if (algo == CNGI_ALGO_SHIFT) {
+        if (!shift_ok) {
+            set_error("standard_grid: shift kernel needs support in {3,5,7,9} and tap tables that fit shared memory");
+            return CNGI_ERR_UNSUPPORTED;
+        }
+        return launch_shift(p, a, st);
+    }
     if (algo == CNGI_ALGO_TRACK) {
         if (!track_ok) {
             set_error("standard_grid: track kernel supports support in {3,5,7,9} (got %d)", a->support);

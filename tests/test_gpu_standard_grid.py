@@ -11,7 +11,7 @@ from _util import load_golden, rel_err, same_support
 pytestmark = pytest.mark.gpu
 
 TOL = {"f64": 1e-12, "f32": 1e-5}
-ALGOS = {"naive": 1, "track": 2}
+ALGOS = {"naive": 1, "track": 2, "shift": 3}
 
 
 @pytest.fixture(scope="module")
