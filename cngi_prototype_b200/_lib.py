@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("CNGI_B200_LIB") or os.path.join(HERE, "csrc", "libcng
 
 F32, F64 = 0, 1
 CHAN_GENERAL, CHAN_CUBE, CHAN_CONTINUUM = 0, 1, 2
-ALGO_AUTO, ALGO_NAIVE, ALGO_TRACK, ALGO_SHIFT = 0, 1, 2, 3
+ALGO_AUTO, ALGO_NAIVE, ALGO_TRACK, ALGO_SHIFT, ALGO_WINDOW = 0, 1, 2, 3, 4
 
 i64, i32, f64, vp = C.c_int64, C.c_int32, C.c_double, C.c_void_p
 

@@ -68,5 +68,8 @@ __device__ __forceinline__ double2 pk_mul(double2 a, double s) { return make_dou
 // standard_grid_shift.cu
 bool shift_kernel_supported(const cngi_std_grid_args *a, int table_len);
 int launch_shift(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
+// standard_grid_window.cu
+bool window_kernel_supported(const cngi_std_grid_args *a, int table_len);
+int launch_window(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
 
 }  // namespace cngi

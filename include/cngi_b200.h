@@ -53,7 +53,7 @@ enum { CNGI_F32 = 0, CNGI_F64 = 1 };
    (_standard_grid.py:151-156); GENERAL reads the chan_map array. */
 enum { CNGI_CHAN_GENERAL = 0, CNGI_CHAN_CUBE = 1, CNGI_CHAN_CONTINUUM = 2 };
 /* kernel selection for the standard gridder */
-enum { CNGI_ALGO_AUTO = 0, CNGI_ALGO_NAIVE = 1, CNGI_ALGO_TRACK = 2, CNGI_ALGO_SHIFT = 3 };
+enum { CNGI_ALGO_AUTO = 0, CNGI_ALGO_NAIVE = 1, CNGI_ALGO_TRACK = 2, CNGI_ALGO_SHIFT = 3, CNGI_ALGO_WINDOW = 4 };
 
 int cngi_b200_abi_version(void);
 const char *cngi_b200_last_error(void);

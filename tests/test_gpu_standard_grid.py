@@ -11,7 +11,7 @@ from _util import load_golden, rel_err, same_support
 pytestmark = pytest.mark.gpu
 
 TOL = {"f64": 1e-12, "f32": 1e-5}
-ALGOS = {"naive": 1, "track": 2, "shift": 3}
+ALGOS = {"naive": 1, "track": 2, "shift": 3, "window": 4}
 
 
 @pytest.fixture(scope="module")
@@ -41,7 +41,7 @@ GOLDENS = ["std_single_sample", "std_halfway_edges", "std_cube_sq", "std_cube_od
 
 
 @pytest.mark.parametrize("name", GOLDENS)
-@pytest.mark.parametrize("algo", ["naive", "track"])
+@pytest.mark.parametrize("algo", ["naive", "track", "window"])
 @pytest.mark.parametrize("path", ["host", "device"])
 def test_golden_fp64(sg, name, algo, path):
     import torch
@@ -62,7 +62,7 @@ def test_golden_fp64(sg, name, algo, path):
 
 
 @pytest.mark.parametrize("name", ["std_cube_sq", "std_continuum_odd", "std_halfway_edges"])
-@pytest.mark.parametrize("algo", ["naive", "track"])
+@pytest.mark.parametrize("algo", ["naive", "track", "window"])
 def test_golden_fp32(sg, oracle, name, algo):
     d, gp = load_golden(name)
     vis, w = _cast(d, "f32")
@@ -123,8 +123,9 @@ def test_supports_and_pol_counts(sg, oracle, support, oversampling, n_pol):
         _check(g, s, g_ref, s_ref, TOL["f64"])
 
 
+@pytest.mark.parametrize("algo", ["track", "shift", "window"])
 @pytest.mark.parametrize("chan_group,time_segment", [(1, 0), (2, 7), (4, 16), (8, 1000), (8, 3)])
-def test_invariance_to_work_decomposition(sg, oracle, chan_group, time_segment):
+def test_invariance_to_work_decomposition(sg, oracle, chan_group, time_segment, algo):
     """Result must not depend on how tracks are cut into work items."""
     from cngi_prototype_b200 import synth
     d = synth.make_vis_set(9, 50, 21, 2, 1e9, 1.3e9, 300.0, 150.0, seed=77)
@@ -132,8 +133,8 @@ def test_invariance_to_work_decomposition(sg, oracle, chan_group, time_segment):
     for mode in ("cube", "continuum"):
         gp = synth.grid_parms_for(160, d["cell"], chan_mode=mode)
         g_ref, s_ref = oracle._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp)
-        g, s = sg._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp, algorithm=2,
-                                            chan_group=chan_group, time_segment=time_segment)
+        g, s = sg._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp,
+                                            algorithm=ALGOS[algo], chan_group=chan_group, time_segment=time_segment)
         _check(g, s, g_ref, s_ref, TOL["f64"])
 
 
@@ -144,8 +145,9 @@ def test_many_channels_span_several_channel_windows(sg, oracle):
     cgk = oracle._create_prolate_spheroidal_kernel_1D(100, 7)
     gp = synth.grid_parms_for(64, d["cell"], chan_mode="continuum")
     g_ref, s_ref = oracle._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp)
-    g, s = sg._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp, algorithm=2)
-    _check(g, s, g_ref, s_ref, TOL["f64"])
+    for algo in ("track", "shift", "window"):
+        g, s = sg._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp, algorithm=ALGOS[algo])
+        _check(g, s, g_ref, s_ref, TOL["f64"])
 
 
 def test_random_order_uvw_no_coherence(sg, oracle):
@@ -158,8 +160,9 @@ def test_random_order_uvw_no_coherence(sg, oracle):
     cgk = oracle._create_prolate_spheroidal_kernel_1D(100, 7)
     gp = synth.grid_parms_for(128, d["cell"], chan_mode="continuum")
     g_ref, s_ref = oracle._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp)
-    g, s = sg._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp, algorithm=2)
-    _check(g, s, g_ref, s_ref, TOL["f64"])
+    for algo in ("track", "shift", "window"):
+        g, s = sg._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp, algorithm=ALGOS[algo])
+        _check(g, s, g_ref, s_ref, TOL["f64"])
 
 
 def test_empty_and_all_masked(sg, oracle):
@@ -204,7 +207,7 @@ def test_full_size_config1_properties(sg):
     """BASELINE config 1 at full size (351 bl x 1000 t x 64 ch x 2 pol, 1024^2, S=7, fp64, cube):
     size-independent properties instead of an oracle run:
       * PSF mode: sum over each plane == sum_weight of that plane (both are sum_samples w * sum_taps conv);
-      * track and naive kernels agree to 1e-12 with identical support masks;
+      * track, shift, window and naive kernels agree to 1e-12 with identical support masks;
       * linearity: grid(2*vis) == 2*grid(vis) exactly (power-of-two scaling commutes with every rounding)."""
     import torch
     from cngi_prototype_b200 import synth
@@ -217,15 +220,18 @@ def test_full_size_config1_properties(sg):
     g, s = sg._standard_grid_psf_numpy_wrap(T["uvw"], T["weight"], T["freq_chan"], cgk, gpp)
     tot = g.sum(dim=(2, 3))
     assert float(((tot - s).abs() / s.abs()).max()) < 1e-11
-    gt, st = sg._standard_grid_numpy_wrap(T["vis"], T["uvw"], T["weight"], T["freq_chan"], cgk, gp, algorithm=2)
     gn, sn = sg._standard_grid_numpy_wrap(T["vis"], T["uvw"], T["weight"], T["freq_chan"], cgk, gp, algorithm=1)
-    assert bool(((gt != 0) == (gn != 0)).all())
-    assert float((gt - gn).abs().max() / gn.abs().max()) < 1e-12
-    assert float(((st - sn).abs() / sn.abs()).max()) < 1e-12
+    for algo in ("track", "shift", "window"):
+        gt, st = sg._standard_grid_numpy_wrap(T["vis"], T["uvw"], T["weight"], T["freq_chan"], cgk, gp,
+                                              algorithm=ALGOS[algo])
+        assert bool(((gt != 0) == (gn != 0)).all()), algo
+        assert float((gt - gn).abs().max() / gn.abs().max()) < 1e-12, algo
+        assert float(((st - sn).abs() / sn.abs()).max()) < 1e-12, algo
+        del gt
     del gn
-    g2, _ = sg._standard_grid_numpy_wrap(T["vis"] * 2, T["uvw"], T["weight"], T["freq_chan"], cgk, gp, algorithm=2,
+    g2, _ = sg._standard_grid_numpy_wrap(T["vis"] * 2, T["uvw"], T["weight"], T["freq_chan"], cgk, gp, algorithm=4,
                                          time_segment=1000)
-    g1, _ = sg._standard_grid_numpy_wrap(T["vis"], T["uvw"], T["weight"], T["freq_chan"], cgk, gp, algorithm=2,
+    g1, _ = sg._standard_grid_numpy_wrap(T["vis"], T["uvw"], T["weight"], T["freq_chan"], cgk, gp, algorithm=4,
                                          time_segment=1000)
     # same work decomposition, but atomics may land in a different order: equal within rounding, not bitwise
     assert float((g2 - 2 * g1).abs().max() / g1.abs().max()) < 1e-12

@@ -1,7 +1,7 @@
 #!/bin/bash
-# run on the GPU box: times each tuning variant of the track kernel on config C2 (fp32 continuum + cube)
+# run on the GPU box: tools/run_variants.sh <algo> <variant names...> -- times each tuning variant on config C2 (fp32)
+algo=$1; shift
 for v in "$@"; do
-  lib=variants/libcngi_b200_${v%%:*}.so; blk=${v##*:}
   echo "== $v"
-  CNGI_B200_LIB=$PWD/$lib CNGI_TRACK_BLOCK=$blk timeout 300 python tools/probe_std_grid.py --config c2 --precs f32 --algos 2 2>&1 | grep ms
+  CNGI_B200_LIB=$PWD/variants/libcngi_b200_$v.so timeout 300 python tools/probe_std_grid.py --config c2 --precs f32 --algos $algo 2>&1 | grep ms
 done
