@@ -14,7 +14,7 @@ its neighbours (double-buffered accumulators); the pipeline is drained inside th
 
 Prints ONE JSON line.  `value` is device-resident throughput (inputs in HBM), `e2e` the same step through the
 public API from pinned HOST buffers with H2D/D2H copies inside the timed region, `roofline` the dominant kernel
-(std_grid_track) against the measured HBM peak, `cpu_baseline` the oracle port of the reference on host cores.
+(std_grid_window) against the measured HBM peak, `cpu_baseline` the oracle port of the reference on host cores.
 """
 import argparse
 import json
@@ -356,7 +356,7 @@ def run_b200(a):
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel (std_grid_track), algorithmic bytes per SURVEY.md section 8d:
+    # roofline of the dominant kernel (std_grid_window), algorithmic bytes per SURVEY.md section 8d:
     # n_samples * (8 B vis + 4 B weight) + uvw + grid written once
     peak, peak_src = peaks()
     alg_bytes = n_samples * 12 + a.n_time * d["n_baseline"] * 24 + n_ic * 2 * a.n_uv * a.n_uv * 8
@@ -365,13 +365,13 @@ def run_b200(a):
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("std_grid_track_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("std_grid_dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "std_grid_track_kernel<float,complex,S=7,PP=2>",
+                "traffic": traffic, "kernel": "std_grid_window_kernel<float,complex,S=7,PP=2>",
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src,
-                "note": "the kernel is FP32-issue bound (49 taps x 2 pol x 2 FMA per sample), not HBM bound; see DESIGN.md"}
+                "note": "not HBM bound: the issue slots (62 % active) and the shared-memory pipe limit it; FP32 floor 0.45 ms/launch (49 taps x 2 pol x 2 FMA per sample); see DESIGN.md section 4.1"}
 
     cb = None
     if not a.no_cpu_baseline:

@@ -123,12 +123,12 @@ def main():
         cpu_note="single thread (the oracle degrid is not threaded)")
     grid = torch.zeros((1, 2, 4096, 4096), dtype=torch.complex64, device="cuda")
     gsw = torch.zeros((1, 2), dtype=torch.float64, device="cuda")
-    for algo, name in ((2, "track"), (1, "naive")):
+    for algo, name in ((4, "window"), (2, "track"), (1, "naive")):
         ms = gpu_ms(lambda: _standard_grid.standard_grid(T["vis"], T["uvw"], T["weight"], T["freq_chan"], cgk, gp, False, True,
                                                          grid=grid, sum_weight=gsw, algorithm=algo))
         add("A1 image (%s kernel)" % name, "C2 ALMA-like fp32 4096^2 continuum", d["weight"].size, ms)
     c = cpu_s(lambda: O._standard_grid_numpy_wrap(ds["vis"], ds["uvw"], ds["weight"], ds["freq_chan"], cgk, gp, n_threads=threads))
-    rows[-2].update(cpu_mvis_per_s=round(ds["weight"].size / c / 1e6, 2), cpu_threads=threads)
+    rows[-3].update(cpu_mvis_per_s=round(ds["weight"].size / c / 1e6, 2), cpu_threads=threads)
     # A9 on the 4096^2 continuum grid, default 1.2x padding would be 4915 (5 * 983): time both
     cu, cv = correcting_function_1D([4096, 4096], [3412, 3412])
     ms = gpu_ms(lambda: _fft.grid_to_image(grid, [3412, 3412], sum_weight=gsw, corr_u=cu, corr_v=cv))
