@@ -658,15 +658,9 @@ template <typename T, bool CPLX> static int dispatch(StdParams p, const cngi_std
                           a->oversampling >= 1 && p.table_len <= 8192;
     const bool shift_ok = shift_kernel_supported(a, p.table_len);
     if (algo == CNGI_ALGO_AUTO) {
-        // measured on B200 (tools/probe_std_grid.py, profiles/r01_rows.json): the window kernel wins everywhere except
-        // single-channel fp32 items on a grid far larger than L2 (C2 as a 128-channel cube: 34 GB of planes), where
-        // almost every sample slides the window and the kernel is bound by the reductions; the shift kernel's
-        // per-cell zero test pays there
-        const bool window_ok = window_kernel_supported(a, p.table_len);
-        const double grid_bytes = (double)p.n_ic * p.n_ip * p.n_u * p.n_v * (a->precision == CNGI_F32 ? 4 : 8) * (a->complex_grid ? 2 : 1);
-        const bool big_cube_f32 = a->precision == CNGI_F32 && a->chan_mode != CNGI_CHAN_CONTINUUM && grid_bytes > 4e9;
-        if (window_ok && !big_cube_f32) algo = CNGI_ALGO_WINDOW;
-        else if (shift_ok && big_cube_f32) algo = CNGI_ALGO_SHIFT;
+        // measured on B200 (tools/probe_std_grid.py): the window kernel wins every case tried
+        // (fp32/fp64, continuum/cube, 1024^2 .. 8192^2); the shift and track kernels stay selectable
+        if (window_kernel_supported(a, p.table_len)) algo = CNGI_ALGO_WINDOW;
         else algo = track_ok ? CNGI_ALGO_TRACK : CNGI_ALGO_NAIVE;
     }
     if (algo == CNGI_ALGO_WINDOW) {

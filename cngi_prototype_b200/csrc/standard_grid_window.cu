@@ -3,21 +3,22 @@
 //
 // Same decomposition as the "track" kernel in standard_grid.cu: a work item walks ONE baseline through a time
 // segment (through G neighbouring channels when they share an image plane) and keeps the W x W cells it is under in
-// REGISTERS -- W lanes per item, lane r owns the column u == r (mod W), accumulator j is the row v == j (mod W) --
-// and cells are reduced into the grid with native REDG only when they leave that window.  What changed is
+// REGISTERS -- W lanes per item, lane r owns the grid row v == r (mod W) (v is the contiguous axis of the grid),
+// accumulator j is the column u == j (mod W) -- and cells are reduced into the grid with native REDG only when they
+// leave that window.  What changed is
 // everything around the FMAs; ncu on the track kernel (profiles/r01_std_grid_track_f32_continuum.txt) showed 108
 // instructions per 4-sample warp iteration of which 18 were packed FMAs, and 300-instruction window slides:
 //
 //   * Taps are never staged per sample.  Shared memory holds every tap row the kernel can need, pre-rotated:
 //     tap[rot][off][W] = the S taps for oversampling offset `off`, zero padded to W and rotated by `rot`, so a lane
-//     fetches its u tap with one LDS.32 and its W v-taps (already in accumulator order) with W/4 LDS.128.  Phase 1
+//     fetches its v tap with one LDS.32 and its W u-taps (already in accumulator order) with W/4 LDS.128.  Phase 1
 //     stages {lowest stamp cell, two row byte-offsets} + the weighted data: 32 B per sample, no tap arithmetic.
 //   * Phase 2's fast path is ~25 instructions around the 18 packed FMAs of a sample: one packed compare decides
 //     "the stamp still fits the window" (cell ids are staged as u<<16|v).  Consuming two samples per iteration was
 //     measured too (NS = 2): no faster, the shared-memory pipe is the co-limiter.
-//   * Window slides are cheap and touch no register but the ones that leave: a row leaving the window is reduced
-//     through a static binary dispatch on (v mod W) -- 3 branches, 2 REDG, 2 clears -- and a column leaving reduces
-//     the lane's W accumulators with W precomputed row addresses.
+//   * Window slides are cheap: a column leaving the window is reduced by all W lanes through a static binary
+//     dispatch on (u mod W) -- 3 branches, 2 REDG covering W consecutive cells -- and a grid row leaving reduces one
+//     lane's W accumulators; accumulators are only READ there and cleared afterwards with selects.
 //   * Raw samples are prefetched one round ahead with cp.async into per-warp shared-memory buffers instead of
 //     registers (the register file is what limits this kernel to 16 warps per SM), lanes in channel order so that
 //     the global and shared sides of every copy are contiguous.
@@ -278,55 +279,60 @@ std_grid_window_kernel(StdParams p)
         for (int j = 0; j < W; ++j)
 #pragma unroll
             for (int n = 0; n < NV; ++n) acc[j][n].x = acc[j][n].y = (T)0;
-        // register window: columns [lo_u, lo_u + W), rows [lo_v, lo_v + W), always inside the grid; wkey = lo_u<<16 | lo_v
-        int lo_u = 0, lo_v = 0, wkey = kNoWindowKey;
+        // Register window, always inside the grid: grid rows [lo_a, lo_a + W) along v -- the LANE axis, lane r owns the
+        // row v == r (mod W) -- and columns [lo_b, lo_b + W) along u -- the ACCUMULATOR axis, accumulator j is the column
+        // u == j (mod W).  v is the contiguous axis of the grid, so when a column leaves the window the W lanes of the item
+        // reduce W consecutive cells (one coalesced 64-byte request per pol instead of W strided sectors): the reductions
+        // are what bounds cube gridding on grids far larger than L2 (~50 G reduction sectors/s measured at L2).
+        // wkey = lo_a<<16 | lo_b.
+        int lo_a = 0, lo_b = 0, wkey = kNoWindowKey;
 
-        auto my_column = [&]() { return lo_u + ((r2 - lo_u) & (W - 1)); };   // the u in the window with u == r2 (mod W)
+        auto my_line = [&]() { return lo_a + ((r2 - lo_a) & (W - 1)); };   // the v in the window with v == r2 (mod W)
         // Reductions only READ the accumulators; they are cleared afterwards with selects outside any divergent
         // region (writes under divergence make ptxas copy the whole accumulator file around the branch).
-        auto red_column = [&]() {   // all W cells of this lane's column; accumulator j is the row v == j (mod W)
-            const int m = lo_v & (W - 1);
-            const int cell0 = my_column() * p.n_v + (lo_v - m);
+        auto red_lane = [&]() {   // all W cells of this lane's grid row; accumulator j is the column u == j (mod W)
+            const int m = lo_b & (W - 1);
+            const int cell0 = (lo_b - m) * p.n_v + my_line();
             static_for<0, W>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                const int cell = cell0 + j + ((j < m) ? W : 0);
+                const int cell = cell0 + (j + ((j < m) ? W : 0)) * p.n_v;
 #pragma unroll
                 for (int n = 0; n < NV; ++n)
                     red_pair(gplane[CPLX ? n : 2 * n], cell, acc[j][n], gplane[CPLX ? n : (2 * n + 1 < PP ? 2 * n + 1 : 0)]);
             });
         };
-        auto red_row = [&](int v) {   // row v of the window: every lane reduces its cell of that row
-            const int cell = my_column() * p.n_v + v;
-            static_dispatch<0, W>(v & (W - 1), [&](auto jc) {
+        auto red_column = [&](int u) {   // column u of the window: every lane reduces its cell of it (consecutive v)
+            const int cell = u * p.n_v + my_line();
+            static_dispatch<0, W>(u & (W - 1), [&](auto jc) {
                 constexpr int j = decltype(jc)::value;
 #pragma unroll
                 for (int n = 0; n < NV; ++n)
                     red_pair(gplane[CPLX ? n : 2 * n], cell, acc[j][n], gplane[CPLX ? n : (2 * n + 1 < PP ? 2 * n + 1 : 0)]);
             });
         };
-        // make the stamp whose lowest cell is (need_u, need_v) fit the window, sliding it by the least amount
-        auto slide = [&](int need_u, int need_v) {
-            int new_u = need_u, new_v = need_v;
+        // make the stamp whose lowest cell is (v, u) = (need_a, need_b) fit the window, sliding it by the least amount
+        auto slide = [&](int need_a, int need_b) {
+            int new_a = need_a, new_b = need_b;
             if (wkey != kNoWindowKey) {
-                const int du = need_u - lo_u, dv = need_v - lo_v;
-                new_u = du < 0 ? need_u : (du > SPARE ? need_u - SPARE : lo_u);
-                new_v = dv < 0 ? need_v : (dv > SPARE ? need_v - SPARE : lo_v);
+                const int da = need_a - lo_a, db = need_b - lo_b;
+                new_a = da < 0 ? need_a : (da > SPARE ? need_a - SPARE : lo_a);
+                new_b = db < 0 ? need_b : (db > SPARE ? need_b - SPARE : lo_b);
             }
-            new_u = min(new_u, p.n_u - W);   // keep the spare rows / columns inside the grid
-            new_v = min(new_v, p.n_v - W);
+            new_a = min(new_a, p.n_v - W);   // keep the spare rows / columns inside the grid
+            new_b = min(new_b, p.n_u - W);
             if (wkey != kNoWindowKey) {
-                const int u = my_column();
-                const int sh = new_v - lo_v;
-                const bool whole = (u < new_u) || (u >= new_u + W) || (sh >= W) || (sh <= -W);   // my column leaves
-                // rows at window positions [lower, upper) leave
+                const int a = my_line();
+                const int sh = new_b - lo_b;
+                const bool whole = (a < new_a) || (a >= new_a + W) || (sh >= W) || (sh <= -W);   // my grid row leaves
+                // columns at window positions [lower, upper) leave
                 const int lower = whole ? 0 : (sh > 0 ? 0 : W + sh);
                 const int upper = whole ? W : (sh > 0 ? sh : W);
                 if (whole) {
-                    red_column();
+                    red_lane();
                 } else {
-                    for (int pos = lower; pos < upper; ++pos) red_row(lo_v + pos);
+                    for (int pos = lower; pos < upper; ++pos) red_column(lo_b + pos);
                 }
-                const int m = lo_v & (W - 1);
+                const int m = lo_b & (W - 1);
 #pragma unroll
                 for (int j = 0; j < W; ++j) {
                     const int pos = (j - m) & (W - 1);
@@ -338,8 +344,8 @@ std_grid_window_kernel(StdParams p)
                     }
                 }
             }
-            lo_u = new_u, lo_v = new_v;
-            wkey = (new_u << 16) | new_v;
+            lo_a = new_a, lo_b = new_b;
+            wkey = (new_a << 16) | new_b;
         };
 
         // ---- raw samples: cp.async into the warp's shared-memory buffers, one round ahead -----------------
@@ -465,11 +471,12 @@ std_grid_window_kernel(StdParams p)
 #pragma unroll
                     for (int ip = 0; ip < PP; ++ip) sw_acc[ip] += wsel[ip] * norm;
                     const int need_u = cp.uc - HALF, need_v = cp.vc - HALF;
-                    // {packed lowest stamp cell, address of the u tap row, address of the (rotated) v tap row,
-                    //  byte offset of the stamp's first column inside a rotated row}
-                    idx = make_int4((need_u << 16) | need_v, (int)tap_s + uo * ROW_BYTES,
-                                    (int)tap_s + (need_v & (W - 1)) * rot_stride + vo * ROW_BYTES,
-                                    (need_u & (W - 1)) * (int)sizeof(T));
+                    // {lowest stamp cell packed v<<16|u, address of the v tap row (the lane picks its own tap from it),
+                    //  address of the u tap row rotated into accumulator order, byte offset of the stamp's first row
+                    //  inside a rotated row}
+                    idx = make_int4((need_v << 16) | need_u, (int)tap_s + vo * ROW_BYTES,
+                                    (int)tap_s + (need_u & (W - 1)) * rot_stride + uo * ROW_BYTES,
+                                    (need_v & (W - 1)) * (int)sizeof(T));
                 }
             }
             if (sizeof(T) == 4) {
@@ -548,7 +555,7 @@ std_grid_window_kernel(StdParams p)
             consume();
             __syncwarp();
         }
-        if (wkey != kNoWindowKey) red_column();
+        if (wkey != kNoWindowKey) red_lane();
 
         // ---- sum_weight: lanes that share a channel reduce first, then one reduction per image plane -------
         const int span = IPW * G;   // lanes L and L + span handle the same channel

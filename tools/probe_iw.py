@@ -1,0 +1,25 @@
+"""Quick device-timing probe of the imaging-weight kernels on config C2 (development tool)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+from cngi_prototype_b200 import synth, _imaging_weight  # noqa: E402
+from tools.probe_std_grid import timeit  # noqa: E402
+
+d = synth.config_c2(n_time=500, dtype="f32")
+T = {k: torch.as_tensor(d[k]).cuda() for k in ("uvw", "weight", "freq_chan")}
+gpw = synth.grid_parms_for(4096, d["cell"], chan_mode="continuum", support=1, oversampling=0, do_psf=True,
+                           complex_grid=False, do_imaging_weight=True)
+rho = torch.zeros((1, 2, 4096, 4096), dtype=torch.float64, device="cuda")
+rsw = torch.zeros((1, 2), dtype=torch.float64, device="cuda")
+for fpo in (True, False):
+    for rep in range(2):
+        rho.zero_(), rsw.zero_()
+        print("iw_grid first_pol_only=%s" % fpo, timeit(lambda: _imaging_weight.imaging_weight_grid(
+            T["uvw"], T["weight"], T["freq_chan"], gpw, grid=rho, sum_weight=rsw, first_pol_only=fpo)), flush=True)
+bf = _imaging_weight.calculate_briggs_parms(rho, rsw, dict(weighting="briggs", robust=0.5))
+print("degrid", timeit(lambda: _imaging_weight._standard_imaging_weight_degrid_numpy_wrap(
+    rho, T["uvw"], T["weight"], bf, T["freq_chan"], gpw, kernel_side_layout=True)))
