@@ -221,7 +221,7 @@ template <typename T, int LW> __global__ void __launch_bounds__(256) aperture_gr
 // and keeps W accumulators (rows v == s (mod W)) per polarisation; cells are reduced into the grid (REDG) only when
 // they leave the window.  W = 16 covers supports up to 15 with one spare column / row of hysteresis.
 // The CF is not separable, so taps are not staged: every lane fetches its W taps per sample straight from the
-// block-major tap table tapsW[block][iv][iu] (block = (field, cf, u offset, v offset), zero outside the CF's own
+// block-major tap table tapsW[block][iu][iv] (block = (field, cf, u offset, v offset), zero outside the CF's own
 // support), where the W lanes of an item read one contiguous 128-byte row per load.  The per-block tap sum needed by
 // sum_weight (_aperture_grid.py:508-511) is tabulated once per call (tapnorm).
 template <typename T, int W> __global__ void aperture_build_blocks_kernel(ApParams p, typename Cplx<T>::type *tapsW, double2 *tapnorm)
@@ -239,7 +239,7 @@ template <typename T, int W> __global__ void aperture_build_blocks_kernel(ApPara
     const int shalf = p.smax / 2;
     double sre = 0.0, sim = 0.0;
     for (int e = threadIdx.x; e < W * W; e += blockDim.x) {
-        const int iv_t = e / W, iu_t = e % W;       // [iv][iu]: the lanes of an item (iu) are contiguous
+        const int iu_t = e / W, iv_t = e % W;       // [iu][iv]: the lanes of an item (iv) are contiguous
         const int iu = iu_t - shalf, iv = iv_t - shalf;
         CT out;
         out.x = out.y = (T)0;
@@ -326,7 +326,9 @@ template <typename T, int W, int PP> __global__ void __launch_bounds__(128) aper
     for (int ip = 0; ip < PP; ++ip) sw_acc[ip] = 0.0;
     long long carry_key = -1;
 
-    // ---- phase-2 role: lane <-> (item, u residue mod W) ----
+    // ---- phase-2 role: lane <-> (item, v residue mod W): lane r owns the grid row v == r (mod W) of the register window
+    // (v is the contiguous grid axis, so a column leaving the window is reduced by W lanes into W consecutive cells),
+    // accumulator j is the column u == j (mod W) ----
     const int k2 = lane / W, r2 = lane & (W - 1);
     int apol[PP];
 #pragma unroll
@@ -351,11 +353,11 @@ template <typename T, int W, int PP> __global__ void __launch_bounds__(128) aper
             }
         }
     };
-    auto my_column = [&]() { return lo_u + ((r2 - lo_u) & (W - 1)); };
-    auto flush_column = [&]() {
-        const int u = my_column();
+    auto my_row = [&]() { return lo_v + ((r2 - lo_v) & (W - 1)); };
+    auto flush_row = [&]() {
+        const int v = my_row();
 #pragma unroll
-        for (int j = 0; j < W; ++j) flush_one(j, u, lo_v + ((j - lo_v) & (W - 1)));
+        for (int j = 0; j < W; ++j) flush_one(j, lo_u + ((j - lo_u) & (W - 1)), v);
     };
 
     for (int t0 = t_lo; t0 < t_hi; t0 += spr) {
@@ -444,15 +446,15 @@ template <typename T, int W, int PP> __global__ void __launch_bounds__(128) aper
                 else if (need_u + S > lo_u + W) new_u = need_u + S - W;
                 if (new_plane || need_v < lo_v) new_v = need_v;
                 else if (need_v + S > lo_v + W) new_v = need_v + S - W;
-                const int u = my_column();
-                const bool col_leaves = new_plane ? (cur_plane >= 0) : (u < new_u || u >= new_u + W);
-                if (col_leaves) {
-                    flush_column();
-                } else if (new_v != lo_v) {
+                const int v = my_row();
+                const bool row_leaves = new_plane ? (cur_plane >= 0) : (v < new_v || v >= new_v + W);
+                if (row_leaves) {
+                    flush_row();
+                } else if (new_u != lo_u) {
 #pragma unroll
                     for (int j = 0; j < W; ++j) {
-                        const int v = lo_v + ((j - lo_v) & (W - 1));
-                        if (v < new_v || v >= new_v + W) flush_one(j, u, v);
+                        const int u = lo_u + ((j - lo_u) & (W - 1));
+                        if (u < new_u || u >= new_u + W) flush_one(j, u, v);
                     }
                 }
                 if (new_plane) {
@@ -462,10 +464,10 @@ template <typename T, int W, int PP> __global__ void __launch_bounds__(128) aper
                 }
                 lo_u = new_u, lo_v = new_v;
             }
-            // taps: slot s of this lane's column <-> stamp row q = (s - bv) mod W, stamp column qu = (r2 - bu) mod W
+            // taps: slot s of this lane's row <-> stamp column qu = (s - bu) mod W, stamp row q = (r2 - bv) mod W
             const int bu = (uc - shalf) & (W - 1), bv = (vc - shalf) & (W - 1);
-            const CT *tp = (const CT *)p.taps + (long long)idx.z * (W * W) + ((r2 - bu) & (W - 1));
-            const CT *tp1 = (const CT *)p.taps + (long long)idx.w * (W * W) + ((r2 - bu) & (W - 1));
+            const CT *tp = (const CT *)p.taps + (long long)idx.z * (W * W) + ((r2 - bv) & (W - 1));
+            const CT *tp1 = (const CT *)p.taps + (long long)idx.w * (W * W) + ((r2 - bv) & (W - 1));
             const bool same_cf = idx.z == idx.w;
             CT d0[PP], d1[PP];   // acc += t.x * (dr, di) + t.y * (-di, dr)
 #pragma unroll
@@ -475,7 +477,7 @@ template <typename T, int W, int PP> __global__ void __launch_bounds__(128) aper
             }
 #pragma unroll
             for (int sl = 0; sl < W; ++sl) {
-                const int row = ((sl - bv) & (W - 1)) * W;
+                const int row = ((sl - bu) & (W - 1)) * W;
                 CT tap = tp[row];
 #pragma unroll
                 for (int ip = 0; ip < PP; ++ip) {
@@ -487,7 +489,7 @@ template <typename T, int W, int PP> __global__ void __launch_bounds__(128) aper
         }
         __syncwarp();
     }
-    if (cur_plane >= 0) flush_column();
+    if (cur_plane >= 0) flush_row();
 
     const int span = IPW * G;
 #pragma unroll
