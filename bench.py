@@ -65,6 +65,26 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def red_peak(footprint_bytes):
+    """Reduction ("atomic") ceiling of this GPU, measured live: G 32-byte sectors/s of REDG.E.ADD.F32x2 in the shape the
+    gridding kernel flushes with (8 lanes on 64 contiguous bytes, scattered over a buffer as large as the uv-grid)."""
+    import torch
+    from cngi_prototype_b200 import _lib
+    from cngi_prototype_b200._devutil import ptr, stream
+    n_cells = int(footprint_bytes // 8)
+    buf = torch.zeros(n_cells, dtype=torch.complex64, device="cuda")
+    blocks, per_thread, best = 148 * 16, 256, float("inf")
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(_lib.lib().cngi_b200_microbench_red(ptr(buf), n_cells, 1, blocks, per_thread, stream()), "microbench_red")
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del buf
+    return blocks * 8 * per_thread * 8 / (best * 1e-3) / 1e9
+
+
 # ------------------------------------------------------------------------------------------------------
 #  CPU arm: the oracle port of the reference's numba loops on the host cores
 # ------------------------------------------------------------------------------------------------------
@@ -361,13 +381,24 @@ def run_b200(a):
     peak, peak_src = peaks()
     alg_bytes = n_samples * 12 + a.n_time * d["n_baseline"] * 24 + n_ic * 2 * a.n_uv * a.n_uv * 8
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, red_sectors = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("std_grid_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic, red_sectors = tj.get("std_grid_dram_bytes_per_launch"), tj.get("std_grid_red_sectors_per_launch")
         except Exception:
             traffic = None
+    # the second ceiling BASELINE.json's metric names: reductions into the grid (sectors per launch from the ncu
+    # capture of this kernel -- a property of the input and the window, not of timing -- over the live kernel time)
+    atomic = None
+    if red_sectors and a.n_time == 500 and a.n_chan == 128 and a.chan_mode == "continuum":
+        rp = red_peak(n_ic * 2 * a.n_uv * a.n_uv * 8)
+        atomic = {"achieved": red_sectors / (kern_ms * 1e-3) / 1e9, "peak": rp, "unit": "Gsector/s",
+                  "frac": red_sectors / (kern_ms * 1e-3) / 1e9 / rp, "sectors_per_launch": int(red_sectors),
+                  "note": "REDG.E.ADD.F32x2 sectors per launch (ncu l1tex__t_sectors_pipe_lsu_mem_global_op_red, "
+                          "profiles/r01_traffic.json) over the live kernel time; peak = cngi_b200_microbench_red, 8 lanes x "
+                          "8 B contiguous, footprint = the uv-grid, measured in this run"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "std_grid_window_kernel<float,complex,S=7,PP=2>",
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src,
@@ -385,7 +416,8 @@ def run_b200(a):
                        "parallelism": ("time-sharded x%d, NCCL all-reduce(density plane 0) + reduce(grid), overlapped across steps" % world) if world > 1 else "single GPU"},
             "vis_tap_per_s": world * n_samples * SUPPORT * SUPPORT / (ms_step * 1e-3),
             "gridding_kernel_vis_per_s": n_samples / (kern_ms * 1e-3),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * a.steps, "roofline": roofline, "cpu_baseline": cb}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * a.steps, "roofline": roofline, "atomic_roofline": atomic,
+            "cpu_baseline": cb}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

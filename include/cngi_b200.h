@@ -56,6 +56,11 @@ enum { CNGI_CHAN_GENERAL = 0, CNGI_CHAN_CUBE = 1, CNGI_CHAN_CONTINUUM = 2 };
 enum { CNGI_ALGO_AUTO = 0, CNGI_ALGO_NAIVE = 1, CNGI_ALGO_TRACK = 2, CNGI_ALGO_SHIFT = 3, CNGI_ALGO_WINDOW = 4 };
 
 int cngi_b200_abi_version(void);
+/* Measurement aid, not on the product path: issues blocks*256*per_thread REDG.E.ADD.F32x2 reductions into
+   buf[0 .. n_cells) (8-byte cells).  pattern 0 = every lane its own 32-byte sector, 1 = groups of 8 lanes on 64
+   contiguous bytes, 2 = a warp on 256 contiguous bytes.  bench.py times it to obtain the reduction ("atomic")
+   roofline the gridders' flush traffic is compared with (no published peak exists). */
+int cngi_b200_microbench_red(void *buf, int64_t n_cells, int32_t pattern, int32_t blocks, int32_t per_thread, void *stream);
 const char *cngi_b200_last_error(void);
 /* 0 if a compute-capability 10.x device is current/available; CNGI_ERR_NO_DEVICE otherwise. */
 int cngi_b200_check_device(void);

@@ -235,3 +235,15 @@ def test_full_size_config1_properties(sg):
                                          time_segment=1000)
     # same work decomposition, but atomics may land in a different order: equal within rounding, not bitwise
     assert float((g2 - 2 * g1).abs().max() / g1.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("pattern", [0, 1, 2])
+def test_reduction_microbench_counts(pattern):
+    """cngi_b200_microbench_red (the atomic-roofline probe of bench.py) issues exactly blocks*256*per_thread reductions."""
+    import torch
+    from cngi_prototype_b200 import _lib
+    from cngi_prototype_b200._devutil import ptr, stream
+    buf = torch.zeros(1 << 16, dtype=torch.complex64, device="cuda")
+    _lib.check(_lib.lib().cngi_b200_microbench_red(ptr(buf), buf.numel(), pattern, 7, 5, stream()), "microbench_red")
+    total = buf.sum().cpu().item()
+    assert total.real == 7 * 256 * 5 and total.imag == -7 * 256 * 5
