@@ -182,6 +182,78 @@ class ContinuumPipeline:
         return iw
 
 
+def cube_layout(rank, world_size, time_split=1):
+    """Ranks form a (channel group) x (time part) grid, time part fastest: returns (chan_group, n_chan_groups,
+    time_part, root_rank_of_the_group).  time_split = 1 is pure channel sharding (no exchange at all)."""
+    assert world_size % time_split == 0, "time_split must divide the world size"
+    cg = rank // time_split
+    return cg, world_size // time_split, rank % time_split, cg * time_split
+
+
+def make_time_groups(world_size, time_split):
+    """One process group per channel group (the ranks that split its samples along time).  Collective: every rank
+    must call it, with the same arguments."""
+    if time_split <= 1 or world_size <= 1:
+        return None
+    groups = [dist.new_group(list(range(g * time_split, (g + 1) * time_split))) for g in range(world_size // time_split)]
+    return groups
+
+
+def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image_out=None):
+    """Channel-sharded cube imaging with bounded memory (BASELINE config 5; synthesis_imaging_cube.py:105-124,171-220).
+
+    Every rank holds (or can slice) the full sample arrays `d` = {vis, uvw, weight, freq_chan[, flag]}.  The image
+    channels are split in contiguous blocks over the channel groups (cube_layout); a group's root owns its planes
+    end to end: for each chunk of `chan_chunk` channels (0 = the whole block) the group grids the chunk into ONE
+    reusable grid buffer, the `time_split` ranks of the group sum their partial grids + sum_weight onto the root
+    (the NCCL grid reduce; skipped when time_split == 1: no exchange is needed then), and the root transforms,
+    crops and corrects the chunk (ops.to_image) into its slab of the output cube.  Peak memory is one chunk of
+    padded grids, not the cube.
+
+    ops.standard_grid(vis, uvw, w, freq, cgk, gp, grid=, sum_weight=[, flag=]) accumulates into the buffers;
+    ops.zeros(shape, complex) allocates; ops.to_image(grid, sum_weight, gp) returns (l, m, chan, pol).
+    Returns (image (l, m, n_chan_owned, pol) or None on non-root ranks, sum_weight (n_chan_owned, pol) or None,
+    (chan_lo, chan_hi)).
+    """
+    rank, ws = world()
+    cg, n_cg, tp, root = cube_layout(rank, ws, time_split)
+    n_time, n_chan = d["uvw"].shape[0], d["freq_chan"].shape[0]
+    clo, chi = shard_range(n_chan, cg, n_cg)
+    tlo, thi = shard_range(n_time, tp, time_split)
+    n_pol = d["weight"].shape[3]
+    n_u, n_v = (int(x) for x in gp["image_size_padded"])
+    step = int(chan_chunk) if chan_chunk else max(chi - clo, 1)
+    gpc = dict(gp, chan_mode="cube")
+    grid = ops.zeros((min(step, max(chi - clo, 1)), n_pol, n_u, n_v), True)
+    gsw = ops.zeros((grid.shape[0], n_pol), False)
+    image, sum_weight = image_out, None
+    group = groups[cg] if groups else None
+    for c0 in range(clo, chi, step):
+        c1 = min(chi, c0 + step)
+        g, s = grid[:c1 - c0], gsw[:c1 - c0]
+        g.zero_()
+        s.zero_()
+        kw = {}
+        if d.get("flag") is not None:
+            kw["flag"] = d["flag"][tlo:thi, :, c0:c1]
+        if thi > tlo:
+            ops.standard_grid(d["vis"][tlo:thi, :, c0:c1], d["uvw"][tlo:thi], d["weight"][tlo:thi, :, c0:c1],
+                              d["freq_chan"][c0:c1], cgk, gpc, grid=g, sum_weight=s, **kw)
+        if group is not None:
+            dist.reduce(_as_real(g), root, group=group)
+            dist.reduce(s, root, group=group)
+        if rank == root:
+            img = ops.to_image(g, s, gpc)
+            if image is None:
+                image = ops.zeros(tuple(img.shape[:2]) + (chi - clo, n_pol), False).to(img.dtype)
+                sum_weight = ops.zeros((chi - clo, n_pol), False)
+            elif sum_weight is None:
+                sum_weight = ops.zeros((chi - clo, n_pol), False)
+            image[:, :, c0 - clo:c1 - clo] = img
+            sum_weight[c0 - clo:c1 - clo] = s
+    return (image, sum_weight, (clo, chi)) if rank == root else (None, None, (clo, chi))
+
+
 def cuda_ops():
     """The product operators (libcngi_b200.so through the Python mirror) in the shape continuum_imaging_step expects."""
     from ._standard_grid import standard_grid
@@ -191,8 +263,19 @@ def cuda_ops():
     def degrid(density, uvw, w, bf, freq, gp_iw):
         return _standard_imaging_weight_degrid_numpy_wrap(density, uvw, w, bf, freq, gp_iw, kernel_side_layout=True)
 
-    def grid(vis, uvw, w, freq, cgk, gp, grid=None, sum_weight=None):
-        return standard_grid(vis, uvw, w, freq, cgk, gp, False, True, grid=grid, sum_weight=sum_weight)
+    def grid(vis, uvw, w, freq, cgk, gp, grid=None, sum_weight=None, flag=None):
+        return standard_grid(vis, uvw, w, freq, cgk, gp, False, True, grid=grid, sum_weight=sum_weight, flag=flag)
+
+    def zeros(shape, is_complex, precision="f32"):
+        dt = {("f32", True): torch.complex64, ("f32", False): torch.float64,
+              ("f64", True): torch.complex128, ("f64", False): torch.float64}[(precision, bool(is_complex))]
+        return torch.zeros(shape, dtype=dt, device="cuda")
+
+    def to_image(g, s, gp):
+        from ._fft import grid_to_image
+        from ._gridding_convolutional_kernels import correcting_function_1D
+        cu, cv = correcting_function_1D(gp["image_size_padded"], gp["image_size"])
+        return grid_to_image(g, gp["image_size"], sum_weight=s, corr_u=cu, corr_v=cv)
 
     return SimpleNamespace(imaging_weight_grid=imaging_weight_grid, briggs=calculate_briggs_parms, degrid=degrid,
-                           standard_grid=grid)
+                           standard_grid=grid, zeros=zeros, to_image=to_image)

@@ -143,23 +143,37 @@ def make_grid(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT"
     return {"GRID": _out(grid.permute(2, 3, 0, 1), like_torch), "SUM_WEIGHT": _out(sw, like_torch)}
 
 
-def _image(vis_dataset, grid_parms, do_psf, time_chunk, weight_key):
+def _image(vis_dataset, grid_parms, do_psf, time_chunk, weight_key, chan_chunk=0):
+    """grid -> ifft -> crop -> / sum_weight / PS image.  chan_chunk > 0 (cube mode only): the image channels are
+    processed `chan_chunk` at a time, so that the padded uv-grids of one chunk, not of the whole cube, are resident
+    (the per-channel independence synthesis_imaging_cube.py:105-124 exploits with dask chunks)."""
+    n_chan = int(vis_dataset["chan"].shape[0])
+    if chan_chunk and grid_parms.get("chan_mode", "cube") == "cube" and chan_chunk < n_chan:
+        images, sws = [], []
+        for c0 in range(0, n_chan, int(chan_chunk)):
+            sl = slice(c0, min(n_chan, c0 + int(chan_chunk)))
+            sub = {k: (v[sl] if k == "chan" else (v[:, :, sl] if getattr(v, "ndim", 0) == 4 else v))
+                   for k, v in vis_dataset.items()}
+            img, sw = _image(sub, grid_parms, do_psf, time_chunk, weight_key)
+            images.append(img)
+            sws.append(sw)
+        return torch.cat(images, dim=2), torch.cat(sws, dim=0)
     grid, sw, gp = _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key)
     cu, cv = correcting_function_1D(gp["image_size_padded"], gp["image_size"])
     return grid_to_image(grid, gp["image_size"], sum_weight=sw, corr_u=cu, corr_v=cv), sw
 
 
-def make_psf(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT"):
+def make_psf(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT", chan_chunk=0):
     """PSF (l, m, chan, pol) and PSF_SUM_WEIGHT (chan, pol): real PS gridding of the weights, inverse FFT, crop,
     / sum_weight / PS correcting image (make_psf.py:105-130).  The Gaussian beam fit (fit_gaussian) is out of scope."""
     like_torch = is_torch(vis_dataset["UVW"])
-    img, sw = _image(vis_dataset, grid_parms, True, time_chunk, weight_key)
+    img, sw = _image(vis_dataset, grid_parms, True, time_chunk, weight_key, chan_chunk)
     return {"PSF": _out(img, like_torch), "PSF_SUM_WEIGHT": _out(sw, like_torch)}
 
 
-def make_image(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT"):
+def make_image(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT", chan_chunk=0):
     """IMAGE (l, m, chan, pol) and SUM_WEIGHT (chan, pol): complex PS gridding of DATA * weight (FLAG honoured as NaN,
     cngi/vis/apply_flags.py:53), inverse FFT, crop, / sum_weight / PS correcting image (make_image.py:106-130)."""
     like_torch = is_torch(vis_dataset["DATA"])
-    img, sw = _image(vis_dataset, grid_parms, False, time_chunk, weight_key)
+    img, sw = _image(vis_dataset, grid_parms, False, time_chunk, weight_key, chan_chunk)
     return {"IMAGE": _out(img, like_torch), "SUM_WEIGHT": _out(sw, like_torch)}

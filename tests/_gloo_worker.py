@@ -40,7 +40,16 @@ def oracle_ops():
         grid += torch.from_numpy(g)
         sum_weight += torch.from_numpy(s)
 
-    return SimpleNamespace(imaging_weight_grid=iw_grid, briggs=briggs, degrid=degrid, standard_grid=std_grid)
+    def zeros(shape, is_complex):
+        return torch.zeros(shape, dtype=torch.complex128 if is_complex else torch.float64)
+
+    def to_image(g, s, gp):
+        corr = O._remove_padding(O._create_prolate_spheroidal_image_2D(gp["image_size_padded"]), gp["image_size"])
+        img = O.correct_image(O.grid_to_uncorrected_image(g.numpy(), gp["image_size"]), s.numpy(), corr)
+        return torch.from_numpy(np.ascontiguousarray(img))
+
+    return SimpleNamespace(imaging_weight_grid=iw_grid, briggs=briggs, degrid=degrid, standard_grid=std_grid, zeros=zeros,
+                           to_image=to_image)
 
 
 def dataset():
@@ -78,7 +87,16 @@ def main():
     cs = D.channel_shard(full, rank, ws)
     gc, sc = O._standard_grid_numpy_wrap(cs["vis"].numpy(), cs["uvw"].numpy(), cs["weight"].numpy(), cs["freq_chan"].numpy(),
                                          cgk, gpc)
-    np.savez(os.path.join(out, "rank%d.npz" % rank), grid=bufs.grid.numpy(), gsw=bufs.gsw.numpy(), iw=iw.numpy(),
+    # cube imaging driver: channel groups own their planes end to end, chunked through one grid buffer; with
+    # time_split == world size the ranks of the single group reduce their partial chunk grids onto the root
+    gpi = dict(gpc, image_size=np.array([80, 80]))
+    img1, sw1, cr1 = D.cube_imaging(oracle_ops(), full, gpi, cgk, chan_chunk=2, time_split=1)
+    groups = D.make_time_groups(ws, ws)
+    img2, sw2, cr2 = D.cube_imaging(oracle_ops(), full, gpi, cgk, chan_chunk=4, time_split=ws, groups=groups)
+    extra = dict(cube_img=img1.numpy(), cube_img_sw=sw1.numpy(), cube_img_range=np.array(cr1))
+    if img2 is not None:
+        extra.update(cube_img_ts=img2.numpy(), cube_img_ts_sw=sw2.numpy())
+    np.savez(os.path.join(out, "rank%d.npz" % rank), **extra, grid=bufs.grid.numpy(), gsw=bufs.gsw.numpy(), iw=iw.numpy(),
              density=bufs.density.numpy(), pipe_grid=pipe_grid, pipe_gsw=pipe_gsw, iw_pipe=iw_pipe.numpy(), cube_grid=gc, cube_sw=sc, chan_range=np.array(D.shard_range(6, rank, ws)),
              time_range=np.array(D.shard_range(24, rank, ws)))
     dist.barrier()

@@ -68,3 +68,15 @@ def test_sharded_step_matches_single_process(tmp_path, oracle, world_size):
     gc, sc = oracle._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gpc)
     assert np.array_equal(np.concatenate([rk["cube_grid"] for rk in ranks], axis=0), gc)
     assert np.array_equal(np.concatenate([rk["cube_sw"] for rk in ranks], axis=0), sc)
+    # cube imaging driver (chunked, grid -> image per chunk): channel-sharded planes concatenate to the single-process
+    # cube image; the time-split variant (partial grids reduced onto the root) gives the same cube on rank 0
+    gpi = dict(gpc, image_size=np.array([80, 80]))
+    corr = oracle._remove_padding(oracle._create_prolate_spheroidal_image_2D(gpi["image_size_padded"]), gpi["image_size"])
+    ref_img = oracle.correct_image(oracle.grid_to_uncorrected_image(gc, gpi["image_size"]), sc, corr)
+    cat = np.concatenate([rk["cube_img"] for rk in ranks], axis=2)
+    assert cat.shape == ref_img.shape
+    assert np.max(np.abs(cat - ref_img)) <= 1e-12 * np.max(np.abs(ref_img))
+    assert np.array_equal(np.concatenate([rk["cube_img_sw"] for rk in ranks], axis=0), sc)
+    assert "cube_img_ts" in ranks[0] and all("cube_img_ts" not in rk for rk in ranks[1:])
+    assert np.max(np.abs(ranks[0]["cube_img_ts"] - ref_img)) <= 1e-12 * np.max(np.abs(ref_img))
+    assert np.max(np.abs(ranks[0]["cube_img_ts_sw"] - sc)) <= 1e-12 * np.max(np.abs(sc))

@@ -77,3 +77,36 @@ def test_weight_psf_image_chain_vs_oracle(oracle, mode):
     G = imaging.make_grid(ds2, gp)
     assert G["GRID"].shape == (195, 175, 6 if mode == "cube" else 1, 2)
     assert rel_err(np.moveaxis(G["GRID"], (2, 3), (0, 1)), gg) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_channel_chunked_cube_equals_unchunked(oracle):
+    """make_image / make_psf with chan_chunk (bounded-memory cube imaging) and distributed.cube_imaging (the per-rank
+    driver of the channel-sharded cube, world size 1 here) give the unchunked cube."""
+    import torch
+    from cngi_prototype_b200 import synth, imaging, distributed as D
+    d = synth.config_c1(n_time=30, n_chan=7)
+    cell_arcsec = d["cell"] / imaging.ARCSEC_TO_RAD * 1.25
+    ds = {"DATA": d["vis"], "UVW": d["uvw"], "WEIGHT": d["weight"], "chan": d["freq_chan"]}
+    gp = {"image_size": [96, 90], "cell_size": [cell_arcsec, cell_arcsec], "fft_padding": 1.25, "chan_mode": "cube"}
+    ref = imaging.make_image(ds, gp, weight_key="WEIGHT")
+    for chunk in (1, 3, 7):
+        out = imaging.make_image(ds, gp, weight_key="WEIGHT", chan_chunk=chunk, time_chunk=13)
+        assert out["IMAGE"].shape == ref["IMAGE"].shape == (96, 90, 7, 2)
+        assert rel_err(out["IMAGE"], ref["IMAGE"]) <= 1e-12 and rel_err(out["SUM_WEIGHT"], ref["SUM_WEIGHT"]) <= 1e-12
+    psf = imaging.make_psf(ds, gp, weight_key="WEIGHT")
+    psf3 = imaging.make_psf(ds, gp, weight_key="WEIGHT", chan_chunk=3)
+    assert rel_err(psf3["PSF"], psf["PSF"]) <= 1e-12
+    # the distributed driver with the CUDA operators
+    g = dict(gp)
+    assert imaging._check_grid_parms(g)
+    g.update(oversampling=100, support=7, do_psf=False, complex_grid=True, do_imaging_weight=False)
+    cgk = oracle._create_prolate_spheroidal_kernel_1D(100, 7)
+    T = {"vis": torch.as_tensor(d["vis"]).cuda(), "uvw": torch.as_tensor(d["uvw"]).cuda(),
+         "weight": torch.as_tensor(d["weight"]).cuda(), "freq_chan": torch.as_tensor(d["freq_chan"]).cuda()}
+    ops = D.cuda_ops()
+    zeros = ops.zeros
+    ops.zeros = lambda shape, cplx: zeros(shape, cplx, "f64")
+    img, sw, (clo, chi) = D.cube_imaging(ops, T, g, cgk, chan_chunk=2)
+    assert (clo, chi) == (0, 7)
+    assert rel_err(img.cpu().numpy(), ref["IMAGE"]) <= 1e-12 and rel_err(sw.cpu().numpy(), ref["SUM_WEIGHT"]) <= 1e-12
