@@ -116,8 +116,14 @@ class ContinuumPipeline:
         pipe.flush()            # results of the last step: pipe.last (grid, gsw valid on rank 0)
     """
 
-    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs):
+    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs, side_stream=None):
+        """side_stream (a high-priority CUDA stream, device tensors only): the whole imaging-weight chain of step k+1
+        (density grid, all-reduce, Briggs factors, weight degrid -- memory-latency bound kernels) is issued there and
+        runs CONCURRENTLY with the gridding kernel of step k on the current stream (issue bound): whenever a gridder
+        block retires, a pending block of the high-priority stream takes its slot, and the two kinds of warps fill each
+        other's stalls."""
         self.ops, self.gp, self.gp_iw, self.iw_parms, self.cgk = ops, gp, gp_iw, iw_parms, cgk
+        self.side = side_stream
         self.bufs = [make_bufs(), make_bufs()]
         self.pend_density = [[], []]
         self.pend_grid = [[], []]
@@ -163,18 +169,58 @@ class ContinuumPipeline:
         self.last = b
         return iw
 
+    def _weights_on_side(self, d, slot):
+        """The whole weight chain of a step on the side stream; returns (imaging weights, event that marks them ready)."""
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)   # inputs may have been produced on the current stream
+        with torch.cuda.stream(self.side):
+            self._stage_a(d, slot)
+            b = self.bufs[slot]
+            self._wait(self.pend_density[slot])
+            if b.density.shape[1] >= 2:
+                b.density[:, 1:] = b.density[:, :1]
+                b.dsw[:, 1:] = b.dsw[:, :1]
+            bf = self.ops.briggs(b.density, b.dsw, self.iw_parms)
+            iw = self.ops.degrid(b.density, d["uvw"], d["weight"], bf, d["freq_chan"], self.gp_iw)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        iw.record_stream(main)
+        return iw, ev
+
+    def _grid_on_main(self, d, slot, grid_hook, iw, ev):
+        b = self.bufs[slot]
+        torch.cuda.current_stream().wait_event(ev)
+        self._wait(self.pend_grid[slot])   # the reduce that last read this grid buffer
+        b.grid.zero_()
+        b.gsw.zero_()
+        if grid_hook is not None:
+            grid_hook("begin")
+        self.ops.standard_grid(d["vis"], d["uvw"], iw, d["freq_chan"], self.cgk, self.gp, grid=b.grid, sum_weight=b.gsw)
+        if grid_hook is not None:
+            grid_hook("end")
+        if world()[1] > 1:   # partial uv-grids -> the rank that runs the FFT
+            self.pend_grid[slot] = [dist.reduce(_as_real(b.grid), 0, async_op=True), dist.reduce(b.gsw, 0, async_op=True)]
+        self.last = b
+        return iw
+
     def step(self, d, grid_hook=None):
         slot = self.k & 1
-        self._stage_a(d, slot)
-        if self.prev is not None:
-            self._stage_b(*self.prev)
-        self.prev = (d, slot, grid_hook)
+        if self.side is not None:
+            iw, ev = self._weights_on_side(d, slot)
+            if self.prev is not None:
+                self._grid_on_main(*self.prev)
+            self.prev = (d, slot, grid_hook, iw, ev)
+        else:
+            self._stage_a(d, slot)
+            if self.prev is not None:
+                self._stage_b(*self.prev)
+            self.prev = (d, slot, grid_hook)
         self.k += 1
 
     def flush(self):
         iw = None
         if self.prev is not None:
-            iw = self._stage_b(*self.prev)
+            iw = self._grid_on_main(*self.prev) if self.side is not None else self._stage_b(*self.prev)
             self.prev = None
         for slot in (0, 1):
             self._wait(self.pend_density[slot])

@@ -110,3 +110,36 @@ def test_channel_chunked_cube_equals_unchunked(oracle):
     img, sw, (clo, chi) = D.cube_imaging(ops, T, g, cgk, chan_chunk=2)
     assert (clo, chi) == (0, 7)
     assert rel_err(img.cpu().numpy(), ref["IMAGE"]) <= 1e-12 and rel_err(sw.cpu().numpy(), ref["SUM_WEIGHT"]) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_continuum_pipeline_side_stream_matches_single_stream():
+    """ContinuumPipeline with the weight chain on a concurrent high-priority stream == the single-stream pipeline."""
+    import torch
+    from types import SimpleNamespace
+    from cngi_prototype_b200 import synth, distributed as D
+    from cngi_prototype_b200._gridding_convolutional_kernels import _create_prolate_spheroidal_kernel_1D
+    d = synth.config_c2(n_time=24, n_chan=16, dtype="f32")
+    n = 256
+    T = {k: torch.as_tensor(d[k]).cuda() for k in ("vis", "uvw", "weight", "freq_chan")}
+    gp = synth.grid_parms_for(n, d["cell"], chan_mode="continuum")
+    gp_iw = synth.grid_parms_for(n, d["cell"], chan_mode="continuum", support=1, oversampling=0, do_psf=True,
+                                 complex_grid=False, do_imaging_weight=True)
+    cgk = torch.as_tensor(_create_prolate_spheroidal_kernel_1D(100, 7)).cuda()
+
+    def make_bufs():
+        return SimpleNamespace(density=torch.empty((1, 2, n, n), dtype=torch.float64, device="cuda"),
+                               dsw=torch.empty((1, 2), dtype=torch.float64, device="cuda"),
+                               grid=torch.empty((1, 2, n, n), dtype=torch.complex64, device="cuda"),
+                               gsw=torch.empty((1, 2), dtype=torch.float64, device="cuda"))
+    res = []
+    for side in (None, torch.cuda.Stream(priority=-1)):
+        pipe = D.ContinuumPipeline(D.cuda_ops(), gp, gp_iw, dict(weighting="briggs", robust=0.5), cgk, make_bufs,
+                                   side_stream=side)
+        for _ in range(4):
+            pipe.step(T)
+        iw = pipe.flush()
+        torch.cuda.synchronize()
+        res.append((pipe.last.grid.cpu().numpy().copy(), pipe.last.gsw.cpu().numpy().copy(), iw.cpu().numpy().copy()))
+    assert rel_err(res[1][0], res[0][0]) <= 1e-5 and rel_err(res[1][1], res[0][1]) <= 1e-12
+    assert np.array_equal(res[1][2], res[0][2])
