@@ -98,6 +98,7 @@ EXPORTS = [
     "cngi_b200_imaging_weight_degrid", "cngi_b200_aperture_grid", "cngi_b200_aperture_weight_grid",
     "cngi_b200_standard_degrid", "cngi_b200_fft_plan_create", "cngi_b200_fft_plan_destroy",
     "cngi_b200_grid_to_image", "cngi_b200_standard_grid_host", "cngi_b200_microbench_red",
+    "cngi_b200_microbench_smem_atomics",
 ]
 
 _lib = None
@@ -131,6 +132,7 @@ def lib():
         L.cngi_b200_aperture_weight_grid.argtypes = [C.POINTER(ApertureGridArgs), vp]
         L.cngi_b200_standard_degrid.argtypes = [C.POINTER(StdDegridArgs), vp]
         L.cngi_b200_microbench_red.argtypes = [vp, i64, i32, i32, i32, vp]
+        L.cngi_b200_microbench_smem_atomics.argtypes = [vp, i32, i32, vp]
         _lib = L
     return _lib
 

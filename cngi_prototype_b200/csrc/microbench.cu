@@ -33,7 +33,44 @@ __global__ void __launch_bounds__(256) red_rate_kernel(float2 *buf, unsigned lon
     }
 }
 
+// The design north_star sketches -- per-block shared-memory subgrids updated with fp atomics -- measured in isolation:
+// every thread adds `per_thread` S x S stamps of (re, im) pairs into a TILE x TILE shared-memory subgrid at
+// pseudo-random positions (no index math, no taps, no loads: an upper bound for that design), then the subgrid is
+// flushed once with REDG.  On sm_100a atomicAdd(float) on shared memory is an ATOMS.CAST.SPIN compare-and-swap loop.
+template <int TILE, int S> __global__ void __launch_bounds__(256) smem_atomic_rate_kernel(float2 *sink, int per_thread)
+{
+    __shared__ float2 tile[TILE * TILE];
+    for (int i = threadIdx.x; i < TILE * TILE; i += blockDim.x) tile[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+    unsigned h = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    for (int i = 0; i < per_thread; ++i) {
+        h = h * 1664525u + 1013904223u;
+        const int u0 = (h >> 8) % (TILE - S + 1), v0 = (h >> 20) % (TILE - S + 1);
+#pragma unroll
+        for (int iu = 0; iu < S; ++iu)
+#pragma unroll
+            for (int iv = 0; iv < S; ++iv) {
+                float2 *c = tile + (u0 + iu) * TILE + v0 + iv;
+                atomicAdd(&c->x, 1.0f);
+                atomicAdd(&c->y, -1.0f);
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TILE * TILE; i += blockDim.x) atomicAdd(sink + i, tile[i]);
+}
+
 }  // namespace cngi
+
+// blocks x 256 threads, each adding per_thread 7x7 complex stamps into a 32x32 shared-memory subgrid with fp atomics;
+// sink (>= 1024 float2) receives the flushed subgrids.  Tap updates issued: blocks*256*per_thread*49.
+extern "C" int cngi_b200_microbench_smem_atomics(void *sink, int32_t blocks, int32_t per_thread, void *stream)
+{
+    using namespace cngi;
+    CNGI_REQUIRE(sink && blocks > 0 && per_thread > 0, "microbench_smem_atomics: bad arguments");
+    smem_atomic_rate_kernel<32, 7><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float2 *)sink, per_thread);
+    CNGI_CUDA_TRY(cudaGetLastError());
+    return CNGI_OK;
+}
 
 // Launches `blocks` blocks of 256 threads, each thread issuing `per_thread` reductions into buf[0 .. n_cells).
 // Sectors touched per warp instruction: 32 (pattern 0), 8 (pattern 1), 8 (pattern 2).

@@ -61,6 +61,10 @@ int cngi_b200_abi_version(void);
    contiguous bytes, 2 = a warp on 256 contiguous bytes.  bench.py times it to obtain the reduction ("atomic")
    roofline the gridders' flush traffic is compared with (no published peak exists). */
 int cngi_b200_microbench_red(void *buf, int64_t n_cells, int32_t pattern, int32_t blocks, int32_t per_thread, void *stream);
+/* Measurement aid: the alternative design (per-block shared-memory subgrid + fp atomics) in isolation.  blocks x 256
+   threads each add per_thread 7x7 complex stamps into a 32x32 shared-memory subgrid with atomicAdd(float) and flush it
+   once; sink holds >= 1024 complex64.  tools/red_peak.py reports tap updates/s next to the product kernel's. */
+int cngi_b200_microbench_smem_atomics(void *sink, int32_t blocks, int32_t per_thread, void *stream);
 const char *cngi_b200_last_error(void);
 /* 0 if a compute-capability 10.x device is current/available; CNGI_ERR_NO_DEVICE otherwise. */
 int cngi_b200_check_device(void);

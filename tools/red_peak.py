@@ -42,7 +42,21 @@ def main():
             g, ms = red_rate(n_cells, pattern)
             out.append({"footprint_mb": mb, "pattern": NAMES[pattern], "gsectors_per_s": round(g, 2), "ms": round(ms, 3)})
             print(json.dumps(out[-1]), flush=True)
-    print(json.dumps({"red_peak": out}))
+    # the alternative design in isolation: shared-memory fp atomics (ATOMS.CAST.SPIN on sm_100a)
+    L = _lib.lib()
+    sink = torch.zeros(1024, dtype=torch.complex64, device="cuda")
+    blocks, per_thread, best = 148 * 8, 64, float("inf")
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.cngi_b200_microbench_smem_atomics(ptr(sink), blocks, per_thread, stream()), "microbench_smem_atomics")
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    smem = {"design": "32x32 shared-memory subgrid per block, atomicAdd(float) x2 per complex tap, no loads / index math",
+            "complex_tap_updates_per_s": blocks * 256 * per_thread * 49 / (best * 1e-3), "ms": round(best, 3)}
+    print(json.dumps(smem), flush=True)
+    print(json.dumps({"red_peak": out, "smem_atomics": smem}))
 
 
 if __name__ == "__main__":
