@@ -74,7 +74,7 @@ class StdDegridArgs(C.Structure):
         ("cgk_1D", vp), ("vis", vp),
         ("delta_lm", f64 * 2),
         ("support", i32), ("oversampling", i32), ("precision", i32), ("chan_mode", i32),
-        ("normalize", i32), ("reserved", i32),
+        ("normalize", i32), ("algorithm", i32),
     ]
 
 

@@ -13,7 +13,8 @@ from ._devutil import (torch, is_torch, chan_mode, precision_of, torch_dtypes, d
                        back)
 
 
-def _standard_degrid_numpy_wrap(model_grid, uvw, freq_chan, cgk_1D, grid_parms, n_pol=None, normalize=False):
+def _standard_degrid_numpy_wrap(model_grid, uvw, freq_chan, cgk_1D, grid_parms, n_pol=None, normalize=False,
+                                algorithm=0):
     """vis (n_time, n_baseline, n_chan, n_pol) from a kernel-side model grid (n_imag_chan, n_imag_pol, n_u, n_v).
 
     normalize=False is the exact adjoint of the gridder; normalize=True divides every sample by its tap sum, which
@@ -41,6 +42,7 @@ def _standard_degrid_numpy_wrap(model_grid, uvw, freq_chan, cgk_1D, grid_parms, 
     a.delta_lm[0], a.delta_lm[1] = float(cell[0]), float(cell[1])
     a.support, a.oversampling = int(grid_parms["support"]), int(grid_parms["oversampling"])
     a.precision, a.chan_mode, a.normalize = precision, chan_mode(grid_parms), int(bool(normalize))
+    a.algorithm = int(algorithm)   # 0 auto, 1 gather kernel, 2 register-window kernel
     with torch.cuda.device(dev):
         _lib.check(L.cngi_b200_standard_degrid(C.byref(a), stream()), "cngi_b200_standard_degrid")
     return back(vis, like_torch)

@@ -166,6 +166,10 @@ template <typename T> static int launch_degrid(DgParams p, bool identity_pol, cu
     return rc;
 }
 
+// standard_degrid_window.cu
+bool degrid_window_supported(const cngi_std_degrid_args *a);
+int launch_degrid_window(const cngi_std_degrid_args *a, cudaStream_t st);
+
 }  // namespace cngi
 
 extern "C" int cngi_b200_standard_degrid(const cngi_std_degrid_args *a, void *stream)
@@ -180,6 +184,12 @@ extern "C" int cngi_b200_standard_degrid(const cngi_std_degrid_args *a, void *st
     CNGI_REQUIRE(a->oversampling < 65000, "standard_degrid: oversampling too large");
     CNGI_REQUIRE(a->n_time * a->n_baseline < (1LL << 31), "standard_degrid: too many rows");
     if (a->n_time == 0 || a->n_baseline == 0 || a->n_chan == 0 || a->n_pol == 0) return CNGI_OK;
+    CNGI_REQUIRE(a->algorithm >= 0 && a->algorithm <= 2, "standard_degrid: bad algorithm %d", a->algorithm);
+    if (a->algorithm == 2 && !degrid_window_supported(a)) {
+        set_error("standard_degrid: window kernel needs support in {3,5,7}, 1 or 2 pols with the identity pol_map");
+        return CNGI_ERR_UNSUPPORTED;
+    }
+    if (a->algorithm != 1 && degrid_window_supported(a)) return launch_degrid_window(a, (cudaStream_t)stream);
     DgParams p{};
     p.n_time = (int)a->n_time, p.n_baseline = (int)a->n_baseline, p.n_chan = (int)a->n_chan, p.n_pol = (int)a->n_pol;
     p.n_ic = (int)a->n_imag_chan, p.n_ip = (int)a->n_imag_pol, p.n_u = (int)a->n_u, p.n_v = (int)a->n_v;

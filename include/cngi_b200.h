@@ -209,7 +209,7 @@ typedef struct cngi_std_degrid_args {
     int32_t chan_mode;
     int32_t normalize;          /* 1: divide each sample by its tap sum (sum_u cgk * sum_v cgk), the same
                                    normalisation the imaging side applies through sum_weight; 0: raw adjoint */
-    int32_t reserved;
+    int32_t algorithm;          /* 0 auto, 1 gather kernel (any support / pol count), 2 register-window kernel       */
 } cngi_std_degrid_args;
 
 int cngi_b200_standard_degrid(const cngi_std_degrid_args *args, void *stream);

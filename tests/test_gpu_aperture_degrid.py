@@ -78,12 +78,18 @@ def test_degrid_vs_oracle_and_adjoint(oracle, prec, support, oversampling):
         if prec == "f32":
             y = y.astype(np.complex64)
         v_ref = oracle._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp)
-        v = _standard_degrid._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp)
-        assert np.array_equal(v == 0, v_ref == 0)          # skipped samples are exactly 0
-        assert rel_err(v, v_ref) <= tol
         vn_ref = oracle._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp, normalize=True)
-        vn = _standard_degrid._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp, normalize=True)
-        assert rel_err(vn, vn_ref) <= tol
+        for algo in ((1, 2) if support <= 7 else (1,)):      # gather kernel, register-window kernel (supports 3/5/7)
+            v = _standard_degrid._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp, algorithm=algo)
+            assert np.array_equal(v == 0, v_ref == 0), algo   # skipped samples are exactly 0
+            assert rel_err(v, v_ref) <= tol, algo
+            vn = _standard_degrid._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp, normalize=True,
+                                                              algorithm=algo)
+            assert rel_err(vn, vn_ref) <= tol, algo
+            # a single-pol predict from a two-pol model grid
+            v1 = _standard_degrid._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp, n_pol=1, algorithm=algo)
+            assert rel_err(v1[..., 0], v_ref[..., 0]) <= tol, algo
+        v = _standard_degrid._standard_degrid_numpy_wrap(y, d["uvw"], d["freq_chan"], cgk, gp)
         # <y, grid(x)> == <degrid(y), x> with unit weights and unflagged data
         x = np.nan_to_num(d["vis"], nan=0.5)
         ones = np.ones_like(d["weight"])

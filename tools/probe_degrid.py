@@ -11,5 +11,7 @@ gp = synth.grid_parms_for(4096, d["cell"], chan_mode="continuum")
 uvw, freq = torch.as_tensor(d["uvw"]).cuda(), torch.as_tensor(d["freq_chan"]).cuda()
 for dt in (torch.complex64, torch.complex128):
     model = torch.randn((1, 2, 4096, 4096), dtype=dt, device="cuda")
-    med, best = timeit(lambda: _standard_degrid._standard_degrid_numpy_wrap(model, uvw, freq, cgk, gp, normalize=True))
-    print(json.dumps(dict(dtype=str(dt), ms=round(med, 3), gvis_s=round(d["weight"].size / med / 1e6, 2))))
+    for algo in (2, 1):   # register-window kernel, gather kernel
+        med, best = timeit(lambda: _standard_degrid._standard_degrid_numpy_wrap(model, uvw, freq, cgk, gp, normalize=True,
+                                                                                algorithm=algo))
+        print(json.dumps(dict(dtype=str(dt), algo=algo, ms=round(med, 3), gvis_s=round(d["weight"].size / med / 1e6, 2))))
