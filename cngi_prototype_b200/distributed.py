@@ -139,23 +139,32 @@ class ContinuumPipeline:
 
     def _stage_a(self, d, slot):
         b = self.bufs[slot]
-        b.density.zero_()
-        b.dsw.zero_()
         n_pol = b.density.shape[1]
+        (b.density[:, :1] if n_pol >= 2 else b.density).zero_()   # only plane 0 is gridded when n_pol >= 2
+        b.dsw.zero_()
         self.ops.imaging_weight_grid(d["uvw"], d["weight"], d["freq_chan"], self.gp_iw, grid=b.density, sum_weight=b.dsw,
                                      first_pol_only=n_pol >= 2)
         if world()[1] > 1:   # every rank needs the full density for its own degrid; plane 0 carries all the information
             first = b.density[:, :1] if n_pol >= 2 else b.density
             self.pend_density[slot] = [dist.all_reduce(first, async_op=True), dist.all_reduce(b.dsw, async_op=True)]
 
+    def _weights(self, d, b):
+        """Briggs factors + weight degrid from the (all-reduced) density.  With n_pol >= 2 only pol plane 0 was gridded
+        (all planes are identical by construction): the other planes are stride-0 views of it -- no replication pass,
+        and the sum of squares reads one plane."""
+        n_pol = b.density.shape[1]
+        if n_pol >= 2:
+            rho0, sw0 = b.density[:, :1], b.dsw[:, :1]
+            bf = self.ops.briggs(rho0, sw0, self.iw_parms).expand(-1, -1, n_pol)
+            rho = rho0.expand(-1, n_pol, -1, -1)
+        else:
+            bf, rho = self.ops.briggs(b.density, b.dsw, self.iw_parms), b.density
+        return self.ops.degrid(rho, d["uvw"], d["weight"], bf, d["freq_chan"], self.gp_iw)
+
     def _stage_b(self, d, slot, grid_hook):
         b = self.bufs[slot]
         self._wait(self.pend_density[slot])
-        if b.density.shape[1] >= 2:
-            b.density[:, 1:] = b.density[:, :1]
-            b.dsw[:, 1:] = b.dsw[:, :1]
-        bf = self.ops.briggs(b.density, b.dsw, self.iw_parms)
-        iw = self.ops.degrid(b.density, d["uvw"], d["weight"], bf, d["freq_chan"], self.gp_iw)
+        iw = self._weights(d, b)
         self._wait(self.pend_grid[slot])   # the reduce that last read this grid buffer
         b.grid.zero_()
         b.gsw.zero_()
@@ -177,11 +186,7 @@ class ContinuumPipeline:
             self._stage_a(d, slot)
             b = self.bufs[slot]
             self._wait(self.pend_density[slot])
-            if b.density.shape[1] >= 2:
-                b.density[:, 1:] = b.density[:, :1]
-                b.dsw[:, 1:] = b.dsw[:, :1]
-            bf = self.ops.briggs(b.density, b.dsw, self.iw_parms)
-            iw = self.ops.degrid(b.density, d["uvw"], d["weight"], bf, d["freq_chan"], self.gp_iw)
+            iw = self._weights(d, b)
             ev = torch.cuda.Event()
             ev.record(self.side)
         iw.record_stream(main)
