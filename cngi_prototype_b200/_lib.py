@@ -91,6 +91,16 @@ class GridToImageArgs(C.Structure):
     ]
 
 
+class DirectionRotateArgs(C.Structure):
+    _fields_ = [
+        ("n_time", i64), ("n_baseline", i64), ("n_chan", i64), ("n_pol", i64),
+        ("vis", vp), ("vis_rot", vp), ("uvw", vp), ("uvw_rot", vp), ("field", vp), ("freq_chan", vp),
+        ("uvw_rotmat", vp), ("phase_rotation", vp), ("rot_field_id", vp),
+        ("n_field", i64), ("status", vp),
+        ("common_tangent_reprojection", i32), ("single_precision", i32), ("precision", i32),
+    ]
+
+
 # every symbol include/cngi_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "cngi_b200_abi_version", "cngi_b200_last_error", "cngi_b200_check_device",
@@ -98,7 +108,7 @@ EXPORTS = [
     "cngi_b200_imaging_weight_degrid", "cngi_b200_aperture_grid", "cngi_b200_aperture_weight_grid",
     "cngi_b200_standard_degrid", "cngi_b200_fft_plan_create", "cngi_b200_fft_plan_destroy",
     "cngi_b200_grid_to_image", "cngi_b200_standard_grid_host", "cngi_b200_microbench_red",
-    "cngi_b200_microbench_smem_atomics",
+    "cngi_b200_microbench_smem_atomics", "cngi_b200_direction_rotate",
 ]
 
 _lib = None
@@ -131,6 +141,7 @@ def lib():
         L.cngi_b200_aperture_grid.argtypes = [C.POINTER(ApertureGridArgs), vp]
         L.cngi_b200_aperture_weight_grid.argtypes = [C.POINTER(ApertureGridArgs), vp]
         L.cngi_b200_standard_degrid.argtypes = [C.POINTER(StdDegridArgs), vp]
+        L.cngi_b200_direction_rotate.argtypes = [C.POINTER(DirectionRotateArgs), vp]
         L.cngi_b200_microbench_red.argtypes = [vp, i64, i32, i32, i32, vp]
         L.cngi_b200_microbench_smem_atomics.argtypes = [vp, i32, i32, vp]
         _lib = L

@@ -16,6 +16,7 @@
  *   ngcasa/imaging/predict_modelvis_image.py:20 (stub)    degrid predict                   -> cngi_b200_standard_degrid
  *   ngcasa/imaging/make_image.py:116-130                  ifft2 + crop + correct_image     -> cngi_b200_grid_to_image
  *   ngcasa/imaging/_imaging_utils/_normalize.py:39-89     normalize_image                  -> cngi_b200_grid_to_image (pb/sinc)
+ *   ngcasa/imaging/direction_rotate.py:190-248            apply_rotation_matrix/apply_phasor -> cngi_b200_direction_rotate
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer unless its name ends in _host.  Arrays are C-order and
@@ -246,6 +247,37 @@ typedef struct cngi_grid_to_image_args {
 } cngi_grid_to_image_args;
 
 int cngi_b200_grid_to_image(cngi_fft_plan *plan, const cngi_grid_to_image_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * N3  direction_rotate: rotate uvw to a new phase centre and phase-rotate the visibilities (the step in
+ *     front of the mosaic gridders).  ngcasa/imaging/direction_rotate.py:190-213 (apply_rotation_matrix),
+ *     :217-248 (apply_phasor).  The per-field matrices come from calc_rotation_mats (:127-175), a host-side
+ *     n_field x 3 x 3 computation (cngi_prototype_b200/direction_rotate.py).
+ *       uvw_rot[t,b,:] = uvw[t,b,:] @ uvw_rotmat[field(t)]
+ *       vis_rot        = vis * exp(i ((2 pi d) f) (1/c)),  d = uvw_rot[0:end] . phase_rotation[field(t), 0:end]
+ *     field(t) = index in rot_field_id of the one FIELD_ID value of integration t (ids > -1 for the rotation,
+ *     != INT_NAN for the phasor, as the reference); the reference asserts it is constant over baseline --
+ *     here *status is set to 1 instead (outputs of that integration: uvw_rot 0, vis_rot NaN).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cngi_direction_rotate_args {
+    int64_t n_time, n_baseline, n_chan, n_pol;
+    const void *vis;            /* complex [n_time,n_baseline,n_chan,n_pol], or NULL: rotate uvw only       */
+    void *vis_rot;              /* complex out, same shape; may alias vis                                  */
+    const double *uvw;          /* [n_time,n_baseline,3]                                                   */
+    double *uvw_rot;            /* out, may alias uvw, may be NULL                                         */
+    const int64_t *field;       /* FIELD_ID [n_time,n_baseline]                                            */
+    const double *freq_chan;    /* [n_chan] Hz                                                             */
+    const double *uvw_rotmat;   /* [n_field,3,3]                                                           */
+    const double *phase_rotation; /* [n_field,3]                                                           */
+    const int64_t *rot_field_id;  /* [n_field]                                                             */
+    int64_t n_field;
+    int32_t *status;            /* optional device int, set to 1 on a field lookup failure (never cleared)  */
+    int32_t common_tangent_reprojection; /* 1: phase uses u,v only (:219-222)                              */
+    int32_t single_precision;   /* CNGI_F64 only: round the result through complex64 (:244-245)            */
+    int32_t precision;          /* CNGI_F32: complex64 in/out (arithmetic is fp64 either way)              */
+} cngi_direction_rotate_args;
+
+int cngi_b200_direction_rotate(const cngi_direction_rotate_args *args, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry point: what a ctypes / cgo-style binding calls with numpy-like HOST arrays.

@@ -373,3 +373,251 @@ def normalize_image(image, sum_weight, normalizing_image, oversampling, correct_
 
 def max_threads():
     return int(_lib().oracle_max_threads())
+
+
+# --------------------------------------------------------------------------------------------------
+# N3  direction_rotate: uvw rotation + visibility phasor.
+#     Restates /root/reference/ngcasa/imaging/direction_rotate.py:127-248 with explicit loops
+#     (no scipy Rotation, no BLAS matmul, no xarray).  PINNED by tests/golden/direction_rotate_*.npz,
+#     which were produced by the reference's own calc_rotation_mats / apply_rotation_matrix / apply_phasor.
+# --------------------------------------------------------------------------------------------------
+INT_NAN = -2147483648          # cngi/_utils/_constants.py:19
+_C0 = 299792458.0              # scipy.constants.c (direction_rotate.py:239)
+
+
+def _rot_x(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[1.0, 0.0, 0.0], [0.0, c, -s], [0.0, s, c]])
+
+
+def _rot_z(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+
+
+def directional_cosine(radec):
+    """direction_rotate.py:177-188."""
+    return np.array([np.cos(radec[0]) * np.cos(radec[1]), np.sin(radec[0]) * np.cos(radec[1]), np.sin(radec[1])])
+
+
+def calc_rotation_mats(field_id_of_samples, field_ids, field_phase_dir, new_phase_center,
+                       common_tangent_reprojection=True):
+    """direction_rotate.py:127-175.  field_id_of_samples: the FIELD_ID array (n_time, n_baseline);
+    field_ids/field_phase_dir: the FIELD table (ids, (n, 2) ra/dec radians).  Intrinsic Euler 'XZ' = Rx*Rz,
+    'ZX' = Rz*Rx (scipy.spatial.transform convention for upper-case axes).
+    Returns uvw_rotmat (n_field, 3, 3), phase_rotation (n_field, 3), rot_field_id (sorted unique ids > -1)."""
+    ra, dec = new_phase_center[0], new_phase_center[1]
+    rot_new = _rot_x(np.pi / 2 - dec) @ _rot_z(-ra + np.pi / 2)
+    cos_new = directional_cosine(np.array([ra, dec]))
+    ids = np.unique(np.asarray(field_id_of_samples))
+    ids = ids[ids > -1]
+    table = {int(f): np.asarray(field_phase_dir)[i] for i, f in enumerate(np.asarray(field_ids))}
+    rotmat = np.zeros((len(ids), 3, 3))
+    phase_rot = np.zeros((len(ids), 3))
+    for i, f in enumerate(ids):
+        pc = table[int(f)]
+        rot_field = _rot_z(-np.pi / 2 + pc[0]) @ _rot_x(pc[1] - np.pi / 2)
+        rotmat[i] = (rot_new @ rot_field).T
+        if common_tangent_reprojection:
+            rotmat[i, 2, 0:2] = 0.0
+        phase_rot[i] = rot_new @ (cos_new - directional_cosine(pc))
+    return rotmat, phase_rot, ids
+
+
+def field_index_per_time(field_id_of_samples, rot_field_id, nan_value=-1, greater=True):
+    """The per-integration field lookup of direction_rotate.py:196-201 (ids > -1) / :224-228 (ids != INT_NAN):
+    the field must be constant over baseline (assert in the reference)."""
+    f = np.asarray(field_id_of_samples)
+    out = np.zeros(f.shape[0], dtype=np.int64)
+    for t in range(f.shape[0]):
+        row = f[t]
+        u = np.unique(row[row > -1] if greater else row[row != INT_NAN])
+        assert len(u) == 1, "direction_rotate only supports xds where field_id remains constant over baseline."
+        out[t] = np.where(np.asarray(rot_field_id) == u[0])[0][0]
+    return out
+
+
+def apply_rotation_matrix(uvw, field_id_of_samples, uvw_rotmat, rot_field_id):
+    """direction_rotate.py:190-213: uvw_rot[t, b, :] = uvw[t, b, :] @ R[field(t)], written out term by term."""
+    idx = field_index_per_time(field_id_of_samples, rot_field_id, greater=True)
+    R = uvw_rotmat[idx]                                   # (n_time, 3, 3)
+    out = np.empty_like(uvw)
+    for k in range(3):
+        out[:, :, k] = (uvw[:, :, 0] * R[:, None, 0, k] + uvw[:, :, 1] * R[:, None, 1, k]) + uvw[:, :, 2] * R[:, None, 2, k]
+    return out
+
+
+def apply_phasor(vis_data, uvw_rot, field_id_of_samples, freq_chan, phase_rotation, rot_field_id,
+                 common_tangent_reprojection, single_precision):
+    """direction_rotate.py:217-248.  phase = ((2*pi*d) * f) * (1/c) -- numpy evaluates
+    `2.0*1j*np.pi*d*f/c` left to right and its complex/real division multiplies by the reciprocal
+    (verified bit for bit against numpy in tests/test_oracle_golden.py)."""
+    idx = field_index_per_time(field_id_of_samples, rot_field_id, greater=False)
+    P = phase_rotation[idx]                               # (n_time, 3)
+    d = uvw_rot[:, :, 0] * P[:, None, 0] + uvw_rot[:, :, 1] * P[:, None, 1]
+    if not common_tangent_reprojection:
+        d = d + uvw_rot[:, :, 2] * P[:, None, 2]
+    y = (((2.0 * np.pi) * d)[:, :, None] * np.asarray(freq_chan)[None, None, :]) * (1.0 / _C0)
+    phasor = np.cos(y) + 1j * np.sin(y)
+    out = vis_data * phasor[:, :, :, None]
+    if single_precision:
+        out = out.astype(np.complex64).astype(np.complex128)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# N2  make_gridding_convolution_function (SURVEY.md section 8f), a_term only (the reference forces
+#     a_term=True, ps_term=False: make_gridding_convolution_function.py:131-132).
+#     Restates make_gridding_convolution_function.py:161-311 (pipeline), :331-359 (phase gradient),
+#     :361-392 (resize + support), :394-412 (baseline patterns), :414-457 (support search), :512-560 (maps) and
+#     _imaging_utils/_make_pb_symmetric.py:135-235 (Airy patterns) with numpy.fft and scipy.special.jn.
+#     PINNED by tests/golden/gcf_*.npz (reference functions run by file path), except world2pix: astropy is absent
+#     here, so the FITS SIN projection is written out and pinned to the CASA test vector quoted in the reference's
+#     own comments (:565-577) -- "parity unpinned" beyond that vector.
+# --------------------------------------------------------------------------------------------------
+def airy_disk_rorder(freq_chan, n_pol, pb_parms, grid_parms, casa=True):
+    """_make_pb_symmetric.py:187-235 (casa=True) / :135-183.  Returns (n_dish, n_chan, n_pol, n0, n1)."""
+    from scipy.special import jn
+    cell, size, centre = grid_parms["cell_size"], grid_parms["image_size"], grid_parms["image_center"]
+    k = (2 * np.pi * np.asarray(freq_chan, dtype=np.float64)) / _C0
+    x = np.arange(-centre[0], size[0] - centre[0]) * cell[0]
+    y = np.arange(-centre[1], size[1] - centre[1]) * cell[1]
+    xg, yg = np.meshgrid(x, y, indexing="ij")
+    rad = np.sqrt(xg ** 2 + yg ** 2)
+    out = np.zeros((len(pb_parms["list_dish_diameters"]), len(k), 1, size[0], size[1]))
+    for i, (dish, block) in enumerate(zip(pb_parms["list_dish_diameters"], pb_parms["list_blockage_diameters"])):
+        r = np.moveaxis(rad[:, :, None] * k * (dish / 2), 2, 0)
+        r[:, centre[0], centre[1]] = 1.0
+        if block == 0.0:
+            v = 2.0 * jn(1, r) / r
+        elif casa:
+            area_ratio, length_ratio = (dish / block) ** 2, dish / block
+            v = (area_ratio * 2.0 * jn(1, r) / r - 2.0 * jn(1, r * length_ratio) / (r * length_ratio)) / (area_ratio - 1.0)
+        else:
+            e = block / dish
+            v = (2.0 * jn(1, r) / r - 2.0 * e * jn(1, r * e) / r) / (1.0 - e ** 2)
+        out[i, :, 0] = v ** pb_parms["ipower"]
+    out[:, :, 0, centre[0], centre[1]] = 1.0
+    return np.tile(out, (1, 1, n_pol, 1, 1))
+
+
+def create_cf_baseline_map(unique_ant_indx, baseline_ant, n_unique_ant):
+    """:512-528.  Pairs (i <= j) of antenna types; baselines whose types come as (j, i) with j > i keep map 0
+    (the reference only matches the ordered pair)."""
+    pairs = np.array([[i, j] for i in range(n_unique_ant) for j in range(i, n_unique_ant)], dtype=int).reshape(-1, 2)
+    types = np.asarray(unique_ant_indx)[np.asarray(baseline_ant)]
+    cf_map = np.zeros(len(types), dtype=int)
+    for k, (i, j) in enumerate(pairs):
+        cf_map[(types[:, 0] == i) & (types[:, 1] == j)] = k
+    return cf_map, pairs
+
+
+def create_cf_chan_map(freq_chan, chan_tolerance_factor):
+    """:536-560."""
+    f = np.asarray(freq_chan, dtype=np.float64)
+    n_chan = len(f)
+    tol = np.max(f) * chan_tolerance_factor
+    n_pb = int(np.floor((np.max(f) - np.min(f)) / tol) + 0.5)
+    if n_pb == 0:
+        n_pb = 1
+    if n_pb >= n_chan:
+        return np.arange(n_chan), f
+    width = (np.max(f) - np.min(f)) / n_pb
+    pb_freq = np.arange(n_pb) * width + np.min(f) + width / 2
+    return np.array([np.abs(pb_freq - v).argmin() for v in f], dtype=int), pb_freq
+
+
+def calc_conv_size(sub, n_pad, cut_level, oversampling, max_support):
+    """:414-457.  Walks +x then +y from the centre of the (real) weight kernel until <= cut * max|.|."""
+    a = np.abs(sub)
+    cut = cut_level * a.max()
+    assert a.min() < cut, "######### ERROR: support_cut_level too small or imsize too small."
+    sup = []
+    for axis in (0, 1):
+        i = [n_pad[0] // 2, n_pad[1] // 2]
+        while sub[i[0], i[1]] > cut:
+            i[axis] += 1
+            assert i[axis] < n_pad[axis], "######### ERROR: support_cut_level too small or imsize too small."
+        approx = i[axis] - n_pad[axis] // 2
+        sup.append((int(0.5 + approx / oversampling[axis]) + 1) * 2 + 1)
+    assert sup[0] < max_support[0] and sup[1] < max_support[1], \
+        "######### ERROR: support_cut_level too small or imsize too small."
+    s = max(sup)
+    return [s, s]
+
+
+def resize_and_calc_support(conv_kernel, conv_weight_kernel, gcf_parms, grid_parms):
+    """:361-392.  Inputs (n_pair, n_chan, n_pol, n0, n1) real; crop to resize_conv_size about the centre, divide
+    each by the sum over its (support + 1) * oversampling window / (os_u os_v)."""
+    n_pad, rs, osamp = grid_parms["image_size_padded"], gcf_parms["resize_conv_size"], gcf_parms["oversampling"]
+    shape = conv_kernel.shape[:3]
+    support = np.zeros(shape + (2,), dtype=int)
+    start = n_pad // 2 - rs // 2
+    ck = np.zeros(shape + tuple(rs))
+    wk = np.zeros(shape + tuple(rs))
+    for idx in np.ndindex(*shape):
+        support[idx] = calc_conv_size(conv_weight_kernel[idx], n_pad, gcf_parms["support_cut_level"], osamp,
+                                      gcf_parms["max_support"])
+        emb = (support[idx] + 1) * osamp
+        e0 = rs // 2 - emb // 2
+        for src, dst in ((conv_kernel, ck), (conv_weight_kernel, wk)):
+            c = src[idx][start[0]:start[0] + rs[0], start[1]:start[1] + rs[1]]
+            norm = np.real(np.sum(c[e0[0]:e0[0] + emb[0], e0[1]:e0[1] + emb[1]]) / (osamp[0] * osamp[1]))
+            dst[idx] = c / norm
+    return ck, wk, support
+
+
+def sin_world2pix_offset(field_phase_dir, phase_center, cell_size):
+    """Pixel offset of each field centre from the reference pixel under the FITS RA---SIN / DEC--SIN projection
+    (what `w.all_world2pix(dir_deg, 1) - n_pad//2` returns at :348 with crpix = n_pad//2, cdelt = cell in degrees):
+    x = cos(dec) sin(ra - ra0), y = sin(dec) cos(dec0) - cos(dec) sin(dec0) cos(ra - ra0), offset = (x, y) / cell."""
+    d = np.asarray(field_phase_dir, dtype=np.float64).reshape(-1, 2)
+    ra0, dec0 = phase_center[0], phase_center[1]
+    dra = d[:, 0] - ra0
+    x = np.cos(d[:, 1]) * np.sin(dra)
+    y = np.sin(d[:, 1]) * np.cos(dec0) - np.cos(d[:, 1]) * np.sin(dec0) * np.cos(dra)
+    return np.stack([x / cell_size[0], y / cell_size[1]], axis=1)
+
+
+def make_phase_gradient(field_phase_dir, gcf_parms, grid_parms):
+    """:331-359 with the analytic SIN projection in place of astropy.wcs."""
+    n_pad = grid_parms["image_size_padded"]
+    pix_dist = sin_world2pix_offset(field_phase_dir, gcf_parms["phase_center"], grid_parms["cell_size"])
+    pix = -(pix_dist) * 2 * np.pi / (n_pad * gcf_parms["oversampling"])
+    size = gcf_parms["resize_conv_size"]
+    c = size // 2
+    xg, yg = np.meshgrid(np.arange(-c[0], size[0] - c[0]), np.arange(-c[1], size[1] - c[1]), indexing="ij")
+    return np.moveaxis(np.exp(1j * (xg[:, :, None] * pix[:, 0] + yg[:, :, None] * pix[:, 1])), 2, 0)
+
+
+def make_gridding_convolution_function(gcf_parms, grid_parms):
+    """The a_term branch of :161-311 on plain arrays.  gcf_parms: function, list_dish_diameters,
+    list_blockage_diameters, unique_ant_indx, basline_ant (n_baseline, 2), freq_chan, pol, field_phase_dir (n_field, 2),
+    phase_center, oversampling, max_support, support_cut_level, chan_tolerance_factor.  Returns a dict with the
+    reference's gcf_dataset variable names."""
+    gp = dict(gcf_parms)
+    gp["oversampling"] = np.asarray(gp.get("oversampling", [10, 10])).astype(int)
+    gp["max_support"] = np.asarray(gp.get("max_support", [15, 15])).astype(int)
+    gp.setdefault("support_cut_level", 2.5e-2)
+    gp.setdefault("chan_tolerance_factor", 0.005)
+    gp["resize_conv_size"] = (gp["max_support"] + 1) * gp["oversampling"]
+    n_pad = np.asarray(grid_parms["image_size_padded"]).astype(int)
+    cf_bl_map, pairs = create_cf_baseline_map(np.asarray(gp["unique_ant_indx"]), np.asarray(gp["basline_ant"]),
+                                              len(gp["list_dish_diameters"]))
+    cf_chan_map, pb_freq = create_cf_chan_map(gp["freq_chan"], gp["chan_tolerance_factor"])
+    pb_grid = dict(cell_size=np.asarray(grid_parms["cell_size"]) * gp["oversampling"], image_size=n_pad,
+                   image_center=n_pad // 2)
+    casa = gp.get("function", "casa_airy") == "casa_airy"
+    planes = {}
+    for ipower in (1, 2):
+        pat = airy_disk_rorder(pb_freq, 1, dict(gp, ipower=ipower), pb_grid, casa=casa)
+        bp = np.zeros((len(pairs), len(pb_freq), 1, n_pad[0], n_pad[1]))
+        for k, (i, j) in enumerate(pairs):
+            bp[k, :, 0] = pat[i, :, 0] * pat[j, :, 0]
+        planes[ipower] = np.real(np.fft.fftshift(np.fft.fft2(np.fft.ifftshift(bp, axes=(3, 4)), axes=(3, 4)), axes=(3, 4)))
+    ck, wk, support = resize_and_calc_support(planes[1], planes[2], gp, dict(grid_parms, image_size_padded=n_pad))
+    pg = make_phase_gradient(gp["field_phase_dir"], gp, dict(grid_parms, image_size_padded=n_pad))
+    return dict(SUPPORT=support, CONV_KERNEL=ck, WEIGHT_CONV_KERNEL=wk, PHASE_GRADIENT=pg,
+                CF_BASELINE_MAP=cf_bl_map, CF_CHAN_MAP=cf_chan_map, CF_POL_MAP=np.zeros(len(gp["pol"]), dtype=int),
+                PS_CORR_IMAGE=np.ones(tuple(grid_parms["image_size"])), pb_freq=pb_freq, pb_ant_pairs=pairs,
+                oversampling=gp["oversampling"])

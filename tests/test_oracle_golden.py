@@ -102,3 +102,84 @@ def test_mt_driver_matches_single_thread(oracle):
                                                   n_threads=4)
         assert np.max(np.abs(g1 - g4)) <= 1e-13 * np.max(np.abs(g1))
         np.testing.assert_allclose(s1, s4, rtol=1e-13)
+
+
+# ---- N3 direction_rotate --------------------------------------------------------
+def _phase_bound(d):
+    """The reference's own reproducibility limit: its BLAS dot and complex multiply may or may not fuse, so the
+    phase argument y = 2 pi d f / c is only defined to a few ulp(y); |delta vis| <= |vis| * few * eps * |y|."""
+    y = 2 * np.pi * np.abs(d["uvw_rot"][:, :, :3]).sum(-1).max() * np.abs(d["phase_rotation"]).max() * d["freq_chan"].max() / 299792458.0
+    return 1e-15 + 8 * np.finfo(np.float64).eps * y
+
+
+@pytest.mark.parametrize("name", ["direction_rotate_ctr_sp", "direction_rotate_full_dp"])
+def test_direction_rotate(oracle, name):
+    import os
+    from _util import GOLDEN, rel_err
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    ctr, sp = bool(d["ctr"]), bool(d["sp"])
+    R, P, ids = oracle.calc_rotation_mats(d["field"], d["table_ids"], d["table_dirs"], d["new_phase_center"], ctr)
+    assert np.array_equal(ids, d["rot_field_id"])
+    np.testing.assert_allclose(R, d["uvw_rotmat"], rtol=0, atol=1e-15)      # scipy builds them from quaternions
+    np.testing.assert_allclose(P, d["phase_rotation"], rtol=0, atol=1e-18)
+    ur = oracle.apply_rotation_matrix(d["uvw"], d["field"], d["uvw_rotmat"], d["rot_field_id"])
+    assert rel_err(ur, d["uvw_rot"]) < 4e-16
+    vr = oracle.apply_phasor(d["vis"], d["uvw_rot"], d["field"], d["freq_chan"], d["phase_rotation"],
+                             d["rot_field_id"], ctr, sp)
+    assert np.array_equal(np.isnan(vr), np.isnan(d["vis_rot"]))
+    m = ~np.isnan(vr)
+    assert np.max(np.abs(vr[m] - d["vis_rot"][m])) <= _phase_bound(d) * np.abs(d["vis"][m]).max()
+    if sp:   # after the complex64 round trip the two agree bit for bit
+        assert np.array_equal(vr[m], d["vis_rot"][m])
+
+
+def test_direction_rotate_phase_order():
+    """numpy evaluates `2.0*1j*np.pi*d*f/c` as ((2 pi d) f) (1/c): the form the oracle and the CUDA kernel use."""
+    rng = np.random.default_rng(3)
+    dd = rng.normal(0, 0.3, (200, 1))
+    f = np.linspace(1e9, 350e9, 16)[None, :]
+    y = (2.0 * 1j * np.pi * dd * f / 299792458.0)
+    assert np.array_equal(y.imag, (((2.0 * np.pi) * dd) * f) * (1.0 / 299792458.0)) and not y.real.any()
+    e = np.exp(y)
+    assert np.array_equal(e.real, np.cos(y.imag)) and np.array_equal(e.imag, np.sin(y.imag))
+
+
+# ---- N2 make_gridding_convolution_function (SURVEY.md section 8f) ----------------------------------------
+def _gcf_parms_from(d, tag):
+    return dict(function=tag, list_dish_diameters=d["dish"], list_blockage_diameters=d["blockage"],
+                unique_ant_indx=d["unique_ant_indx"], basline_ant=d["baseline_ant"], freq_chan=d["freq_chan"],
+                pol=np.array([0, 1]), oversampling=d["oversampling"], max_support=d["max_support"],
+                field_phase_dir=np.array([[1.0, 0.5], [1.0001, 0.5001]]), phase_center=np.array([1.0, 0.5]))
+
+
+@pytest.mark.parametrize("tag", ["casa_airy", "airy"])
+def test_gcf(oracle, tag):
+    import os
+    from _util import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "gcf_%s.npz" % tag))
+    g = oracle.make_gridding_convolution_function(_gcf_parms_from(d, tag), dict(
+        image_size=d["n_pad"], image_size_padded=d["n_pad"], cell_size=d["cell_size"]))
+    for key, name in (("conv_kernel", "CONV_KERNEL"), ("weight_conv_kernel", "WEIGHT_CONV_KERNEL"),
+                      ("support", "SUPPORT"), ("cf_baseline_map", "CF_BASELINE_MAP"), ("cf_chan_map", "CF_CHAN_MAP"),
+                      ("pb_freq", "pb_freq"), ("pb_ant_pairs", "pb_ant_pairs")):
+        assert np.array_equal(g[name], d[key]), key
+    assert g["PHASE_GRADIENT"].shape == (2, 60, 60) and np.all(g["PHASE_GRADIENT"][0] == 1.0)
+
+
+def test_gcf_chan_maps(oracle):
+    import os
+    from _util import GOLDEN
+    c = np.load(os.path.join(GOLDEN, "gcf_chan_maps.npz"))
+    for k in range(4):
+        m, pf = oracle.create_cf_chan_map(c["f%d" % k], float(c["tol%d" % k]))
+        assert np.array_equal(m, c["map%d" % k]) and np.array_equal(pf, c["pbf%d" % k])
+
+
+def test_sin_projection_known_answer(oracle):
+    """The only world2pix vector the reference holds: the CASA trace quoted in the comments at
+    make_gridding_convolution_function.py:565-577 (crpix 120, cdelt -/+5e-05 deg)."""
+    deg = np.pi / 180
+    off = oracle.sin_world2pix_offset(np.array([[-179.5337374791666889 * deg, -18.863873258333338612 * deg]]),
+                                      np.array([180.46846189999996568 * deg, -18.863873247222226581 * deg]),
+                                      np.array([-5e-05 * deg, 5e-05 * deg]))
+    np.testing.assert_allclose(off[0] + 120, [161.6249842951184803, 119.99951947142589859], rtol=0, atol=2e-9)
