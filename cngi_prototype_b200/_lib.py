@@ -101,6 +101,17 @@ class DirectionRotateArgs(C.Structure):
     ]
 
 
+class GcfArgs(C.Structure):
+    _fields_ = [
+        ("n_pad", i64 * 2), ("conv_size", i64 * 2), ("pb_cell", f64 * 2),
+        ("oversampling", i32 * 2), ("max_support", i32 * 2), ("function", i32), ("reserved", i32),
+        ("n_dish", i64), ("dish_diameter_host", vp), ("blockage_diameter_host", vp),
+        ("n_pair", i64), ("ant_pairs_host", vp), ("n_freq", i64), ("pb_freq_host", vp),
+        ("support_cut_level", f64),
+        ("conv_kernel", vp), ("weight_conv_kernel", vp), ("support", vp), ("status", vp),
+    ]
+
+
 # every symbol include/cngi_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "cngi_b200_abi_version", "cngi_b200_last_error", "cngi_b200_check_device",
@@ -108,7 +119,8 @@ EXPORTS = [
     "cngi_b200_imaging_weight_degrid", "cngi_b200_aperture_grid", "cngi_b200_aperture_weight_grid",
     "cngi_b200_standard_degrid", "cngi_b200_fft_plan_create", "cngi_b200_fft_plan_destroy",
     "cngi_b200_grid_to_image", "cngi_b200_standard_grid_host", "cngi_b200_microbench_red",
-    "cngi_b200_microbench_smem_atomics", "cngi_b200_direction_rotate",
+    "cngi_b200_microbench_smem_atomics", "cngi_b200_direction_rotate", "cngi_b200_make_gcf",
+    "cngi_b200_phase_gradient",
 ]
 
 _lib = None
@@ -142,6 +154,8 @@ def lib():
         L.cngi_b200_aperture_weight_grid.argtypes = [C.POINTER(ApertureGridArgs), vp]
         L.cngi_b200_standard_degrid.argtypes = [C.POINTER(StdDegridArgs), vp]
         L.cngi_b200_direction_rotate.argtypes = [C.POINTER(DirectionRotateArgs), vp]
+        L.cngi_b200_make_gcf.argtypes = [C.POINTER(GcfArgs), vp]
+        L.cngi_b200_phase_gradient.argtypes = [vp, i64, i64, i64, vp, vp]
         L.cngi_b200_microbench_red.argtypes = [vp, i64, i32, i32, i32, vp]
         L.cngi_b200_microbench_smem_atomics.argtypes = [vp, i32, i32, vp]
         _lib = L

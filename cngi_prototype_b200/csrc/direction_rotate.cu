@@ -138,43 +138,87 @@ __device__ __forceinline__ void cmul(double a, double b, double c, double s, dou
     im = __dadd_rn(__dmul_rn(a, s), __dmul_rn(b, c));
 }
 
-// NP = compile-time pol count (1, 2) or 0 = run-time n_pol.
-template <typename T, int NP>
+// Phase of one (row, channel): the reference's ((2 pi d) f) (1/c), then sin/cos in fp64.
+__device__ __forceinline__ void phasor_of(double two_pi_d, double f, double &c, double &s)
+{
+    const double y = __dmul_rn(__dmul_rn(two_pi_d, f), 1.0 / kSpeedOfLight);
+    sincos(y, &s, &c);
+}
+
+// complex64 path: the phasor is rounded to fp32 and the product formed in fp32 (the fp32 bar is 1e-5 relative;
+// the phase itself stays fp64).  One 128-bit access = 2 pols.
+__device__ __forceinline__ float2 cmulf(float2 v, float c, float s)
+{
+    return make_float2(fmaf(v.x, c, -v.y * s), fmaf(v.x, s, v.y * c));
+}
+
+// One warp per (t, b) row: the lanes redundantly rotate the row's uvw and form 2 pi d (23 fp64 operations per row,
+// not per sample), then walk the channels 32 at a time, CH chunks in flight, so every access is a contiguous
+// 512-byte (complex64 x 2 pol) run.  NP = compile-time pol count (1, 2) or 0 = run-time n_pol.
+template <typename T, int NP, int CH>
 __global__ void __launch_bounds__(256)
 dr_phasor_kernel(const void *vis, void *vis_rot, const double *__restrict__ uvw, const int *__restrict__ idx,
                  const double *__restrict__ freq, const double *__restrict__ rotmat,
                  const double *__restrict__ phase_rot, int n_time, int n_baseline, int n_chan, int n_pol,
-                 long long n_items, int end_slice, bool single)
+                 unsigned n_rows, int end_slice, bool single)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_items) return;
-    const long long r = i / n_chan;
-    const int c = (int)(i - r * n_chan);
-    const int t = (int)(r / n_baseline);
+    const unsigned r = blockIdx.x * 8u + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    const int t = (int)(r / (unsigned)n_baseline);
     const int f_rot = idx[t], f_ph = idx[n_time + t];
-    double c_ = nan(""), s_ = nan("");
+    double tpd = nan("");
     if (f_rot >= 0 && f_ph >= 0) {
         double u, v, w;
-        rotate_uvw(uvw + 3 * r, rotmat + 9 * f_rot, u, v, w);
+        rotate_uvw(uvw + 3 * (size_t)r, rotmat + 9 * f_rot, u, v, w);
         const double *P = phase_rot + 3 * f_ph;
         double d = __dadd_rn(__dmul_rn(u, P[0]), __dmul_rn(v, P[1]));
         if (end_slice == 3) d = __dadd_rn(d, __dmul_rn(w, P[2]));
-        const double y = __dmul_rn(__dmul_rn(__dmul_rn(6.283185307179586, d), freq[c]), 1.0 / kSpeedOfLight);
-        sincos(y, &s_, &c_);
+        tpd = __dmul_rn(6.283185307179586, d);
     }
-    if (NP == 2) {
-        double re[2], im[2], ore[2], oim[2];
-        VisIO<T>::load2(vis, (size_t)i, re, im);
-        cmul(re[0], im[0], c_, s_, ore[0], oim[0]);
-        cmul(re[1], im[1], c_, s_, ore[1], oim[1]);
-        VisIO<T>::store2(vis_rot, (size_t)i, ore, oim, single);
-    } else {
-        const int np = NP == 1 ? 1 : n_pol;
-        for (int p = 0; p < np; ++p) {
-            double re, im, ore, oim;
-            VisIO<T>::load1(vis, (size_t)i * np + p, re, im);
-            cmul(re, im, c_, s_, ore, oim);
-            VisIO<T>::store1(vis_rot, (size_t)i * np + p, ore, oim, single);
+    const size_t row0 = (size_t)r * n_chan;
+    for (int c0 = 0; c0 < n_chan; c0 += 32 * CH) {
+        if (NP == 2 && sizeof(T) == 4) {
+            float4 x[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int c = c0 + 32 * j + lane;
+                if (c < n_chan) x[j] = __ldcs(reinterpret_cast<const float4 *>(vis) + row0 + c);
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int c = c0 + 32 * j + lane;
+                if (c < n_chan) {
+                    double cd, sd;
+                    phasor_of(tpd, freq[c], cd, sd);
+                    const float cf = __double2float_rn(cd), sf = __double2float_rn(sd);
+                    const float2 a = cmulf(make_float2(x[j].x, x[j].y), cf, sf);
+                    const float2 b = cmulf(make_float2(x[j].z, x[j].w), cf, sf);
+                    __stcs(reinterpret_cast<float4 *>(vis_rot) + row0 + c, make_float4(a.x, a.y, b.x, b.y));
+                }
+            }
+        } else {
+            const int np = NP == 0 ? n_pol : NP;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int c = c0 + 32 * j + lane;
+                if (c < n_chan) {
+                    double cd, sd;
+                    phasor_of(tpd, freq[c], cd, sd);
+                    for (int p = 0; p < np; ++p) {
+                        double re, im, ore, oim;
+                        VisIO<T>::load1(vis, (row0 + c) * np + p, re, im);
+                        if (sizeof(T) == 4) {
+                            const float2 o = cmulf(make_float2((float)re, (float)im), __double2float_rn(cd),
+                                                   __double2float_rn(sd));
+                            ore = o.x, oim = o.y;
+                        } else {
+                            cmul(re, im, cd, sd, ore, oim);
+                        }
+                        VisIO<T>::store1(vis_rot, (row0 + c) * np + p, ore, oim, single);
+                    }
+                }
+            }
         }
     }
 }
@@ -182,18 +226,19 @@ dr_phasor_kernel(const void *vis, void *vis_rot, const double *__restrict__ uvw,
 template <typename T>
 static int launch_phasor(const cngi_direction_rotate_args *a, const int *idx, cudaStream_t st)
 {
-    const long long n_items = (long long)a->n_time * a->n_baseline * a->n_chan;
-    if (n_items == 0) return CNGI_OK;
-    const unsigned blocks = (unsigned)ceil_div(n_items, 256);
+    const long long n_rows = (long long)a->n_time * a->n_baseline;
+    if (n_rows == 0 || a->n_chan == 0) return CNGI_OK;
+    const unsigned blocks = (unsigned)ceil_div(n_rows, 8);
     const int end_slice = a->common_tangent_reprojection ? 2 : 3;
     const bool single = a->single_precision != 0;
-#define CNGI_DR_LAUNCH(NP)                                                                                         \
-    dr_phasor_kernel<T, NP><<<blocks, 256, 0, st>>>(a->vis, a->vis_rot, a->uvw, idx, a->freq_chan, a->uvw_rotmat,   \
-                                                    a->phase_rotation, (int)a->n_time, (int)a->n_baseline,          \
-                                                    (int)a->n_chan, (int)a->n_pol, n_items, end_slice, single)
-    if (a->n_pol == 2) CNGI_DR_LAUNCH(2);
-    else if (a->n_pol == 1) CNGI_DR_LAUNCH(1);
-    else CNGI_DR_LAUNCH(0);
+#define CNGI_DR_LAUNCH(NP, CH)                                                                                     \
+    dr_phasor_kernel<T, NP, CH><<<blocks, 256, 0, st>>>(a->vis, a->vis_rot, a->uvw, idx, a->freq_chan,              \
+                                                        a->uvw_rotmat, a->phase_rotation, (int)a->n_time,           \
+                                                        (int)a->n_baseline, (int)a->n_chan, (int)a->n_pol,          \
+                                                        (unsigned)n_rows, end_slice, single)
+    if (a->n_pol == 2) CNGI_DR_LAUNCH(2, 4);
+    else if (a->n_pol == 1) CNGI_DR_LAUNCH(1, 4);
+    else CNGI_DR_LAUNCH(0, 2);
 #undef CNGI_DR_LAUNCH
     CNGI_CUDA_TRY(cudaGetLastError());
     return CNGI_OK;
@@ -207,8 +252,7 @@ extern "C" int cngi_b200_direction_rotate(const cngi_direction_rotate_args *a, v
     cudaStream_t st = (cudaStream_t)stream;
     CNGI_REQUIRE(a != nullptr, "direction_rotate: args is NULL");
     CNGI_REQUIRE(a->n_time >= 0 && a->n_baseline >= 0 && a->n_chan >= 0 && a->n_pol >= 1, "direction_rotate: bad shape");
-    CNGI_REQUIRE(a->n_time < (1LL << 31) && a->n_baseline < (1LL << 31) && a->n_chan < (1LL << 31),
-                 "direction_rotate: axis too long");
+    CNGI_REQUIRE(a->n_time * a->n_baseline < (1LL << 31) && a->n_chan < (1LL << 31), "direction_rotate: axis too long");
     CNGI_REQUIRE(a->uvw && a->field && a->uvw_rotmat && a->phase_rotation && a->rot_field_id && a->n_field >= 1,
                  "direction_rotate: uvw, field, uvw_rotmat, phase_rotation, rot_field_id are required");
     CNGI_REQUIRE((a->vis == nullptr) == (a->vis_rot == nullptr), "direction_rotate: vis and vis_rot go together");

@@ -17,6 +17,7 @@
  *   ngcasa/imaging/make_image.py:116-130                  ifft2 + crop + correct_image     -> cngi_b200_grid_to_image
  *   ngcasa/imaging/_imaging_utils/_normalize.py:39-89     normalize_image                  -> cngi_b200_grid_to_image (pb/sinc)
  *   ngcasa/imaging/direction_rotate.py:190-248            apply_rotation_matrix/apply_phasor -> cngi_b200_direction_rotate
+ *   ngcasa/imaging/make_gridding_convolution_function.py:161-457  a_term GCF            -> cngi_b200_make_gcf, cngi_b200_phase_gradient
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer unless its name ends in _host.  Arrays are C-order and
@@ -278,6 +279,43 @@ typedef struct cngi_direction_rotate_args {
 } cngi_direction_rotate_args;
 
 int cngi_b200_direction_rotate(const cngi_direction_rotate_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * N2  A-term gridding convolution functions (the producer of conv_kernel / weight_conv_kernel / weight_support /
+ *     phase_gradient that cngi_b200_aperture_grid consumes).  a_term branch of
+ *     ngcasa/imaging/make_gridding_convolution_function.py:161-311: Airy voltage patterns per antenna type
+ *     (_make_pb_symmetric.py:135-235) -> per antenna-type pair products (:394-412) -> fft (:246-247) -> support
+ *     search (:414-457) -> crop + normalise (:361-392).  Outputs are float64 like the reference's.
+ *     status (device int, OR-ed, never cleared): 1 = min >= cut level (:423), 2 = walk left the image (:429,:440),
+ *     4 = support >= max_support (:447-448) -- the reference's asserts.
+ * ---------------------------------------------------------------------------------------------- */
+enum { CNGI_PB_AIRY = 0, CNGI_PB_CASA_AIRY = 1 };
+typedef struct cngi_gcf_args {
+    int64_t n_pad[2];               /* grid_parms['image_size_padded']                                  */
+    int64_t conv_size[2];           /* resize_conv_size = (max_support + 1) * oversampling  (:134)       */
+    double pb_cell[2];              /* cell_size * oversampling, radians (:398)                          */
+    int32_t oversampling[2];
+    int32_t max_support[2];
+    int32_t function;               /* CNGI_PB_AIRY / CNGI_PB_CASA_AIRY                                  */
+    int32_t reserved;
+    int64_t n_dish;                 /* unique antenna types                                             */
+    const double *dish_diameter_host, *blockage_diameter_host;   /* HOST [n_dish], metres                */
+    int64_t n_pair;
+    const int64_t *ant_pairs_host;  /* HOST [n_pair,2] antenna-type pairs (create_cf_baseline_map :512)  */
+    int64_t n_freq;
+    const double *pb_freq_host;     /* HOST [n_freq] PB frequencies (create_cf_chan_map :536)            */
+    double support_cut_level;
+    double *conv_kernel;            /* out [n_pair,n_freq,1,conv_size[0],conv_size[1]]                  */
+    double *weight_conv_kernel;     /* out, same shape                                                  */
+    int64_t *support;               /* out [n_pair,n_freq,1,2]                                          */
+    int32_t *status;                /* device int, see above                                            */
+} cngi_gcf_args;
+
+int cngi_b200_make_gcf(const cngi_gcf_args *args, void *stream);
+/* make_phase_gradient :351-358: out[f,i,j] = exp(i ((i - cu/2) pix[f,0] + (j - cv/2) pix[f,1])), complex128.
+   pix [n_field,2] (device) = -(SIN world2pix offset) * 2 pi / (n_pad * oversampling), computed by the host mirror. */
+int cngi_b200_phase_gradient(const double *pix, int64_t n_field, int64_t cu, int64_t cv, void *phase_gradient,
+                             void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry point: what a ctypes / cgo-style binding calls with numpy-like HOST arrays.
