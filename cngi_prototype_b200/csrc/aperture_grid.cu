@@ -620,6 +620,7 @@ template <typename T, int W, int PP> static int launch_aperture_track(ApParams p
     double2 *tapnorm = nullptr;
     int rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
     if (rc != CNGI_OK) return rc;
+    tune_pool_once();
     cudaError_t e = cudaMallocAsync((void **)&taps, (size_t)n_blocks * W * W * sizeof(CT), st);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&tapnorm, (size_t)n_blocks * sizeof(double2), st);
     if (e != cudaSuccess) {
@@ -679,6 +680,7 @@ template <typename T> static int launch_aperture_rows(ApParams p, cudaStream_t s
     if (rc != CNGI_OK) return rc;
     p.scale = scale;
     CT *taps = nullptr;
+    tune_pool_once();
     cudaError_t e = cudaMallocAsync((void **)&taps, (size_t)n_elems * sizeof(CT), st);
     if (e != cudaSuccess) {
         cudaFreeAsync(scale, st);
@@ -746,6 +748,7 @@ extern "C" int cngi_b200_aperture_weight_grid(const cngi_aperture_grid_args *a, 
     rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
     if (rc != CNGI_OK) return rc;
     p.scale = scale;
+    tune_pool_once();
     CNGI_CUDA_TRY(cudaMallocAsync((void **)&p.buckets, n_buckets * sizeof(double), st));
     CNGI_CUDA_TRY(cudaMemsetAsync(p.buckets, 0, n_buckets * sizeof(double), st));
     const long long blocks = ceil_div(total, 256);

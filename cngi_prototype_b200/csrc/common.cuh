@@ -135,6 +135,7 @@ __device__ __forceinline__ void warp_grouped_add(double *base, int index, double
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();
+int tune_pool_once();   // keep stream-ordered scratch memory in the pool across synchronisations
 
 // uv_scale[0][c], uv_scale[1][c] for all channels in a stream-ordered scratch buffer (one ddiv per channel
 // instead of one per sample for the kernels that map a thread to a single sample).  Free with cudaFreeAsync.

@@ -197,17 +197,47 @@ dr_phasor_kernel(const void *vis, void *vis_rot, const double *__restrict__ uvw,
                     __stcs(reinterpret_cast<float4 *>(vis_rot) + row0 + c, make_float4(a.x, a.y, b.x, b.y));
                 }
             }
-        } else {
-            const int np = NP == 0 ? n_pol : NP;
+        } else if (NP > 0) {
+            // compile-time pol count: all loads of the CH chunks are issued before the first sincos
+            constexpr int NPC = NP > 0 ? NP : 1;
+            using CT = typename Cplx<T>::type;
+            CT x[CH][NPC];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int c = c0 + 32 * j + lane;
+#pragma unroll
+                for (int p = 0; p < NPC; ++p)
+                    if (c < n_chan) x[j][p] = __ldcs(reinterpret_cast<const CT *>(vis) + (row0 + c) * NPC + p);
+            }
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
                 const int c = c0 + 32 * j + lane;
                 if (c < n_chan) {
                     double cd, sd;
                     phasor_of(tpd, freq[c], cd, sd);
-                    for (int p = 0; p < np; ++p) {
+#pragma unroll
+                    for (int p = 0; p < NPC; ++p) {
+                        double ore, oim;
+                        if (sizeof(T) == 4) {
+                            const float2 o = cmulf(make_float2((float)x[j][p].x, (float)x[j][p].y),
+                                                   __double2float_rn(cd), __double2float_rn(sd));
+                            ore = o.x, oim = o.y;
+                        } else {
+                            cmul((double)x[j][p].x, (double)x[j][p].y, cd, sd, ore, oim);
+                        }
+                        VisIO<T>::store1(vis_rot, (row0 + c) * NPC + p, ore, oim, single);
+                    }
+                }
+            }
+        } else {
+            for (int j = 0; j < CH; ++j) {
+                const int c = c0 + 32 * j + lane;
+                if (c < n_chan) {
+                    double cd, sd;
+                    phasor_of(tpd, freq[c], cd, sd);
+                    for (int p = 0; p < n_pol; ++p) {
                         double re, im, ore, oim;
-                        VisIO<T>::load1(vis, (row0 + c) * np + p, re, im);
+                        VisIO<T>::load1(vis, (row0 + c) * n_pol + p, re, im);
                         if (sizeof(T) == 4) {
                             const float2 o = cmulf(make_float2((float)re, (float)im), __double2float_rn(cd),
                                                    __double2float_rn(sd));
@@ -215,7 +245,7 @@ dr_phasor_kernel(const void *vis, void *vis_rot, const double *__restrict__ uvw,
                         } else {
                             cmul(re, im, cd, sd, ore, oim);
                         }
-                        VisIO<T>::store1(vis_rot, (row0 + c) * np + p, ore, oim, single);
+                        VisIO<T>::store1(vis_rot, (row0 + c) * n_pol + p, ore, oim, single);
                     }
                 }
             }
@@ -260,6 +290,7 @@ extern "C" int cngi_b200_direction_rotate(const cngi_direction_rotate_args *a, v
     CNGI_REQUIRE(a->precision == CNGI_F32 || a->precision == CNGI_F64, "direction_rotate: bad precision");
     if (a->n_time == 0 || a->n_baseline == 0) return CNGI_OK;
 
+    if (int rc = tune_pool_once()) return rc;
     int *idx = nullptr;
     CNGI_CUDA_TRY(cudaMallocAsync((void **)&idx, (size_t)2 * a->n_time * sizeof(int), st));
     dr_field_index_kernel<<<(unsigned)ceil_div(a->n_time, 4), 128, 0, st>>>(a->field, (int)a->n_time, (int)a->n_baseline,

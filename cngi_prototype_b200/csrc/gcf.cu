@@ -227,6 +227,7 @@ extern "C" int cngi_b200_make_gcf(const cngi_gcf_args *a, void *stream)
                      a->ant_pairs_host[2 * k + 1] >= 0 && a->ant_pairs_host[2 * k + 1] < a->n_dish,
                      "make_gcf: antenna-type pair %lld out of range", k);
 
+    if (int rc = tune_pool_once()) return rc;
     cufftHandle plan;
     int dims[2] = {(int)n0, (int)n1};
     cufftResult fr = cufftPlanMany(&plan, 2, dims, nullptr, 1, (int)(n0 * n1), nullptr, 1, (int)(n0 * n1), CUFFT_Z2Z, 2);

@@ -28,21 +28,6 @@ struct DevBuf {
     }
 };
 
-static int tune_pool_once()
-{
-    static bool done[64];
-    int dev = 0;
-    CNGI_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !done[dev]) {
-        cudaMemPool_t pool;
-        CNGI_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t keep = UINT64_MAX;
-        CNGI_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        done[dev] = true;
-    }
-    return CNGI_OK;
-}
-
 struct StreamPair {
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t loaded[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
