@@ -87,3 +87,29 @@ def grid_to_image(grid, image_size, sum_weight=None, corr_u=None, corr_v=None, n
         _lib.check(L.cngi_b200_grid_to_image(plan._h, C.byref(a), stream()), "cngi_b200_grid_to_image")
     out = image.permute(2, 3, 0, 1)   # (l, m, chan, pol) view, like the reference's moveaxis
     return out if like_torch else out.cpu().numpy()
+
+
+def image_to_grid(image, image_size_padded, corr_u=None, corr_v=None):
+    """API-side real image (l, m, n_chan, n_pol) -> kernel-side complex grid (n_chan, n_pol, n_u, n_v):
+    fftshift(fft2(ifftshift(pad(image / (corr_u x corr_v))))), the inverse of grid_to_image's transform (unnormalised
+    forward DFT).  What a degridding predict feeds to _standard_degrid (predict_modelvis_image.py:37-40 lists the
+    steps; the reference never implemented them)."""
+    L = _lib.lib()
+    like_torch = is_torch(image)
+    dev = device_of(image)
+    up = Uploader(dev)
+    precision = precision_of(image)
+    rdt, cdt = torch_dtypes(precision)
+    img = up(image, rdt).permute(2, 3, 0, 1).contiguous()          # kernel-side planes
+    n_c, n_p, n_l, n_m = (int(s) for s in img.shape)
+    n_u, n_v = int(image_size_padded[0]), int(image_size_padded[1])
+    grid = torch.empty((n_c, n_p, n_u, n_v), dtype=cdt, device=dev)
+    a = _lib.ImageToGridArgs()
+    a.n_planes, a.n_u, a.n_v = n_c * n_p, n_u, n_v
+    a.image_size[0], a.image_size[1] = n_l, n_m
+    a.image, a.grid, a.precision = ptr(img), ptr(grid), precision
+    a.corr_u, a.corr_v = ptr(up(corr_u, torch.float64)), ptr(up(corr_v, torch.float64))
+    plan = _plan_for(n_u, n_v, n_c * n_p, precision, dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.cngi_b200_image_to_grid(plan._h, C.byref(a), stream()), "cngi_b200_image_to_grid")
+    return grid if like_torch else grid.cpu().numpy()

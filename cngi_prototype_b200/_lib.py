@@ -91,6 +91,13 @@ class GridToImageArgs(C.Structure):
     ]
 
 
+class ImageToGridArgs(C.Structure):
+    _fields_ = [
+        ("n_planes", i64), ("n_u", i64), ("n_v", i64), ("image_size", i64 * 2),
+        ("image", vp), ("corr_u", vp), ("corr_v", vp), ("precision", i32), ("reserved", i32), ("grid", vp),
+    ]
+
+
 class DirectionRotateArgs(C.Structure):
     _fields_ = [
         ("n_time", i64), ("n_baseline", i64), ("n_chan", i64), ("n_pol", i64),
@@ -120,7 +127,7 @@ EXPORTS = [
     "cngi_b200_standard_degrid", "cngi_b200_fft_plan_create", "cngi_b200_fft_plan_destroy",
     "cngi_b200_grid_to_image", "cngi_b200_standard_grid_host", "cngi_b200_microbench_red",
     "cngi_b200_microbench_smem_atomics", "cngi_b200_direction_rotate", "cngi_b200_make_gcf",
-    "cngi_b200_phase_gradient",
+    "cngi_b200_phase_gradient", "cngi_b200_image_to_grid",
 ]
 
 _lib = None
@@ -154,6 +161,7 @@ def lib():
         L.cngi_b200_aperture_weight_grid.argtypes = [C.POINTER(ApertureGridArgs), vp]
         L.cngi_b200_standard_degrid.argtypes = [C.POINTER(StdDegridArgs), vp]
         L.cngi_b200_direction_rotate.argtypes = [C.POINTER(DirectionRotateArgs), vp]
+        L.cngi_b200_image_to_grid.argtypes = [vp, C.POINTER(ImageToGridArgs), vp]
         L.cngi_b200_make_gcf.argtypes = [C.POINTER(GcfArgs), vp]
         L.cngi_b200_phase_gradient.argtypes = [vp, i64, i64, i64, vp, vp]
         L.cngi_b200_microbench_red.argtypes = [vp, i64, i32, i32, i32, vp]

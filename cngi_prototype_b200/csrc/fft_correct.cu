@@ -94,6 +94,42 @@ template <typename T> __global__ void __launch_bounds__(256) fft_post_kernel(Pos
     ((T *)p.image)[(long long)gp * npix + pix] = (T)val;
 }
 
+
+// image -> uv-grid (the inverse of the chain above, for the degridding predict): the cropped, real image is divided by
+// the correcting function, zero padded, ifftshift-ed, and multiplied by exp(+2 pi i h j / n) per axis so that the
+// forward DFT comes out already fftshift-ed -- one pass writes the FFT input, cuFFT writes the grid.
+struct PreParams {
+    const void *image;         // real [planes, n_l, n_m]
+    void *work;                // complex [planes, n_u, n_v]
+    const double2 *phase_u, *phase_v;
+    const double *corr_u, *corr_v;
+    int n_u, n_v, n_l, n_m, start_u, start_v;
+};
+
+template <typename T> __global__ void __launch_bounds__(256) fft_pre_kernel(PreParams p)
+{
+    using CT = typename Cplx<T>::type;
+    const int j1 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j0 = blockIdx.y;
+    const int pl = blockIdx.z;
+    if (j1 >= p.n_v) return;
+    // ifftshift: work[j] = padded[(j + h) % n]
+    int i0 = j0 + p.n_u / 2, i1 = j1 + p.n_v / 2;
+    if (i0 >= p.n_u) i0 -= p.n_u;
+    if (i1 >= p.n_v) i1 -= p.n_v;
+    const int l = i0 - p.start_u, m = i1 - p.start_v;
+    double val = 0.0;
+    if (l >= 0 && l < p.n_l && m >= 0 && m < p.n_m) {
+        val = (double)((const T *)p.image)[((long long)pl * p.n_l + l) * p.n_m + m];
+        if (p.corr_u) val = val / (p.corr_u[l] * p.corr_v[m]);
+    }
+    const double2 pu = p.phase_u[j0], pv = p.phase_v[j1];          // conj(pu) conj(pv) = conj(pu pv)
+    const double pr = pu.x * pv.x - pu.y * pv.y, pi = -(pu.x * pv.y + pu.y * pv.x);
+    CT z;
+    z.x = (T)(val * pr), z.y = (T)(val * pi);
+    ((CT *)p.work)[((long long)pl * p.n_u + j0) * p.n_v + j1] = z;
+}
+
 template <typename T> __global__ void divide_by_centre_kernel(T *image, int n_l, int n_m, long long n_planes)
 {
     // each block handles one plane; the centre value is read before any thread overwrites it
@@ -258,6 +294,61 @@ extern "C" int cngi_b200_grid_to_image(cngi_fft_plan *pl, const cngi_grid_to_ima
             divide_by_centre_kernel<double><<<(unsigned)a->n_planes, 256, 0, st>>>((double *)a->image, (int)a->image_size[0],
                                                                                   (int)a->image_size[1], a->n_planes);
         CNGI_CUDA_TRY(cudaGetLastError());
+    }
+    return CNGI_OK;
+}
+
+extern "C" int cngi_b200_image_to_grid(cngi_fft_plan *pl, const cngi_image_to_grid_args *a, void *stream)
+{
+    using namespace cngi;
+    CNGI_REQUIRE(pl && a, "image_to_grid: null plan or args");
+    CNGI_REQUIRE(a->image && a->grid, "image_to_grid: null image or grid");
+    CNGI_REQUIRE(a->n_u == pl->n_u && a->n_v == pl->n_v && a->precision == pl->precision,
+                 "image_to_grid: plan was made for %lld x %lld precision %d", (long long)pl->n_u, (long long)pl->n_v, pl->precision);
+    CNGI_REQUIRE(a->image_size[0] > 0 && a->image_size[1] > 0 && a->image_size[0] <= a->n_u && a->image_size[1] <= a->n_v,
+                 "image_to_grid: image_size must be within the padded grid");
+    CNGI_REQUIRE((a->corr_u == nullptr) == (a->corr_v == nullptr), "image_to_grid: corr_u and corr_v go together");
+    CNGI_REQUIRE(a->n_u < 65536, "image_to_grid: grid too tall for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool f32 = pl->precision == CNGI_F32;
+    const size_t cb = f32 ? 8 : 16, rb = f32 ? 4 : 8;
+    const long long plane_cells = (long long)a->n_u * a->n_v, plane_pix = (long long)a->image_size[0] * a->image_size[1];
+    for (int64_t p0 = 0; p0 < a->n_planes; p0 += pl->max_planes) {
+        const int64_t nb = std::min<int64_t>(pl->max_planes, a->n_planes - p0);
+        CNGI_REQUIRE(nb < 65536, "image_to_grid: too many planes per batch");
+        cufftHandle h = pl->plan;
+        if (nb != pl->max_planes) {
+            if (pl->tail_planes != nb) {
+                if (pl->plan_tail) cufftDestroy(pl->plan_tail);
+                pl->plan_tail = 0, pl->tail_planes = 0;
+                int rc = make_cufft(&pl->plan_tail, pl->n_u, pl->n_v, nb, pl->precision);
+                if (rc != CNGI_OK) return rc;
+                pl->tail_planes = nb;
+            }
+            h = pl->plan_tail;
+        }
+        if (cufftSetStream(h, st) != CUFFT_SUCCESS) {
+            set_error("cufftSetStream failed");
+            return CNGI_ERR_CUDA;
+        }
+        PreParams pp{};
+        pp.image = (const char *)a->image + (size_t)p0 * plane_pix * rb;
+        pp.work = pl->work, pp.phase_u = pl->phase_u, pp.phase_v = pl->phase_v, pp.corr_u = a->corr_u, pp.corr_v = a->corr_v;
+        pp.n_u = (int)a->n_u, pp.n_v = (int)a->n_v, pp.n_l = (int)a->image_size[0], pp.n_m = (int)a->image_size[1];
+        pp.start_u = (int)(a->n_u / 2 - a->image_size[0] / 2), pp.start_v = (int)(a->n_v / 2 - a->image_size[1] / 2);
+        dim3 grid((unsigned)ceil_div(pp.n_v, 256), (unsigned)pp.n_u, (unsigned)nb);
+        if (f32)
+            fft_pre_kernel<float><<<grid, 256, 0, st>>>(pp);
+        else
+            fft_pre_kernel<double><<<grid, 256, 0, st>>>(pp);
+        CNGI_CUDA_TRY(cudaGetLastError());
+        char *dst = (char *)a->grid + (size_t)p0 * plane_cells * cb;
+        cufftResult r = f32 ? cufftExecC2C(h, (cufftComplex *)pl->work, (cufftComplex *)dst, CUFFT_FORWARD)
+                            : cufftExecZ2Z(h, (cufftDoubleComplex *)pl->work, (cufftDoubleComplex *)dst, CUFFT_FORWARD);
+        if (r != CUFFT_SUCCESS) {
+            set_error("cufftExec failed with %d", (int)r);
+            return CNGI_ERR_CUDA;
+        }
     }
     return CNGI_OK;
 }

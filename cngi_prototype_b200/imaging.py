@@ -177,3 +177,36 @@ def make_image(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT
     like_torch = is_torch(vis_dataset["DATA"])
     img, sw = _image(vis_dataset, grid_parms, False, time_chunk, weight_key, chan_chunk)
     return {"IMAGE": _out(img, like_torch), "SUM_WEIGHT": _out(sw, like_torch)}
+
+
+def predict_modelvis_image(img_dataset, vis_dataset, grid_parms, model_key="MODEL", time_chunk=0):
+    """MODEL_DATA (n_time, n_baseline, n_chan, n_pol) from a model image (l, m, chan, pol), Jy/pixel -- BASELINE config 4.
+
+    The reference's predict_modelvis_image.py:20-40 is a stub whose comments list the steps (fourier_transform,
+    _degrid); this is the inverse of make_image: divide by the PS correcting image, zero pad to image_size_padded,
+    forward FFT, degrid with the same prolate-spheroidal taps (support 7, oversampling 100) normalised by the tap sum.
+    A model with one channel is a continuum model (chan_mode 'continuum'), otherwise one image channel per data channel.
+    Returns a copy of vis_dataset with MODEL_DATA added (the variable self_cal reads, calibration/self_cal.py:107-109)."""
+    from ._standard_degrid import _standard_degrid_numpy_wrap
+    from ._fft import image_to_grid
+    _gp = copy.deepcopy(grid_parms)
+    model = img_dataset[model_key]
+    n_model_chan = int(model.shape[2])
+    _gp.setdefault("chan_mode", "continuum" if n_model_chan == 1 else "cube")
+    assert _check_grid_parms(_gp), "######### ERROR: grid_parms checking failed"
+    n_chan = int(vis_dataset["chan"].shape[0])
+    assert n_model_chan == (1 if _gp["chan_mode"] == "continuum" else n_chan), \
+        "######### ERROR: model image channels do not match chan_mode"
+    _gp["oversampling"], _gp["support"] = 100, 7
+    cgk_1D = _create_prolate_spheroidal_kernel_1D(_gp["oversampling"], _gp["support"])
+    like_torch = is_torch(vis_dataset["UVW"])
+    dev = device_of(model, vis_dataset["UVW"])
+    uvw, freq = _dev(vis_dataset, "UVW", dev, torch.float64), _dev(vis_dataset, "chan", dev, torch.float64)
+    cu, cv = correcting_function_1D(_gp["image_size_padded"], _gp["image_size"])
+    model_t = model if is_torch(model) else torch.as_tensor(np.ascontiguousarray(model))
+    grid = image_to_grid(model_t.to(dev), _gp["image_size_padded"], corr_u=cu, corr_v=cv)
+    parts = [_standard_degrid_numpy_wrap(grid, uvw[sl], freq, cgk_1D, _gp, normalize=True)
+             for sl in _time_chunks(uvw.shape[0], time_chunk)]
+    out = dict(vis_dataset)
+    out["MODEL_DATA"] = _out(parts[0] if len(parts) == 1 else torch.cat(parts, dim=0), like_torch)
+    return out

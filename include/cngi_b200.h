@@ -249,6 +249,23 @@ typedef struct cngi_grid_to_image_args {
 
 int cngi_b200_grid_to_image(cngi_fft_plan *plan, const cngi_grid_to_image_args *args, void *stream);
 
+/* image -> uv-grid, the inverse of cngi_b200_grid_to_image's transform, for the degridding predict:
+   G = fftshift(fft2(ifftshift(pad(image / (corr_u x corr_v))))) (the inverse of make_image.py:116-130; the reference's
+   predict_modelvis_image.py:20-40 is a stub that lists "fourier_transform, _degrid").  Unnormalised forward DFT. */
+typedef struct cngi_image_to_grid_args {
+    int64_t n_planes;           /* n_imag_chan * n_imag_pol                                          */
+    int64_t n_u, n_v;           /* padded grid size                                                  */
+    int64_t image_size[2];      /* image size (l, m) <= (n_u, n_v); centred in the padded plane       */
+    const void *image;          /* real [n_planes, l, m]                                             */
+    const double *corr_u;       /* [image_size[0]] or NULL: image is divided by corr_u[l]*corr_v[m]   */
+    const double *corr_v;
+    int32_t precision;
+    int32_t reserved;
+    void *grid;                 /* complex out [n_planes, n_u, n_v]                                   */
+} cngi_image_to_grid_args;
+
+int cngi_b200_image_to_grid(cngi_fft_plan *plan, const cngi_image_to_grid_args *args, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * N3  direction_rotate: rotate uvw to a new phase centre and phase-rotate the visibilities (the step in
  *     front of the mosaic gridders).  ngcasa/imaging/direction_rotate.py:190-213 (apply_rotation_matrix),
