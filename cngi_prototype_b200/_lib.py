@@ -127,7 +127,7 @@ EXPORTS = [
     "cngi_b200_standard_degrid", "cngi_b200_fft_plan_create", "cngi_b200_fft_plan_destroy",
     "cngi_b200_grid_to_image", "cngi_b200_standard_grid_host", "cngi_b200_microbench_red",
     "cngi_b200_microbench_smem_atomics", "cngi_b200_direction_rotate", "cngi_b200_make_gcf",
-    "cngi_b200_phase_gradient", "cngi_b200_image_to_grid",
+    "cngi_b200_phase_gradient", "cngi_b200_image_to_grid", "cngi_b200_standard_grid_image_psf",
 ]
 
 _lib = None
@@ -154,6 +154,7 @@ def lib():
         L.cngi_b200_fft_plan_destroy.argtypes = [vp]
         L.cngi_b200_grid_to_image.argtypes = [vp, C.POINTER(GridToImageArgs), vp]
         L.cngi_b200_standard_grid.argtypes = [C.POINTER(StdGridArgs), vp]
+        L.cngi_b200_standard_grid_image_psf.argtypes = [C.POINTER(StdGridArgs), vp, vp, vp]
         L.cngi_b200_standard_grid_host.argtypes = [C.POINTER(StdGridArgs), i64]
         L.cngi_b200_imaging_weight_grid.argtypes = [C.POINTER(IwGridArgs), vp]
         L.cngi_b200_imaging_weight_degrid.argtypes = [C.POINTER(IwDegridArgs), vp]

@@ -168,3 +168,61 @@ def _standard_grid_psf_numpy_wrap(uvw, weight, freq_chan, cgk_1D, grid_parms, **
         from ._imaging_weight import imaging_weight_grid
         return imaging_weight_grid(uvw, weight, freq_chan, grid_parms, **kw)
     return standard_grid(None, uvw, weight, freq_chan, cgk_1D, grid_parms, grid_parms["do_psf"], False, **kw)
+
+
+def standard_grid_image_psf(vis_data, uvw, weight, freq_chan, cgk_1D, grid_parms, flag=None, grid=None,
+                            sum_weight=None, psf_grid=None, psf_sum_weight=None, force_fused=False):
+    """Image grid AND psf grid of the same samples in ONE pass (cngi_b200_standard_grid_image_psf): what
+    synthesis_imaging_cube.py:195-211 computes with _make_psf followed by _make_image on the same uvw and weights.
+    Returns (grid complex, sum_weight, psf_grid real, psf_sum_weight), kernel-side layouts, accumulated into the
+    buffers given.  Device path only (numpy inputs are uploaded); support must be 7 -- otherwise the two single
+    passes are issued."""
+    L = _lib.lib()
+    _lib.require_device()
+    like_torch = _is_torch(weight)
+    dev = weight.device if like_torch else torch.device("cuda", torch.cuda.current_device())
+    keep = []
+
+    def dev_t(x, dt):
+        t = x if _is_torch(x) else torch.as_tensor(np.asarray(x))
+        t = t.to(device=dev, dtype=dt).contiguous()
+        keep.append(t)
+        return t
+
+    precision = _precision_of(weight)
+    rdt, cdt = _dtypes(precision, True)
+    w = dev_t(weight, rdt)
+    shape4 = tuple(int(s) for s in w.shape)
+    n_chan, n_pol = shape4[2], shape4[3]
+    n_ic = n_chan if grid_parms["chan_mode"] == "cube" else 1
+    n_uv = np.asarray(grid_parms["image_size_padded"]).astype(np.int64)
+    gshape = (n_ic, n_pol, int(n_uv[0]), int(n_uv[1]))
+    # measured on the B200 (tools/probe_fused.py, C2 at 4096^2): the fused pass saves 29 % (fp32 continuum), 16 % (fp32
+    # cube), 12 % (fp64 continuum) and nothing for fp64 cubes (234 registers: two blocks per SM), which take two passes
+    two_passes = int(grid_parms["support"]) != 7 or (precision == F64 and grid_parms["chan_mode"] == "cube" and not force_fused)
+    if two_passes:
+        gp = dict(grid_parms)
+        psf_grid, psf_sum_weight = standard_grid(None, uvw, w, freq_chan, cgk_1D, gp, True, False, grid=psf_grid,
+                                                 sum_weight=psf_sum_weight)
+        grid, sum_weight = standard_grid(vis_data, uvw, w, freq_chan, cgk_1D, gp, False, True, flag=flag, grid=grid,
+                                         sum_weight=sum_weight)
+    else:
+        a = _lib.StdGridArgs()
+        _fill_common(a, shape4, n_ic, n_uv, grid_parms)
+        a.support, a.oversampling = int(grid_parms["support"]), int(grid_parms["oversampling"])
+        a.precision, a.do_psf, a.complex_grid = precision, 0, 1
+        grid = torch.zeros(gshape, dtype=cdt, device=dev) if grid is None else grid
+        psf_grid = torch.zeros(gshape, dtype=rdt, device=dev) if psf_grid is None else psf_grid
+        sum_weight = torch.zeros((n_ic, n_pol), dtype=torch.float64, device=dev) if sum_weight is None else sum_weight
+        psf_sum_weight = torch.zeros((n_ic, n_pol), dtype=torch.float64, device=dev) if psf_sum_weight is None \
+            else psf_sum_weight
+        assert grid.is_contiguous() and grid.dtype == cdt and psf_grid.is_contiguous() and psf_grid.dtype == rdt
+        f = None if flag is None else dev_t(flag, torch.uint8)
+        a.vis, a.weight, a.flag, a.uvw = _ptr(dev_t(vis_data, cdt)), _ptr(w), _ptr(f), _ptr(dev_t(uvw, torch.float64))
+        a.freq_chan, a.cgk_1D = _ptr(dev_t(freq_chan, torch.float64)), _ptr(dev_t(cgk_1D, torch.float64))
+        a.grid, a.sum_weight = _ptr(grid), _ptr(sum_weight)
+        with torch.cuda.device(dev):
+            _lib.check(L.cngi_b200_standard_grid_image_psf(C.byref(a), _ptr(psf_grid), _ptr(psf_sum_weight), _stream()),
+                       "cngi_b200_standard_grid_image_psf")
+    outs = (grid, sum_weight, psf_grid, psf_sum_weight)
+    return outs if like_torch else tuple(t.cpu().numpy() for t in outs)

@@ -706,3 +706,23 @@ extern "C" int cngi_b200_standard_grid(const cngi_std_grid_args *a, void *stream
         return a->complex_grid ? dispatch<float, true>(p, a, st) : dispatch<float, false>(p, a, st);
     return a->complex_grid ? dispatch<double, true>(p, a, st) : dispatch<double, false>(p, a, st);
 }
+
+// N1: the per-channel pipeline of synthesis_imaging_cube.py:195-211 grids the psf and the image of
+// the same samples back to back; this entry point does both in one pass of the window kernel.
+extern "C" int cngi_b200_standard_grid_image_psf(const cngi_std_grid_args *a, void *psf_grid, double *psf_sum_weight,
+                                                 void *stream)
+{
+    using namespace cngi;
+    int rc = validate(a);
+    if (rc != CNGI_OK) return rc;
+    CNGI_REQUIRE(psf_grid != nullptr && psf_sum_weight != nullptr, "standard_grid_image_psf: null psf outputs");
+    CNGI_REQUIRE(!a->do_psf && a->complex_grid, "standard_grid_image_psf: args describe the image pass (do_psf 0, complex grid)");
+    StdParams p = make_params(a);
+    if (a->support != 7 || !window_kernel_supported(a, p.table_len)) {
+        set_error("standard_grid_image_psf: the fused pass needs support 7 and tap tables that fit shared memory; "
+                  "call cngi_b200_standard_grid twice instead");
+        return CNGI_ERR_UNSUPPORTED;
+    }
+    p.psf_grid = psf_grid, p.psf_sum_weight = psf_sum_weight;
+    return launch_window_dual(p, a, (cudaStream_t)stream);
+}

@@ -18,6 +18,8 @@ struct StdParams {
     const double *cgk;
     void *grid;
     double *sum_weight;
+    void *psf_grid;          // fused image + psf pass only (real, same plane layout as grid)
+    double *psf_sum_weight;
     double dl, dm;
     int support, oversampling, do_psf, chan_mode;
     int table_len;
@@ -71,5 +73,6 @@ int launch_shift(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
 // standard_grid_window.cu
 bool window_kernel_supported(const cngi_std_grid_args *a, int table_len);
 int launch_window(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
+int launch_window_dual(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
 
 }  // namespace cngi

@@ -31,12 +31,14 @@
 
 namespace cngi {
 
-template <typename T, bool CPLX, int S, int PP> struct WinCfg {
+template <typename T, bool CPLX, int S, int PP, bool DUAL = false> struct WinCfg {
     static constexpr int W = (S < 4) ? 4 : 8;                    // lanes per item == columns == rows of the register window
     static constexpr int SPARE = W - S;                          // hysteresis: cells the stamp can move without a slide
     static constexpr int IPW = 32 / W;                           // items per warp
     static constexpr int ITER = W;                               // samples per item per round
-    static constexpr int NV = CPLX ? PP : (PP + 1) / 2;          // accumulator pairs per cell
+    static constexpr int NVC = CPLX ? PP : (PP + 1) / 2;         // accumulator pairs per cell of the grid proper
+    static constexpr int NVP = DUAL ? (PP + 1) / 2 : 0;          // fused image + psf pass: (pol 2m, pol 2m+1) pairs of the psf grid
+    static constexpr int NV = NVC + NVP;
     static constexpr int TPV = 16 / (int)sizeof(T);              // T's per 16-byte vector
     static constexpr int WD = (NV * 2 + TPV - 1) / TPV * TPV;    // padded weighted-data count per record
 #ifndef CNGI_WIN_NS_F32
@@ -79,6 +81,13 @@ template <typename Cfg, typename T> __host__ __device__ inline WinSmem win_smem_
 #define CNGI_WIN_MINB_F64 3
 #endif
 
+#ifndef CNGI_WIN_DUAL_MINB_F32
+#define CNGI_WIN_DUAL_MINB_F32 3
+#endif
+#ifndef CNGI_WIN_DUAL_MINB_F64
+#define CNGI_WIN_DUAL_MINB_F64 2
+#endif
+
 // calls f(integral_constant<int, j>) for the runtime j in [LO, LO + N) through a binary tree of branches, so that
 // the body indexes registers with a compile-time constant
 template <int LO, int N, typename F> __device__ __forceinline__ void static_dispatch(int j, F &&f)
@@ -114,11 +123,16 @@ __device__ __forceinline__ void cp_async_bytes(unsigned dst, const void *src, st
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <typename T, bool CPLX, int S, int PP, int BLK, bool NZ>
-__global__ void __launch_bounds__(BLK, (sizeof(T) == 4 ? CNGI_WIN_MINB_F32 : CNGI_WIN_MINB_F64))
+// DUAL: one pass grids the image (complex, vis * weight) AND the psf (real, weight) of the same samples -- they share
+// every cell index and tap (synthesis_imaging_cube.py:195-211 calls _make_psf and _make_image back to back on the
+// same uvw and weights); the psf accumulators ride along as extra (pol 2m, pol 2m+1) pairs of every window cell.
+template <typename T, bool CPLX, int S, int PP, int BLK, bool NZ, bool DUAL = false>
+__global__ void __launch_bounds__(BLK, DUAL ? (sizeof(T) == 4 ? CNGI_WIN_DUAL_MINB_F32 : CNGI_WIN_DUAL_MINB_F64) : (sizeof(T) == 4 ? CNGI_WIN_MINB_F32 : CNGI_WIN_MINB_F64))
 std_grid_window_kernel(StdParams p)
 {
-    using Cfg = WinCfg<T, CPLX, S, PP>;
+    static_assert(!DUAL || CPLX, "the fused image + psf pass grids a complex image");
+    using Cfg = WinCfg<T, CPLX, S, PP, DUAL>;
+    constexpr int NVC = Cfg::NVC;
     using CT = typename Cplx<T>::type;
     using P2 = typename Pair<T>::type;
     constexpr int W = Cfg::W, IPW = Cfg::IPW, ITER = Cfg::ITER, NV = Cfg::NV, WD = Cfg::WD, NS = Cfg::NS;
@@ -222,10 +236,10 @@ std_grid_window_kernel(StdParams p)
         asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x.x), "=d"(x.y) : "r"(addr));
         return x;
     };
-    auto red_pair = [](T *base, int cell, P2 v, T *base1) {   // one accumulator pair into the grid
+    auto red_pair = [](auto is_cplx, T *base, int cell, P2 v, T *base1) {   // one accumulator pair into the grid
         // NZ: skip cells that only ever received zero taps (the spare row / column) -- pays when the kernel is bound by
         // the reductions (single-channel tracks on a grid far larger than L2), costs issue slots otherwise
-        if constexpr (CPLX) {
+        if constexpr (decltype(is_cplx)::value) {
             if (!NZ || v.x != (T)0 || v.y != (T)0) {
                 CT val;
                 val.x = v.x, val.y = v.y;
@@ -274,6 +288,15 @@ std_grid_window_kernel(StdParams p)
         for (int ip = 0; ip < PP; ++ip)
             gplane[ip] = (T *)p.grid +
                          ((long long)plane2 * p.n_ip + apol[ip < npol ? ip : 0]) * ((long long)p.n_u * p.n_v) * (CPLX ? 2 : 1);
+        T *pplane[PP];   // psf planes of the fused pass (real)
+        double psw_acc[PP];
+#pragma unroll
+        for (int ip = 0; ip < PP; ++ip) {
+            psw_acc[ip] = 0.0;
+            pplane[ip] = nullptr;
+            if constexpr (DUAL)
+                pplane[ip] = (T *)p.psf_grid + ((long long)plane2 * p.n_ip + apol[ip < npol ? ip : 0]) * ((long long)p.n_u * p.n_v);
+        }
         P2 acc[W][NV];
 #pragma unroll
         for (int j = 0; j < W; ++j)
@@ -296,18 +319,46 @@ std_grid_window_kernel(StdParams p)
             static_for<0, W>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 const int cell = cell0 + (j + ((j < m) ? W : 0)) * p.n_v;
+                if constexpr (!DUAL) {   // (kept as a plain unrolled loop: the static_for form below costs the product kernel 10 %)
 #pragma unroll
-                for (int n = 0; n < NV; ++n)
-                    red_pair(gplane[CPLX ? n : 2 * n], cell, acc[j][n], gplane[CPLX ? n : (2 * n + 1 < PP ? 2 * n + 1 : 0)]);
+                    for (int n = 0; n < NV; ++n)
+                        red_pair(std::bool_constant<CPLX>{}, gplane[CPLX ? n : 2 * n], cell, acc[j][n],
+                                 gplane[CPLX ? n : (2 * n + 1 < PP ? 2 * n + 1 : 0)]);
+                } else {
+                    static_for<0, NV>([&](auto nc) {
+                        constexpr int n = decltype(nc)::value;
+                        if constexpr (n < NVC) {
+                            red_pair(std::bool_constant<CPLX>{}, gplane[CPLX ? n : 2 * n], cell, acc[j][n],
+                                     gplane[CPLX ? n : (2 * n + 1 < PP ? 2 * n + 1 : 0)]);
+                        } else {   // psf pair of the fused pass
+                            constexpr int m = n - NVC;
+                            red_pair(std::false_type{}, pplane[2 * m], cell, acc[j][n], pplane[2 * m + 1 < PP ? 2 * m + 1 : 0]);
+                        }
+                    });
+                }
             });
         };
         auto red_column = [&](int u) {   // column u of the window: every lane reduces its cell of it (consecutive v)
             const int cell = u * p.n_v + my_line();
             static_dispatch<0, W>(u & (W - 1), [&](auto jc) {
                 constexpr int j = decltype(jc)::value;
+                if constexpr (!DUAL) {   // (kept as a plain unrolled loop: the static_for form below costs the product kernel 10 %)
 #pragma unroll
-                for (int n = 0; n < NV; ++n)
-                    red_pair(gplane[CPLX ? n : 2 * n], cell, acc[j][n], gplane[CPLX ? n : (2 * n + 1 < PP ? 2 * n + 1 : 0)]);
+                    for (int n = 0; n < NV; ++n)
+                        red_pair(std::bool_constant<CPLX>{}, gplane[CPLX ? n : 2 * n], cell, acc[j][n],
+                                 gplane[CPLX ? n : (2 * n + 1 < PP ? 2 * n + 1 : 0)]);
+                } else {
+                    static_for<0, NV>([&](auto nc) {
+                        constexpr int n = decltype(nc)::value;
+                        if constexpr (n < NVC) {
+                            red_pair(std::bool_constant<CPLX>{}, gplane[CPLX ? n : 2 * n], cell, acc[j][n],
+                                     gplane[CPLX ? n : (2 * n + 1 < PP ? 2 * n + 1 : 0)]);
+                        } else {   // psf pair of the fused pass
+                            constexpr int m = n - NVC;
+                            red_pair(std::false_type{}, pplane[2 * m], cell, acc[j][n], pplane[2 * m + 1 < PP ? 2 * m + 1 : 0]);
+                        }
+                    });
+                }
             });
         };
         // make the stamp whose lowest cell is (v, u) = (need_a, need_b) fit the window, sliding it by the least amount
@@ -424,13 +475,21 @@ std_grid_window_kernel(StdParams p)
                         if (!p.do_psf) raw_vis[ip] = vsrc[ip];
                     }
                 }
-                double wsel[PP];
+                double wsel[PP], psel[PP];
                 bool any = false;
 #pragma unroll
                 for (int ip = 0; ip < PP; ++ip) {
                     wsel[ip] = 0.0;
+                    psel[ip] = 0.0;
                     if (ip < npol) {
                         const T w = raw_w[ip];
+                        if constexpr (DUAL) {   // psf mask: the weight alone (_standard_grid.py:327-333,340)
+                            if (!(isnan(w) || w == (T)0)) {
+                                any = true;
+                                psel[ip] = (double)w;
+                                wd[2 * NVC + ip] = w;
+                            }
+                        }
                         T wre = w, wim = (T)0;
                         bool use;
                         if (p.do_psf) {
@@ -470,6 +529,10 @@ std_grid_window_kernel(StdParams p)
                     const double norm = tapsum[uo] * tapsum[vo];   // == sum over the stamp of cu*cv
 #pragma unroll
                     for (int ip = 0; ip < PP; ++ip) sw_acc[ip] += wsel[ip] * norm;
+                    if constexpr (DUAL) {
+#pragma unroll
+                        for (int ip = 0; ip < PP; ++ip) psw_acc[ip] += psel[ip] * norm;
+                    }
                     const int need_u = cp.uc - HALF, need_v = cp.vc - HALF;
                     // {lowest stamp cell packed v<<16|u, address of the v tap row (the lane picks its own tap from it),
                     //  address of the u tap row rotated into accumulator order, byte offset of the stamp's first row
@@ -565,6 +628,11 @@ std_grid_window_kernel(StdParams p)
             for (int o = span; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
             const bool lead = (lane < span) && chan_ok && (ip < npol);
             warp_grouped_add(p.sum_weight, a_chan1 * p.n_ip + apol[ip], v, lead);
+            if constexpr (DUAL) {
+                double q = psw_acc[ip];
+                for (int o = span; o < 32; o <<= 1) q += __shfl_xor_sync(FULL, q, o);
+                warp_grouped_add(p.psf_sum_weight, a_chan1 * p.n_ip + apol[ip], q, lead);
+            }
         }
     }
 }
@@ -578,14 +646,14 @@ static int env_knob(const char *name, int dflt)   // development knobs (tools/pr
     return e ? atoi(e) : dflt;
 }
 
-template <typename T, bool CPLX, int S, int PP, bool NZ>
+template <typename T, bool CPLX, int S, int PP, bool NZ, bool DUAL = false>
 static int launch_window_t(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
 {
-    using Cfg = WinCfg<T, CPLX, S, PP>;
+    using Cfg = WinCfg<T, CPLX, S, PP, DUAL>;
     constexpr int BLK = 128;
     if (p.n_time == 0 || p.n_baseline == 0 || p.n_chan == 0 || p.n_pol == 0) return CNGI_OK;
     constexpr int kMaxChanWindow = 2048;   // 32 KB of uv-scale table per block at most
-    auto kern = std_grid_window_kernel<T, CPLX, S, PP, BLK, NZ>;
+    auto kern = std_grid_window_kernel<T, CPLX, S, PP, BLK, NZ, DUAL>;
     static const int persist = env_knob("CNGI_WIN_PERSIST", 0);
     for (int c_lo = 0; c_lo < p.n_chan; c_lo += kMaxChanWindow) {
         p.c_lo = c_lo;
@@ -670,6 +738,20 @@ bool window_kernel_supported(const cngi_std_grid_args *a, int table_len)
     const int tsz = a->precision == CNGI_F32 ? 4 : 8;
     const int w = a->support < 4 ? 4 : 8;
     return (long long)n_off * (w * w * tsz + 8) <= 56 * 1024;
+}
+
+// fused image + psf pass (support 7, the one make_image / make_psf use: make_image.py:106-107)
+int launch_window_dual(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
+{
+#ifdef CNGI_WIN_MINIMAL
+    return CNGI_ERR_UNSUPPORTED;
+#else
+    if (a->precision == CNGI_F32)
+        return p.n_pol == 1 ? launch_window_t<float, true, 7, 1, false, true>(p, a, st)
+                            : launch_window_t<float, true, 7, 2, false, true>(p, a, st);
+    return p.n_pol == 1 ? launch_window_t<double, true, 7, 1, false, true>(p, a, st)
+                        : launch_window_t<double, true, 7, 2, false, true>(p, a, st);
+#endif
 }
 
 int launch_window(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from ._devutil import torch, is_torch
-from ._standard_grid import standard_grid
+from ._standard_grid import standard_grid, standard_grid_image_psf
 from ._imaging_weight import imaging_weight_grid, calculate_briggs_parms, _standard_imaging_weight_degrid_numpy_wrap
 from ._gridding_convolutional_kernels import _create_prolate_spheroidal_kernel_1D, correcting_function_1D
 from ._fft import grid_to_image
@@ -57,7 +57,7 @@ def _finish(grid, sum_weight, grid_parms, correct):
     return grid_to_image(grid, grid_parms["image_size"])
 
 
-def synthesis_imaging_chunk(vis_data, uvw, data_weight, flag, freq_chan, grid_parms, imaging_weights_parms):
+def synthesis_imaging_chunk(vis_data, uvw, data_weight, flag, freq_chan, grid_parms, imaging_weights_parms, fused=True):
     """Weights -> PSF -> image for one channel chunk (the shape of _synthesis_imaging_cube_std_chunk :171-220
     without the PB and beam-fit steps, which are not gridding).  Returns image, image_sum_weight, psf, psf_sum_weight
     (images API-side (l, m, chan, pol))."""
@@ -65,6 +65,9 @@ def synthesis_imaging_chunk(vis_data, uvw, data_weight, flag, freq_chan, grid_pa
     gp["oversampling"], gp["support"] = 100, 7
     cgk_1D = _create_prolate_spheroidal_kernel_1D(100, 7)
     w = _make_imaging_weight_chunk(uvw, data_weight, freq_chan, gp, imaging_weights_parms)
+    if fused:   # one pass over uvw / weights / vis for both grids (cngi_b200_standard_grid_image_psf)
+        grid, img_sw, psf_grid, psf_sw = standard_grid_image_psf(vis_data, uvw, w, freq_chan, cgk_1D, gp, flag=flag)
+        return _finish(grid, img_sw, gp, True), img_sw, _finish(psf_grid, psf_sw, gp, True), psf_sw
     psf, psf_sw = _make_psf(uvw, w, freq_chan, cgk_1D, gp, correct=True)
     img, img_sw = _make_image(vis_data, uvw, w, freq_chan, cgk_1D, gp, flag=flag, correct=True)
     return img, img_sw, psf, psf_sw

@@ -100,6 +100,13 @@ typedef struct cngi_std_grid_args {
 } cngi_std_grid_args;
 
 int cngi_b200_standard_grid(const cngi_std_grid_args *args, void *stream);
+/* N1 (fused per-channel pipeline, synthesis_imaging_cube.py:195-211): ONE pass over uvw / weight / vis accumulates the
+   complex image grid exactly as cngi_b200_standard_grid does in image mode (args->grid, args->sum_weight) AND the real
+   psf grid + its sum_weight exactly as the do_psf mode does (psf_grid [n_imag_chan,n_imag_pol,n_u,n_v] real,
+   psf_sum_weight [n_imag_chan,n_imag_pol]); the two share every cell index and tap.  args must describe the image pass
+   (do_psf 0, complex_grid 1).  Support 7 only (make_image.py:106-107); CNGI_ERR_UNSUPPORTED otherwise -- call
+   cngi_b200_standard_grid twice then. */
+int cngi_b200_standard_grid_image_psf(const cngi_std_grid_args *args, void *psf_grid, double *psf_sum_weight, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * A2  imaging-weight density grid: support 1, nearest cell + conjugate cell, pol-averaged weight when
