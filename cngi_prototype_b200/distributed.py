@@ -250,7 +250,7 @@ def make_time_groups(world_size, time_split):
     return groups
 
 
-def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image_out=None):
+def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image_out=None, with_psf=False):
     """Channel-sharded cube imaging with bounded memory (BASELINE config 5; synthesis_imaging_cube.py:105-124,171-220).
 
     Every rank holds (or can slice) the full sample arrays `d` = {vis, uvw, weight, freq_chan[, flag]}.  The image
@@ -265,6 +265,11 @@ def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image
     ops.zeros(shape, complex) allocates; ops.to_image(grid, sum_weight, gp) returns (l, m, chan, pol).
     Returns (image (l, m, n_chan_owned, pol) or None on non-root ranks, sum_weight (n_chan_owned, pol) or None,
     (chan_lo, chan_hi)).
+
+    with_psf: also make the PSF cube of the same samples, the way _synthesis_imaging_cube_std_chunk does
+    (synthesis_imaging_cube.py:195-211) -- through ops.grid_image_psf (ONE fused pass over the chunk's samples filling
+    both grids) when the ops provide it, else through a second ops.standard_grid_psf pass; the psf grid goes through
+    the same reduce and transform.  Returns (image, sum_weight, psf, psf_sum_weight, (chan_lo, chan_hi)) then.
     """
     rank, ws = world()
     cg, n_cg, tp, root = cube_layout(rank, ws, time_split)
@@ -277,6 +282,9 @@ def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image
     gpc = dict(gp, chan_mode="cube")
     grid = ops.zeros((min(step, max(chi - clo, 1)), n_pol, n_u, n_v), True)
     gsw = ops.zeros((grid.shape[0], n_pol), False)
+    pgrid = torch.zeros(tuple(grid.shape), dtype=grid.real.dtype, device=grid.device) if with_psf else None
+    pgsw = ops.zeros((grid.shape[0], n_pol), False) if with_psf else None
+    psf, psf_sum_weight = None, None
     image, sum_weight = image_out, None
     group = groups[cg] if groups else None
     for c0 in range(clo, chi, step):
@@ -287,12 +295,25 @@ def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image
         kw = {}
         if d.get("flag") is not None:
             kw["flag"] = d["flag"][tlo:thi, :, c0:c1]
+        if with_psf:
+            pg, ps = pgrid[:c1 - c0], pgsw[:c1 - c0]
+            pg.zero_()
+            ps.zero_()
         if thi > tlo:
-            ops.standard_grid(d["vis"][tlo:thi, :, c0:c1], d["uvw"][tlo:thi], d["weight"][tlo:thi, :, c0:c1],
-                              d["freq_chan"][c0:c1], cgk, gpc, grid=g, sum_weight=s, **kw)
+            args = (d["uvw"][tlo:thi], d["weight"][tlo:thi, :, c0:c1], d["freq_chan"][c0:c1], cgk, gpc)
+            if with_psf and hasattr(ops, "grid_image_psf"):
+                ops.grid_image_psf(d["vis"][tlo:thi, :, c0:c1], *args, grid=g, sum_weight=s, psf_grid=pg,
+                                   psf_sum_weight=ps, **kw)
+            else:
+                ops.standard_grid(d["vis"][tlo:thi, :, c0:c1], *args, grid=g, sum_weight=s, **kw)
+                if with_psf:
+                    ops.standard_grid_psf(*args, grid=pg, sum_weight=ps)
         if group is not None:
             dist.reduce(_as_real(g), root, group=group)
             dist.reduce(s, root, group=group)
+            if with_psf:
+                dist.reduce(pg, root, group=group)
+                dist.reduce(ps, root, group=group)
         if rank == root:
             img = ops.to_image(g, s, gpc)
             if image is None:
@@ -302,6 +323,15 @@ def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image
                 sum_weight = ops.zeros((chi - clo, n_pol), False)
             image[:, :, c0 - clo:c1 - clo] = img
             sum_weight[c0 - clo:c1 - clo] = s
+            if with_psf:
+                pimg = ops.to_image(pg, ps, gpc)
+                if psf is None:
+                    psf = ops.zeros(tuple(pimg.shape[:2]) + (chi - clo, n_pol), False).to(pimg.dtype)
+                    psf_sum_weight = ops.zeros((chi - clo, n_pol), False)
+                psf[:, :, c0 - clo:c1 - clo] = pimg
+                psf_sum_weight[c0 - clo:c1 - clo] = ps
+    if with_psf:
+        return (image, sum_weight, psf, psf_sum_weight, (clo, chi)) if rank == root else (None, None, None, None, (clo, chi))
     return (image, sum_weight, (clo, chi)) if rank == root else (None, None, (clo, chi))
 
 
@@ -317,6 +347,14 @@ def cuda_ops():
     def grid(vis, uvw, w, freq, cgk, gp, grid=None, sum_weight=None, flag=None):
         return standard_grid(vis, uvw, w, freq, cgk, gp, False, True, grid=grid, sum_weight=sum_weight, flag=flag)
 
+    def grid_image_psf(vis, uvw, w, freq, cgk, gp, grid=None, sum_weight=None, psf_grid=None, psf_sum_weight=None, flag=None):
+        from ._standard_grid import standard_grid_image_psf
+        return standard_grid_image_psf(vis, uvw, w, freq, cgk, gp, flag=flag, grid=grid, sum_weight=sum_weight,
+                                       psf_grid=psf_grid, psf_sum_weight=psf_sum_weight)
+
+    def grid_psf(uvw, w, freq, cgk, gp, grid=None, sum_weight=None):
+        return standard_grid(None, uvw, w, freq, cgk, gp, True, False, grid=grid, sum_weight=sum_weight)
+
     def zeros(shape, is_complex, precision="f32"):
         dt = {("f32", True): torch.complex64, ("f32", False): torch.float64,
               ("f64", True): torch.complex128, ("f64", False): torch.float64}[(precision, bool(is_complex))]
@@ -329,4 +367,5 @@ def cuda_ops():
         return grid_to_image(g, gp["image_size"], sum_weight=s, corr_u=cu, corr_v=cv)
 
     return SimpleNamespace(imaging_weight_grid=imaging_weight_grid, briggs=calculate_briggs_parms, degrid=degrid,
-                           standard_grid=grid, zeros=zeros, to_image=to_image)
+                           standard_grid=grid, standard_grid_psf=grid_psf, grid_image_psf=grid_image_psf, zeros=zeros,
+                           to_image=to_image)

@@ -40,6 +40,11 @@ def oracle_ops():
         grid += torch.from_numpy(g)
         sum_weight += torch.from_numpy(s)
 
+    def std_grid_psf(uvw, w, freq, cgk, gp, grid=None, sum_weight=None):
+        g, s = O._standard_grid_psf_numpy_wrap(uvw.numpy(), w.numpy(), freq.numpy(), cgk, dict(gp, do_psf=True, complex_grid=False))
+        grid += torch.from_numpy(g)
+        sum_weight += torch.from_numpy(s)
+
     def zeros(shape, is_complex):
         return torch.zeros(shape, dtype=torch.complex128 if is_complex else torch.float64)
 
@@ -48,8 +53,8 @@ def oracle_ops():
         img = O.correct_image(O.grid_to_uncorrected_image(g.numpy(), gp["image_size"]), s.numpy(), corr)
         return torch.from_numpy(np.ascontiguousarray(img))
 
-    return SimpleNamespace(imaging_weight_grid=iw_grid, briggs=briggs, degrid=degrid, standard_grid=std_grid, zeros=zeros,
-                           to_image=to_image)
+    return SimpleNamespace(imaging_weight_grid=iw_grid, briggs=briggs, degrid=degrid, standard_grid=std_grid, standard_grid_psf=std_grid_psf,
+                           zeros=zeros, to_image=to_image)
 
 
 def dataset():
@@ -92,10 +97,11 @@ def main():
     gpi = dict(gpc, image_size=np.array([80, 80]))
     img1, sw1, cr1 = D.cube_imaging(oracle_ops(), full, gpi, cgk, chan_chunk=2, time_split=1)
     groups = D.make_time_groups(ws, ws)
-    img2, sw2, cr2 = D.cube_imaging(oracle_ops(), full, gpi, cgk, chan_chunk=4, time_split=ws, groups=groups)
+    img2, sw2, psf2, psw2, cr2 = D.cube_imaging(oracle_ops(), full, gpi, cgk, chan_chunk=4, time_split=ws, groups=groups,
+                                                with_psf=True)
     extra = dict(cube_img=img1.numpy(), cube_img_sw=sw1.numpy(), cube_img_range=np.array(cr1))
     if img2 is not None:
-        extra.update(cube_img_ts=img2.numpy(), cube_img_ts_sw=sw2.numpy())
+        extra.update(cube_img_ts=img2.numpy(), cube_img_ts_sw=sw2.numpy(), cube_psf_ts=psf2.numpy(), cube_psf_ts_sw=psw2.numpy())
     np.savez(os.path.join(out, "rank%d.npz" % rank), **extra, grid=bufs.grid.numpy(), gsw=bufs.gsw.numpy(), iw=iw.numpy(),
              density=bufs.density.numpy(), pipe_grid=pipe_grid, pipe_gsw=pipe_gsw, iw_pipe=iw_pipe.numpy(), cube_grid=gc, cube_sw=sc, chan_range=np.array(D.shard_range(6, rank, ws)),
              time_range=np.array(D.shard_range(24, rank, ws)))

@@ -80,3 +80,9 @@ def test_sharded_step_matches_single_process(tmp_path, oracle, world_size):
     assert "cube_img_ts" in ranks[0] and all("cube_img_ts" not in rk for rk in ranks[1:])
     assert np.max(np.abs(ranks[0]["cube_img_ts"] - ref_img)) <= 1e-12 * np.max(np.abs(ref_img))
     assert np.max(np.abs(ranks[0]["cube_img_ts_sw"] - sc)) <= 1e-12 * np.max(np.abs(sc))
+    # with_psf: the psf cube of the same samples went through the same time-split reduce
+    gp_psf = dict(gpc, do_psf=True, complex_grid=False)
+    pg, ps = oracle._standard_grid_psf_numpy_wrap(d["uvw"], d["weight"], d["freq_chan"], cgk, gp_psf)
+    ref_psf = oracle.correct_image(oracle.grid_to_uncorrected_image(pg, gpi["image_size"]), ps, corr)
+    assert np.max(np.abs(ranks[0]["cube_psf_ts"] - ref_psf)) <= 1e-12 * np.max(np.abs(ref_psf))
+    assert np.max(np.abs(ranks[0]["cube_psf_ts_sw"] - ps)) <= 1e-12 * np.max(np.abs(ps))

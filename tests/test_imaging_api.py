@@ -110,6 +110,10 @@ def test_channel_chunked_cube_equals_unchunked(oracle):
     img, sw, (clo, chi) = D.cube_imaging(ops, T, g, cgk, chan_chunk=2)
     assert (clo, chi) == (0, 7)
     assert rel_err(img.cpu().numpy(), ref["IMAGE"]) <= 1e-12 and rel_err(sw.cpu().numpy(), ref["SUM_WEIGHT"]) <= 1e-12
+    # image + psf cubes from one fused pass per chunk (ops.grid_image_psf -> cngi_b200_standard_grid_image_psf)
+    img, sw, pimg, psw, _ = D.cube_imaging(ops, T, g, cgk, chan_chunk=3, with_psf=True)
+    assert rel_err(img.cpu().numpy(), ref["IMAGE"]) <= 1e-12 and rel_err(pimg.cpu().numpy(), psf["PSF"]) <= 1e-12
+    assert rel_err(psw.cpu().numpy(), psf["PSF_SUM_WEIGHT"]) <= 1e-12
 
 
 @pytest.mark.gpu

@@ -189,6 +189,55 @@ def main():
                                                          gcf["phase_gradient"], ds["freq_chan"], gp))
     add("A6 aperture weight grid", "C3 mosaic, 2048^2 fp32 continuum", d["weight"].size, ms, ds["weight"].size, c,
         cpu_note="single thread")
+    del T, G, grid
+    torch.cuda.empty_cache()
+
+    # ---- section 8(f) rows: N1 fused image+psf, N2 GCF on the device, N3 direction_rotate ------------------------------
+    from cngi_prototype_b200 import direction_rotate as dr, make_gridding_convolution_function as mg
+    d = synth.config_c2(n_time=100 if q else 500, dtype="f32")
+    ds = synth.config_c2(n_time=25, dtype="f64")
+    T = {k: dev(d[k]) for k in ("vis", "uvw", "weight", "freq_chan")}
+    gp = synth.grid_parms_for(4096, d["cell"], chan_mode="continuum")
+    g = torch.zeros((1, 2, 4096, 4096), dtype=torch.complex64, device="cuda")
+    pg = torch.zeros((1, 2, 4096, 4096), dtype=torch.float32, device="cuda")
+    sw, psw = torch.zeros((1, 2), dtype=torch.float64, device="cuda"), torch.zeros((1, 2), dtype=torch.float64, device="cuda")
+    ms_i = gpu_ms(lambda: _standard_grid.standard_grid(T["vis"], T["uvw"], T["weight"], T["freq_chan"], cgk, gp, False, True, grid=g, sum_weight=sw))
+    ms_p = gpu_ms(lambda: _standard_grid.standard_grid(None, T["uvw"], T["weight"], T["freq_chan"], cgk, gp, True, False, grid=pg, sum_weight=psw))
+    ms = gpu_ms(lambda: _standard_grid.standard_grid_image_psf(T["vis"], T["uvw"], T["weight"], T["freq_chan"], cgk, gp, grid=g,
+                                                               sum_weight=sw, psf_grid=pg, psf_sum_weight=psw))
+    add("N1 fused image+psf pass", "C2 ALMA-like fp32 4096^2 continuum", d["weight"].size, ms,
+        two_passes_ms=round(ms_i + ms_p, 3), image_ms=round(ms_i, 3), psf_ms=round(ms_p, 3))
+    del g, pg
+    n_t, n_b = d["uvw"].shape[0], d["uvw"].shape[1]
+    ids = np.arange(7)
+    dirs = np.stack([1.0 + 4e-4 * np.cos(ids), 0.5 + 4e-4 * np.sin(ids)], 1)
+    field = np.repeat((np.arange(n_t) % 7)[:, None], n_b, 1).astype(np.int64)
+    R, P, rid = dr.calc_rotation_mats(field, ids, dirs, dict(new_phase_center=[1.0, 0.5]))
+    Fd, Rd, Pd, rd = dev(field), dev(R), dev(P), dev(rid)
+    ms = gpu_ms(lambda: dr.rotate_chunk(T["vis"], T["uvw"], Fd, T["freq_chan"], Rd, Pd, rd, True, False))
+    fs = field[:25]
+    c = cpu_s(lambda: O.apply_phasor(ds["vis"], O.apply_rotation_matrix(ds["uvw"], fs, R, rid), fs, ds["freq_chan"], P, rid, True, False))
+    add("N3 direction_rotate", "C2/C3 sample shape complex64, 7 fields (through the Python mirror; kernels 0.32 ms, "
+        "profiles/r01_direction_rotate_phasor_f32.txt)", d["weight"].size, ms, ds["weight"].size, c, cpu_note="numpy, single thread")
+    del T
+    torch.cuda.empty_cache()
+    n_ant = 43
+    a1, a2 = np.triu_indices(n_ant, 1)
+    for name, types, dishes, blocks in (("one dish type", np.zeros(n_ant, dtype=int), [10.7], [0.75]),
+                                        ("12 m + 7 m array", (np.arange(n_ant) % 4 == 0).astype(int), [10.7, 6.25], [0.75, 0.75])):
+        gparms = dict(function="casa_airy", list_dish_diameters=np.array(dishes), list_blockage_diameters=np.array(blocks),
+                      unique_ant_indx=types, basline_ant=np.stack([a1, a2], 1), freq_chan=np.linspace(345e9, 347e9, 128),
+                      pol=np.array([0, 1]), field_phase_dir=dirs, phase_center=np.array([1.0, 0.5]), oversampling=[10, 10],
+                      max_support=[15, 15])
+        grid_parms = dict(image_size=np.array([2048, 2048]), image_size_padded=np.array([2048, 2048]),
+                          cell_size=np.array([-0.02, 0.02]) * np.pi / (180 * 3600))
+        out = mg.make_gridding_convolution_function(gparms, grid_parms)
+        ms = gpu_ms(lambda: mg.make_gridding_convolution_function(gparms, grid_parms), n=3, warm=1, reps=2)
+        c = cpu_s(lambda: O.make_gridding_convolution_function(gparms, grid_parms)) if not q else None
+        items = int(out["CONV_KERNEL"].shape[0] * out["CONV_KERNEL"].shape[1])
+        add("N2 make_gridding_convolution_function", "C3: n_pad 2048^2, os 10, max_support 15, 7 fields, %s" % name, items, ms,
+            extra_note="samples column = (antenna-type pair, PB frequency) items; each is two 2048^2 Z2Z FFTs",
+            cpu_oracle_s=None if c is None else round(c, 2), supports=sorted(set(out["SUPPORT"].cpu().numpy().ravel().tolist())))
     print(json.dumps({"rows": rows}))
 
 

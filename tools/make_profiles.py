@@ -31,8 +31,12 @@ def raw_metrics(rep):
 
 summary("r01_window.ncu-rep", "r01_std_grid_window_f32_continuum.txt")
 summary("r01_iw.ncu-rep", "r01_imaging_weight_kernels.txt")
+summary("r01_fused.ncu-rep", "r01_std_grid_window_fused_image_psf_f32.txt")
+summary("r01_dr.ncu-rep", "r01_direction_rotate_phasor_f32.txt")
 shutil.copy(os.path.join(G, "r01_launches.csv"), os.path.join(P, "r01_launches_bench_steps2.csv"))
-for f in ("r01_bench_line.json", "r01_rows.json", "r01_red_peak.json"):
+shutil.copy(os.path.join(G, "r01_next_launches.csv"), os.path.join(P, "r01_gcf_launches.csv"))
+for f in ("r01_bench_line.json", "r01_rows.json", "r01_red_peak.json", "r01_fused.json", "r01_direction_rotate.json",
+          "r01_gcf.json"):
     shutil.copy(os.path.join(G, f), os.path.join(P, f))
 shares = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_shares.py"), os.path.join(G, "r01_launches.csv")],
                         stdout=subprocess.PIPE, text=True).stdout
