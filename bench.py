@@ -409,7 +409,7 @@ def run_b200(a):
                 "note": "not HBM bound: the issue slots (62 % active) and the shared-memory pipe limit it; FP32 floor 0.45 ms/launch (49 taps x 2 pol x 2 FMA per sample); see DESIGN.md section 4.1"}
 
     cb = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only (the N > 1 runs are the scaling series)
         cb, _ = cpu_arm(a, 1, 1, a.cpu_sample_times or 100)
 
     line = {"metric": METRIC, "value": world * n_samples / (ms_step * 1e-3), "unit": "vis/s", "n_gpus": world,

@@ -42,7 +42,7 @@ def _struct_fields(name):
 def test_library_exports_every_declared_symbol(libpath):
     lib = ctypes.CDLL(libpath)
     names = _declared_functions()
-    assert len(names) >= 14
+    assert len(names) >= 21
     for n in names:
         assert hasattr(lib, n), "libcngi_b200.so does not export %s" % n
     from cngi_prototype_b200 import _lib
@@ -54,7 +54,10 @@ def test_library_exports_every_declared_symbol(libpath):
                                           ("cngi_iw_degrid_args", "IwDegridArgs"),
                                           ("cngi_aperture_grid_args", "ApertureGridArgs"),
                                           ("cngi_std_degrid_args", "StdDegridArgs"),
-                                          ("cngi_grid_to_image_args", "GridToImageArgs")])
+                                          ("cngi_grid_to_image_args", "GridToImageArgs"),
+                                          ("cngi_image_to_grid_args", "ImageToGridArgs"),
+                                          ("cngi_direction_rotate_args", "DirectionRotateArgs"),
+                                          ("cngi_gcf_args", "GcfArgs")])
 def test_ctypes_structs_match_header(cname, pyname):
     from cngi_prototype_b200 import _lib
     py = [f[0] for f in getattr(_lib, pyname)._fields_]
