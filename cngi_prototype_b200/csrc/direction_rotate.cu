@@ -283,12 +283,12 @@ extern "C" int cngi_b200_direction_rotate(const cngi_direction_rotate_args *a, v
     CNGI_REQUIRE(a != nullptr, "direction_rotate: args is NULL");
     CNGI_REQUIRE(a->n_time >= 0 && a->n_baseline >= 0 && a->n_chan >= 0 && a->n_pol >= 1, "direction_rotate: bad shape");
     CNGI_REQUIRE(a->n_time * a->n_baseline < (1LL << 31) && a->n_chan < (1LL << 31), "direction_rotate: axis too long");
+    if (a->n_time == 0 || a->n_baseline == 0) return CNGI_OK;   // empty chunk: nothing to do (pointers may be NULL)
     CNGI_REQUIRE(a->uvw && a->field && a->uvw_rotmat && a->phase_rotation && a->rot_field_id && a->n_field >= 1,
                  "direction_rotate: uvw, field, uvw_rotmat, phase_rotation, rot_field_id are required");
     CNGI_REQUIRE((a->vis == nullptr) == (a->vis_rot == nullptr), "direction_rotate: vis and vis_rot go together");
     CNGI_REQUIRE(a->vis == nullptr || a->freq_chan != nullptr, "direction_rotate: freq_chan is required with vis");
     CNGI_REQUIRE(a->precision == CNGI_F32 || a->precision == CNGI_F64, "direction_rotate: bad precision");
-    if (a->n_time == 0 || a->n_baseline == 0) return CNGI_OK;
 
     if (int rc = tune_pool_once()) return rc;
     int *idx = nullptr;

@@ -115,3 +115,16 @@ def test_dataset_form_and_torch():
     vr = out["DATA_ROT"].cpu().numpy()
     m = ~np.isnan(vr)
     assert np.max(np.abs(vr[m] - d["vis_rot"][m])) < 1e-6
+
+
+def test_empty_inputs():
+    """Zero integrations / zero channels: nothing is launched, empty outputs come back (ragged channel counts are in
+    test_against_oracle: 19 channels = one partial 32-lane chunk)."""
+    from cngi_prototype_b200 import direction_rotate as dr
+    R, P, rid = np.eye(3)[None], np.zeros((1, 3)), np.array([0])
+    v, u = dr.rotate_chunk(np.zeros((0, 4, 3, 2), dtype=np.complex128), np.zeros((0, 4, 3)), np.zeros((0, 4), dtype=np.int64),
+                           np.array([1e9, 2e9, 3e9]), R, P, rid)
+    assert v.shape == (0, 4, 3, 2) and u.shape == (0, 4, 3)
+    v, u = dr.rotate_chunk(np.zeros((2, 4, 0, 2), dtype=np.complex64), np.ones((2, 4, 3)), np.zeros((2, 4), dtype=np.int64),
+                           np.zeros(0), R, P, rid)
+    assert v.shape == (2, 4, 0, 2) and np.array_equal(u, np.ones((2, 4, 3)))
