@@ -218,6 +218,8 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     _lib.require_device()
     if world > 1:
+        # rank 0's stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     d = synth.config_c2(n_time=a.n_time, n_chan=a.n_chan, dtype="f32", shard=rank)

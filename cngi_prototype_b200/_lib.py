@@ -119,6 +119,14 @@ class GcfArgs(C.Structure):
     ]
 
 
+class PbArgs(C.Structure):
+    _fields_ = [
+        ("image_size", i64 * 2), ("image_center", i64 * 2), ("cell_size", f64 * 2), ("function", i32), ("ipower", i32),
+        ("n_chan", i64), ("freq_chan_host", vp), ("n_pol", i64), ("n_dish", i64),
+        ("dish_diameter_host", vp), ("blockage_diameter_host", vp), ("pb", vp),
+    ]
+
+
 # every symbol include/cngi_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "cngi_b200_abi_version", "cngi_b200_last_error", "cngi_b200_check_device",
@@ -127,7 +135,7 @@ EXPORTS = [
     "cngi_b200_standard_degrid", "cngi_b200_fft_plan_create", "cngi_b200_fft_plan_destroy",
     "cngi_b200_grid_to_image", "cngi_b200_standard_grid_host", "cngi_b200_microbench_red",
     "cngi_b200_microbench_smem_atomics", "cngi_b200_direction_rotate", "cngi_b200_make_gcf",
-    "cngi_b200_phase_gradient", "cngi_b200_image_to_grid", "cngi_b200_standard_grid_image_psf",
+    "cngi_b200_phase_gradient", "cngi_b200_image_to_grid", "cngi_b200_standard_grid_image_psf", "cngi_b200_make_pb",
 ]
 
 _lib = None
@@ -163,6 +171,7 @@ def lib():
         L.cngi_b200_standard_degrid.argtypes = [C.POINTER(StdDegridArgs), vp]
         L.cngi_b200_direction_rotate.argtypes = [C.POINTER(DirectionRotateArgs), vp]
         L.cngi_b200_image_to_grid.argtypes = [vp, C.POINTER(ImageToGridArgs), vp]
+        L.cngi_b200_make_pb.argtypes = [C.POINTER(PbArgs), vp]
         L.cngi_b200_make_gcf.argtypes = [C.POINTER(GcfArgs), vp]
         L.cngi_b200_phase_gradient.argtypes = [vp, i64, i64, i64, vp, vp]
         L.cngi_b200_microbench_red.argtypes = [vp, i64, i32, i32, i32, vp]

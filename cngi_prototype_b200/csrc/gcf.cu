@@ -187,6 +187,41 @@ __global__ void gcf_phase_gradient_kernel(const double *__restrict__ pix, double
     out[(size_t)f * cu * cv + q] = make_double2(c, s);
 }
 
+
+// ---- make_pb: primary-beam images pb[l, m, chan, pol, dish] = voltage^ipower  (make_pb.py:95-118 with _airy_disk /
+// _casa_airy_disk, _make_pb_symmetric.py:26-132).  One thread per (pixel, chan): consecutive threads write consecutive
+// n_pol * n_dish runs, so the stores are coalesced.
+struct PbParams {
+    double *pb;
+    const double *freq;
+    long long n_items;       // n_l * n_m * n_chan
+    int n_l, n_m, n_chan, n_pol, n_dish, c0, c1, ipower;
+    double cell0, cell1;
+    DishParams dish[8];
+};
+
+__global__ void __launch_bounds__(256) pb_kernel(PbParams p)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_items) return;
+    const int c = (int)(i % p.n_chan);
+    const long long pix = i / p.n_chan;
+    const int m = (int)(pix % p.n_m), l = (int)(pix / p.n_m);
+    const bool centre = (l == p.c0 && m == p.c1);
+    const double x = (double)(l - p.c0) * p.cell0, y = (double)(m - p.c1) * p.cell1;
+    const double k = __ddiv_rn(__dmul_rn(6.283185307179586, p.freq[c]), kSpeedOfLight);
+    const double rad_k = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y))) * k;
+    double *out = p.pb + i * p.n_pol * p.n_dish;
+    for (int d = 0; d < p.n_dish; ++d) {
+        double v = 1.0;
+        if (!centre) {
+            v = voltage(p.dish[d], rad_k);
+            if (p.ipower == 2) v = v * v;
+        }
+        for (int q = 0; q < p.n_pol; ++q) out[q * p.n_dish + d] = v;
+    }
+}
+
 static DishParams dish_params(int function, double dish, double blockage)
 {
     DishParams d;
@@ -300,5 +335,39 @@ extern "C" int cngi_b200_phase_gradient(const double *pix, int64_t n_field, int6
     const dim3 grid((unsigned)ceil_div(cu * cv, 256), (unsigned)n_field);
     gcf_phase_gradient_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pix, (double2 *)phase_gradient, (int)cu, (int)cv);
     CNGI_CUDA_TRY(cudaGetLastError());
+    return CNGI_OK;
+}
+
+extern "C" int cngi_b200_make_pb(const cngi_pb_args *a, void *stream)
+{
+    using namespace cngi;
+    cudaStream_t st = (cudaStream_t)stream;
+    CNGI_REQUIRE(a != nullptr && a->pb != nullptr, "make_pb: null args or output");
+    CNGI_REQUIRE(a->function == CNGI_PB_AIRY || a->function == CNGI_PB_CASA_AIRY, "make_pb: unknown function %d", a->function);
+    CNGI_REQUIRE(a->ipower == 1 || a->ipower == 2, "make_pb: ipower must be 1 (voltage pattern) or 2 (primary beam)");
+    CNGI_REQUIRE(a->image_size[0] > 0 && a->image_size[1] > 0 && a->n_chan > 0 && a->n_pol > 0, "make_pb: empty image");
+    CNGI_REQUIRE(a->n_dish >= 1 && a->n_dish <= 8, "make_pb: 1..8 dish types");
+    CNGI_REQUIRE(a->freq_chan_host && a->dish_diameter_host && a->blockage_diameter_host, "make_pb: host parameter arrays are required");
+    CNGI_REQUIRE(a->image_size[0] < (1LL << 31) && a->image_size[1] < (1LL << 31) && a->n_chan < (1LL << 31), "make_pb: axis too long");
+    if (int rc = tune_pool_once()) return rc;
+    PbParams p{};
+    p.pb = a->pb;
+    p.n_l = (int)a->image_size[0], p.n_m = (int)a->image_size[1], p.n_chan = (int)a->n_chan, p.n_pol = (int)a->n_pol;
+    p.n_dish = (int)a->n_dish, p.c0 = (int)a->image_center[0], p.c1 = (int)a->image_center[1], p.ipower = a->ipower;
+    p.cell0 = a->cell_size[0], p.cell1 = a->cell_size[1];
+    p.n_items = (long long)p.n_l * p.n_m * p.n_chan;
+    for (int d = 0; d < p.n_dish; ++d) p.dish[d] = dish_params(a->function, a->dish_diameter_host[d], a->blockage_diameter_host[d]);
+    double *freq = nullptr;
+    CNGI_CUDA_TRY(cudaMallocAsync((void **)&freq, (size_t)p.n_chan * sizeof(double), st));
+    cudaError_t e = cudaMemcpyAsync(freq, a->freq_chan_host, (size_t)p.n_chan * sizeof(double), cudaMemcpyHostToDevice, st);
+    p.freq = freq;
+    const long long blocks = ceil_div(p.n_items, 256);
+    if (e == cudaSuccess && blocks < (1LL << 31)) {
+        pb_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(freq, st);
+    CNGI_REQUIRE(blocks < (1LL << 31), "make_pb: image cube too large for one launch");
+    CNGI_CUDA_TRY(e);
     return CNGI_OK;
 }

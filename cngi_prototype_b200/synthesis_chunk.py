@@ -57,10 +57,22 @@ def _finish(grid, sum_weight, grid_parms, correct):
     return grid_to_image(grid, grid_parms["image_size"])
 
 
-def synthesis_imaging_chunk(vis_data, uvw, data_weight, flag, freq_chan, grid_parms, imaging_weights_parms, fused=True):
-    """Weights -> PSF -> image for one channel chunk (the shape of _synthesis_imaging_cube_std_chunk :171-220
-    without the PB and beam-fit steps, which are not gridding).  Returns image, image_sum_weight, psf, psf_sum_weight
-    (images API-side (l, m, chan, pol))."""
+def _make_pb(n_pol, freq_chan, pb_parms, grid_parms):
+    """synthesis_imaging_cube.py:262-284: PB of every dish type for the chunk's channels, (l, m, chan, pol, dish)."""
+    from . import make_pb as _mp
+    func = _mp._casa_airy_disk if pb_parms.get("function", "casa_airy") == "casa_airy" else _mp._airy_disk
+    f = freq_chan.cpu().numpy() if is_torch(freq_chan) else np.asarray(freq_chan)
+    return func(f, np.zeros(n_pol), dict(pb_parms, ipower=2), grid_parms)
+
+
+def synthesis_imaging_chunk(vis_data, uvw, data_weight, flag, freq_chan, grid_parms, imaging_weights_parms, fused=True,
+                            pb_parms=None):
+    """Weights -> [PB] -> PSF -> image for one channel chunk (the shape of _synthesis_imaging_cube_std_chunk :171-220
+    without the beam fit, which is image analysis).  Returns image, image_sum_weight, psf, psf_sum_weight
+    (images API-side (l, m, chan, pol)), plus pb (l, m, chan, pol, dish) when pb_parms is given."""
+    if pb_parms is not None:
+        out = synthesis_imaging_chunk(vis_data, uvw, data_weight, flag, freq_chan, grid_parms, imaging_weights_parms, fused)
+        return out + (_make_pb(int(data_weight.shape[3]), freq_chan, pb_parms, grid_parms),)
     gp = dict(grid_parms)
     gp["oversampling"], gp["support"] = 100, 7
     cgk_1D = _create_prolate_spheroidal_kernel_1D(100, 7)

@@ -341,6 +341,25 @@ int cngi_b200_make_gcf(const cngi_gcf_args *args, void *stream);
 int cngi_b200_phase_gradient(const double *pix, int64_t n_field, int64_t cu, int64_t cv, void *phase_gradient,
                              void *stream);
 
+/* make_pb: primary-beam images of each dish type, pb[l, m, chan, pol, dish] = (Airy voltage pattern)^ipower
+   (ngcasa/imaging/make_pb.py:95-118 with _airy_disk / _casa_airy_disk, _imaging_utils/_make_pb_symmetric.py:26-132;
+   make_pb uses ipower 2, synthesis_imaging_cube.py:277 too).  cell_size in radians as given (x negative). */
+typedef struct cngi_pb_args {
+    int64_t image_size[2];
+    int64_t image_center[2];
+    double cell_size[2];
+    int32_t function;               /* CNGI_PB_AIRY / CNGI_PB_CASA_AIRY                                  */
+    int32_t ipower;                 /* 1 voltage pattern, 2 primary beam                                */
+    int64_t n_chan;
+    const double *freq_chan_host;   /* HOST [n_chan] Hz                                                  */
+    int64_t n_pol;                  /* the pattern is replicated over pol (np.tile, :66,:130)            */
+    int64_t n_dish;                 /* <= 8                                                             */
+    const double *dish_diameter_host, *blockage_diameter_host;   /* HOST [n_dish]                        */
+    double *pb;                     /* out float64 [l, m, chan, pol, dish]                              */
+} cngi_pb_args;
+
+int cngi_b200_make_pb(const cngi_pb_args *args, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry point: what a ctypes / cgo-style binding calls with numpy-like HOST arrays.
  * Streams the sample arrays through pinned staging buffers in time chunks (H2D overlapped with the

@@ -621,3 +621,9 @@ def make_gridding_convolution_function(gcf_parms, grid_parms):
                 CF_BASELINE_MAP=cf_bl_map, CF_CHAN_MAP=cf_chan_map, CF_POL_MAP=np.zeros(len(gp["pol"]), dtype=int),
                 PS_CORR_IMAGE=np.ones(tuple(grid_parms["image_size"])), pb_freq=pb_freq, pb_ant_pairs=pairs,
                 oversampling=gp["oversampling"])
+
+
+def airy_disk(freq_chan, n_pol, pb_parms, grid_parms, casa=True):
+    """_make_pb_symmetric.py:79-132 (casa=True) / :26-76: the image-ordered variant, (l, m, chan, pol, dish).  Same
+    arithmetic as airy_disk_rorder (the two reference functions differ only in the axis order of the result)."""
+    return np.moveaxis(airy_disk_rorder(freq_chan, n_pol, pb_parms, grid_parms, casa=casa), (0, 1, 2, 3, 4), (4, 2, 3, 0, 1))

@@ -131,7 +131,26 @@ def gcf():
     save("gcf_chan_maps", **cases)
 
 
+def pb():
+    """_airy_disk / _casa_airy_disk (_make_pb_symmetric.py:26,79) as make_pb.py:95-107 calls them (ipower 2)."""
+    ref_loader.load()
+    pbm = ref_loader._load("ref_make_pb_symmetric", os.path.join(REF, "ngcasa", "imaging", "_imaging_utils",
+                                                                 "_make_pb_symmetric.py"))
+    freq = np.array([100.0e9, 100.7e9, 101.5e9])
+    pol = np.array([0, 1])
+    grid_parms = dict(image_size=np.array([24, 21]), image_center=np.array([12, 10]),
+                      cell_size=np.array([-3.1, 3.1]) * np.pi / (180 * 3600))
+    for tag, func, block in (("casa_airy", pbm._casa_airy_disk, [0.75, 0.0]), ("airy", pbm._airy_disk, [0.75, 0.5])):
+        pb_parms = dict(list_dish_diameters=[10.7, 6.25], list_blockage_diameters=block, ipower=2)
+        out = func(freq, pol, pb_parms, grid_parms)
+        pb_parms["ipower"] = 1
+        out1 = func(freq, pol, pb_parms, grid_parms)
+        save("pb_" + tag, freq_chan=freq, pol=pol, image_size=grid_parms["image_size"], image_center=grid_parms["image_center"],
+             cell_size=grid_parms["cell_size"], dish=np.array(pb_parms["list_dish_diameters"]), blockage=np.array(block),
+             pb=out, voltage=out1)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["direction_rotate", "gcf"]
+    which = sys.argv[1:] or ["direction_rotate", "gcf", "pb"]
     for w in which:
         globals()[w]()

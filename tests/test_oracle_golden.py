@@ -183,3 +183,16 @@ def test_sin_projection_known_answer(oracle):
                                       np.array([180.46846189999996568 * deg, -18.863873247222226581 * deg]),
                                       np.array([-5e-05 * deg, 5e-05 * deg]))
     np.testing.assert_allclose(off[0] + 120, [161.6249842951184803, 119.99951947142589859], rtol=0, atol=2e-9)
+
+
+@pytest.mark.parametrize("tag", ["casa_airy", "airy"])
+def test_make_pb_patterns(oracle, tag):
+    """_airy_disk / _casa_airy_disk (_make_pb_symmetric.py:26,79), ipower 1 and 2: bit-exact."""
+    import os
+    from _util import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "pb_%s.npz" % tag))
+    gp = dict(image_size=d["image_size"], image_center=d["image_center"], cell_size=d["cell_size"])
+    for ipower, key in ((2, "pb"), (1, "voltage")):
+        o = oracle.airy_disk(d["freq_chan"], 2, dict(list_dish_diameters=d["dish"], list_blockage_diameters=d["blockage"],
+                                                     ipower=ipower), gp, casa=(tag == "casa_airy"))
+        assert np.array_equal(o, d[key])
