@@ -14,6 +14,7 @@
 // is written once, transformed in place, and read once for the max/min plus a conv_size^2 window.
 #include "common.cuh"
 #include <cufft.h>
+#include <mutex>
 
 namespace cngi {
 
@@ -222,6 +223,17 @@ __global__ void __launch_bounds__(256) pb_kernel(PbParams p)
     }
 }
 
+// The Z2Z plan (batch 2, n_pad^2) of the last geometry is kept: creating it costs more than one item's kernels.
+// One plan cannot be driven from two host threads at once, so cngi_b200_make_gcf calls are serialised on this mutex.
+static std::mutex g_gcf_mutex;
+static struct {
+    bool valid = false;
+    int dev = -1;
+    long long n0 = 0, n1 = 0;
+    cufftHandle plan = 0;
+    cudaEvent_t done = nullptr;   // end of the last call's work: the next call's stream waits for it before reusing the plan
+} g_gcf_plan;
+
 static DishParams dish_params(int function, double dish, double blockage)
 {
     DishParams d;
@@ -263,13 +275,27 @@ extern "C" int cngi_b200_make_gcf(const cngi_gcf_args *a, void *stream)
                      "make_gcf: antenna-type pair %lld out of range", k);
 
     if (int rc = tune_pool_once()) return rc;
-    cufftHandle plan;
-    int dims[2] = {(int)n0, (int)n1};
-    cufftResult fr = cufftPlanMany(&plan, 2, dims, nullptr, 1, (int)(n0 * n1), nullptr, 1, (int)(n0 * n1), CUFFT_Z2Z, 2);
-    if (fr != CUFFT_SUCCESS) {
-        set_error("make_gcf: cufftPlanMany(%lld x %lld, batch 2) failed with %d", n0, n1, (int)fr);
-        return CNGI_ERR_CUDA;
+    std::lock_guard<std::mutex> lock(g_gcf_mutex);
+    int dev = 0;
+    CNGI_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(g_gcf_plan.valid && g_gcf_plan.dev == dev && g_gcf_plan.n0 == n0 && g_gcf_plan.n1 == n1)) {
+        if (g_gcf_plan.valid) cufftDestroy(g_gcf_plan.plan);
+        g_gcf_plan.valid = false;
+        int dims[2] = {(int)n0, (int)n1};
+        cufftResult fr = cufftPlanMany(&g_gcf_plan.plan, 2, dims, nullptr, 1, (int)(n0 * n1), nullptr, 1, (int)(n0 * n1),
+                                       CUFFT_Z2Z, 2);
+        if (fr != CUFFT_SUCCESS) {
+            set_error("make_gcf: cufftPlanMany(%lld x %lld, batch 2) failed with %d", n0, n1, (int)fr);
+            return CNGI_ERR_CUDA;
+        }
+        g_gcf_plan.valid = true, g_gcf_plan.dev = dev, g_gcf_plan.n0 = n0, g_gcf_plan.n1 = n1;
+        if (g_gcf_plan.done) cudaEventDestroy(g_gcf_plan.done);
+        g_gcf_plan.done = nullptr;
+        CNGI_CUDA_TRY(cudaEventCreateWithFlags(&g_gcf_plan.done, cudaEventDisableTiming));
+    } else {
+        CNGI_CUDA_TRY(cudaStreamWaitEvent(st, g_gcf_plan.done, 0));
     }
+    const cufftHandle plan = g_gcf_plan.plan;
     double2 *planes = nullptr;
     unsigned long long *stats = nullptr;
     int rc = CNGI_OK;
@@ -319,7 +345,7 @@ extern "C" int cngi_b200_make_gcf(const cngi_gcf_args *a, void *stream)
     }
     if (planes) cudaFreeAsync(planes, st);
     if (stats) cudaFreeAsync(stats, st);
-    cufftDestroy(plan);
+    cudaEventRecord(g_gcf_plan.done, st);
     if (rc != CNGI_OK) return rc;
     CNGI_CUDA_TRY(e);
     return CNGI_OK;

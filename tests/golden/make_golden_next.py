@@ -1,12 +1,13 @@
 """Generates the fixtures of the SURVEY.md section 8(f) rows by running the UNMODIFIED reference (this container only).
 
-    NUMBA_CACHE_DIR=/tmp/numba_cache python tests/golden/make_golden_next.py [direction_rotate] [gcf]
+    NUMBA_CACHE_DIR=/tmp/numba_cache python tests/golden/make_golden_next.py [direction_rotate] [gcf] [pb]
 
 direction_rotate_*.npz : /root/reference/ngcasa/imaging/direction_rotate.py:127-248
                          (calc_rotation_mats, apply_rotation_matrix, apply_phasor; the xarray FIELD table is
                          replaced by a 10-line stand-in that implements the one `.sel(field_id=, d1=0)` call)
 gcf_*.npz              : /root/reference/ngcasa/imaging/make_gridding_convolution_function.py:331-457,512-560
                          and _imaging_utils/_make_pb_symmetric.py (see the gcf section below)
+pb_*.npz               : _imaging_utils/_make_pb_symmetric.py:26-132 (_airy_disk, _casa_airy_disk), ipower 1 and 2
 """
 import os
 import sys
