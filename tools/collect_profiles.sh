@@ -17,6 +17,10 @@ ncu --set full --import-source on --clock-control none -k regex:dr_phasor -c 1 -
     python tools/probe_direction_rotate.py > $O/r01_ncu_dr.log 2>&1
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"dr_|gcf_" -c 60 --csv \
     --log-file $O/r01_next_launches.csv python tools/probe_gcf.py > $O/r01_ncu_gcf.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:aperture_track -c 1 -f -o $O/r01_aperture \
+    python tools/probe_aperture.py > $O/r01_ncu_aperture.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:std_degrid_window -c 1 -f -o $O/r01_degrid \
+    python tools/probe_degrid.py > $O/r01_ncu_degrid.log 2>&1
 python tools/probe_fused.py 2> $O/r01_fused.err | tail -1 > $O/r01_fused.json
 python tools/probe_direction_rotate.py 2> $O/r01_dr.err | tail -1 > $O/r01_direction_rotate.json
 python tools/probe_gcf.py --cpu 2> $O/r01_gcf.err | tail -1 > $O/r01_gcf.json
