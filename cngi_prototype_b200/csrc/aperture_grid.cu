@@ -283,7 +283,13 @@ template <typename T, int W, int PP> struct ApTrackCfg {
     static constexpr int WARP_BYTES = 32 * REC_BYTES;
 };
 
-template <typename T, int W, int PP> __global__ void __launch_bounds__(128) aperture_track_kernel(ApParams p)
+// blocks per SM the fp32 16 x 16 instantiation is compiled for: 3 = 168 registers, no spills (2.87 ms on C3);
+// 4 = 128 registers with 36 B of spills inside the tap loop measured 5.31 ms
+#ifndef CNGI_AP_MINB_F32
+#define CNGI_AP_MINB_F32 3
+#endif
+template <typename T, int W, int PP>
+__global__ void __launch_bounds__(128, (sizeof(T) == 4 && W == 16) ? CNGI_AP_MINB_F32 : 1) aperture_track_kernel(ApParams p)
 {
     using Cfg = ApTrackCfg<T, W, PP>;
     using CT = typename Cplx<T>::type;
