@@ -139,7 +139,7 @@ def run_reference(a):
             "config": {"workload": workload_name(a), "note": "CPU arm: each step is a bounded sample of the workload"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "vis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -218,8 +218,6 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     _lib.require_device()
     if world > 1:
-        # rank 0's stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     d = synth.config_c2(n_time=a.n_time, n_chan=a.n_chan, dtype="f32", shard=rank)
@@ -430,9 +428,18 @@ def run_b200(a):
             "gridding_kernel_vis_per_s": n_samples / (kern_ms * 1e-3),
             "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * a.steps, "roofline": roofline, "atomic_roofline": atomic,
             "cpu_baseline": cb}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -441,6 +448,12 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    # stdout carries exactly ONE JSON line (rank 0's): everything libraries print to fd 1 (NCCL's version banner, ...)
+    # is sent to stderr, and the line is written to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
