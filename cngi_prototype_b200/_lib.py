@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("CNGI_B200_LIB") or os.path.join(HERE, "csrc", "libcng
 F32, F64 = 0, 1
 CHAN_GENERAL, CHAN_CUBE, CHAN_CONTINUUM = 0, 1, 2
 ALGO_AUTO, ALGO_NAIVE, ALGO_TRACK, ALGO_SHIFT, ALGO_WINDOW = 0, 1, 2, 3, 4
+ELEM_F32, ELEM_F64, ELEM_C64, ELEM_C128 = 0, 1, 2, 3
 
 i64, i32, f64, vp = C.c_int64, C.c_int32, C.c_double, C.c_void_p
 
@@ -136,6 +137,7 @@ EXPORTS = [
     "cngi_b200_grid_to_image", "cngi_b200_standard_grid_host", "cngi_b200_microbench_red",
     "cngi_b200_microbench_smem_atomics", "cngi_b200_direction_rotate", "cngi_b200_make_gcf",
     "cngi_b200_phase_gradient", "cngi_b200_image_to_grid", "cngi_b200_standard_grid_image_psf", "cngi_b200_make_pb",
+    "cngi_b200_apply_flags",
 ]
 
 _lib = None
@@ -174,6 +176,7 @@ def lib():
         L.cngi_b200_make_pb.argtypes = [C.POINTER(PbArgs), vp]
         L.cngi_b200_make_gcf.argtypes = [C.POINTER(GcfArgs), vp]
         L.cngi_b200_phase_gradient.argtypes = [vp, i64, i64, i64, vp, vp]
+        L.cngi_b200_apply_flags.argtypes = [vp, vp, vp, i64, i32, vp, vp]
         L.cngi_b200_microbench_red.argtypes = [vp, i64, i32, i32, i32, vp]
         L.cngi_b200_microbench_smem_atomics.argtypes = [vp, i32, i32, vp]
         _lib = L

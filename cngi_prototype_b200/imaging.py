@@ -125,6 +125,16 @@ def _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key):
     cgk_1D = _create_prolate_spheroidal_kernel_1D(_gp["oversampling"], _gp["support"])
     wkey = weight_key if weight_key in vis_dataset else "WEIGHT"
     dev = device_of(vis_dataset[wkey], vis_dataset["UVW"])
+    if hasattr(vis_dataset, "iter_device_chunks"):
+        # zarr-backed dataset (read_vis.VisDataset): time blocks are decoded into pinned buffers, copied on a copy stream
+        # and gridded as they arrive -- the reference's per-chunk dask tasks as a three-stage pipeline on one GPU
+        names = [wkey, "UVW"] + ([] if do_psf else ["DATA"] + (["FLAG"] if "FLAG" in vis_dataset else []))
+        freq = _dev(vis_dataset, "chan", dev, torch.float64)
+        grid = sw = None
+        for _, blk in vis_dataset.iter_device_chunks(names, time_chunk, dev):
+            grid, sw = standard_grid(None if do_psf else blk["DATA"], blk["UVW"], blk[wkey], freq, cgk_1D, _gp, do_psf,
+                                     not do_psf, flag=blk.get("FLAG"), grid=grid, sum_weight=sw)
+        return grid, sw, _gp
     w, uvw, freq = _dev(vis_dataset, wkey, dev), _dev(vis_dataset, "UVW", dev, torch.float64), \
         _dev(vis_dataset, "chan", dev, torch.float64)
     vis = None if do_psf else _dev(vis_dataset, "DATA", dev)

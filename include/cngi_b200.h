@@ -18,6 +18,7 @@
  *   ngcasa/imaging/_imaging_utils/_normalize.py:39-89     normalize_image                  -> cngi_b200_grid_to_image (pb/sinc)
  *   ngcasa/imaging/direction_rotate.py:190-248            apply_rotation_matrix/apply_phasor -> cngi_b200_direction_rotate
  *   ngcasa/imaging/make_gridding_convolution_function.py:161-457  a_term GCF            -> cngi_b200_make_gcf, cngi_b200_phase_gradient
+ *   cngi/vis/apply_flags.py:53                            apply_flags (where FLAG == 0)    -> cngi_b200_apply_flags
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer unless its name ends in _host.  Arrays are C-order and
@@ -359,6 +360,20 @@ typedef struct cngi_pb_args {
 } cngi_pb_args;
 
 int cngi_b200_make_pb(const cngi_pb_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * N4  apply_flags (cngi/vis/apply_flags.py:53; the in-place form is synthesis_imaging_cube.py:180):
+ *       out[i] = flag[i] ? NaN : data[i]
+ *     for one data variable with FLAG's dims, both flattened to n_elem.  NaN is what xarray's where() + astype
+ *     produce (fill value of xarray core/dtypes.py maybe_promote): the quiet NaN for reals, (NaN, NaN) for complex
+ *     -- bit-identical to numpy.where(flag == 0, data, fill).astype(dtype).
+ *     out may be data itself (in place: only the flag bytes are read and only flagged elements are written) or a
+ *     disjoint buffer.  n_flagged (optional device counter, added to, never cleared) receives the number of flagged
+ *     elements.  Integer variables are refused (the reference's NaN -> int cast is undefined behaviour).
+ * ---------------------------------------------------------------------------------------------- */
+enum { CNGI_ELEM_F32 = 0, CNGI_ELEM_F64 = 1, CNGI_ELEM_C64 = 2, CNGI_ELEM_C128 = 3 };
+int cngi_b200_apply_flags(const void *data, void *out, const uint8_t *flag, int64_t n_elem, int32_t elem_kind,
+                          uint64_t *n_flagged, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry point: what a ctypes / cgo-style binding calls with numpy-like HOST arrays.

@@ -627,3 +627,20 @@ def airy_disk(freq_chan, n_pol, pb_parms, grid_parms, casa=True):
     """_make_pb_symmetric.py:79-132 (casa=True) / :26-76: the image-ordered variant, (l, m, chan, pol, dish).  Same
     arithmetic as airy_disk_rorder (the two reference functions differ only in the axis order of the result)."""
     return np.moveaxis(airy_disk_rorder(freq_chan, n_pol, pb_parms, grid_parms, casa=casa), (0, 1, 2, 3, 4), (4, 2, 3, 0, 1))
+
+
+# ---- N4: apply_flags ------------------------------------------------------------------------------------------------
+def apply_flags_variable(data, flag):
+    """cngi/vis/apply_flags.py:53 for one variable: ``dv.where(flag == 0).astype(dv.dtype)``.
+
+    xarray (absent from this image; requirements.txt xarray>=0.16) implements DataArray.where(cond) as
+    numpy.where(cond, data, fill) with fill = dtypes.get_fill_value(dtype): NaN for floats, NaN + NaN j for complex
+    (xarray core/dtypes.py, maybe_promote).  PARITY UNPINNED against xarray itself; synthesis_imaging_cube.py:180
+    (``vis_data[flag] = np.nan``) differs only in the imaginary part of flagged complex samples (0 instead of NaN),
+    which no gridder can see (both are masked by the isnan test at _standard_grid.py:340).
+    """
+    data = np.asarray(data)
+    if not (np.issubdtype(data.dtype, np.floating) or np.issubdtype(data.dtype, np.complexfloating)):
+        raise TypeError("apply_flags_variable: float / complex variables only")
+    fill = (np.nan + np.nan * 1j) if np.issubdtype(data.dtype, np.complexfloating) else np.nan
+    return np.where(np.asarray(flag) == 0, data, fill).astype(data.dtype)
