@@ -41,10 +41,11 @@ def _pa_codec(name):
 
 
 def _decompress(codec, payload, n_out):
+    """Decoded payload as a bytes-like object of exactly n_out bytes (a pyarrow buffer is not copied again)."""
     if codec == "zlib":
-        out = zlib.decompress(payload)
+        out = memoryview(zlib.decompress(payload))
     else:
-        out = _pa_codec(codec).decompress(payload, decompressed_size=n_out).to_pybytes()
+        out = memoryview(_pa_codec(codec).decompress(payload, decompressed_size=n_out)).cast("B")
     if len(out) != n_out:
         raise ZarrFormatError("%s payload decoded to %d bytes, expected %d" % (codec, len(out), n_out))
     return out
@@ -63,7 +64,7 @@ def _unshuffle(buf, typesize):
     n = len(buf) // typesize
     a = np.frombuffer(buf, dtype=np.uint8)
     body = a[:n * typesize].reshape(typesize, n).T.reshape(-1)
-    return body.tobytes() + bytes(a[n * typesize:])
+    return body.tobytes() + a[n * typesize:].tobytes()
 
 
 def _shuffle(buf, typesize):
@@ -74,8 +75,10 @@ def _shuffle(buf, typesize):
 
 
 def blosc_decode(frame):
-    """Decodes one c-blosc 1.x frame (see the module docstring for the layout)."""
-    frame = bytes(frame)
+    """Decodes one c-blosc 1.x frame (see the module docstring for the layout) into a bytes-like object.
+
+    Every split is decoded straight into its place in one preallocated buffer (one copy after the codec)."""
+    frame = memoryview(frame).cast("B")
     if len(frame) < 16:
         raise ZarrFormatError("blosc frame shorter than its header")
     version, _vlz, flags, typesize, nbytes, blocksize, cbytes = struct.unpack_from("<BBBBIII", frame, 0)
@@ -97,7 +100,8 @@ def blosc_decode(frame):
     dont_split = bool(flags & 0x10)
     n_blocks = -(-nbytes // blocksize)
     bstarts = struct.unpack_from("<%di" % n_blocks, frame, 16)
-    out = []
+    out = bytearray(nbytes)
+    view = memoryview(out)
     for b in range(n_blocks):
         bsize = min(blocksize, nbytes - b * blocksize)
         leftover = bsize != blocksize
@@ -105,7 +109,7 @@ def blosc_decode(frame):
         n_splits = typesize if split else 1
         ne = bsize // n_splits
         pos = bstarts[b]
-        parts = []
+        dst = b * blocksize
         for _ in range(n_splits):
             (cb,) = struct.unpack_from("<i", frame, pos)
             pos += 4
@@ -113,10 +117,11 @@ def blosc_decode(frame):
                 raise ZarrFormatError("blosc split runs past the end of the frame")
             payload = frame[pos:pos + cb]
             pos += cb
-            parts.append(payload if cb == ne else _decompress(codec, payload, ne))
-        block = b"".join(parts)
-        out.append(_unshuffle(block, typesize) if do_shuffle else block)
-    return b"".join(out)
+            view[dst:dst + ne] = payload if cb == ne else _decompress(codec, payload, ne)
+            dst += ne
+        if do_shuffle:
+            view[b * blocksize:b * blocksize + bsize] = _unshuffle(view[b * blocksize:b * blocksize + bsize], typesize)
+    return out
 
 
 def blosc_encode(raw, typesize, cname="zstd", clevel=2, shuffle=0, blocksize=0):

@@ -53,15 +53,24 @@ __global__ void __launch_bounds__(256) apply_flags_inplace_kernel(typename Elem<
     int mine = 0;
     const uint4 *fv = reinterpret_cast<const uint4 *>(flag + head);
     typename E::type *body = data + head;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
-        const uint4 f = __ldg(fv + i);
-        if ((f.x | f.y | f.z | f.w) == 0u) continue;   // the common case: nothing flagged in these 16 samples
-        const unsigned w[4] = {f.x, f.y, f.z, f.w};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += 4 * stride) {
+        uint4 f4[4];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            if ((w[k >> 2] >> (8 * (k & 3))) & 0xffu) {
-                body[i * 16 + k] = E::nan();
-                ++mine;
+        for (int q = 0; q < 4; ++q)   // four independent 16-byte flag loads in flight
+            f4[q] = (i0 + q * stride < n_vec) ? __ldg(fv + i0 + q * stride) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 f = f4[q];
+            if ((f.x | f.y | f.z | f.w) == 0u) continue;   // the common case: nothing flagged in these 16 samples
+            const long long i = i0 + q * stride;
+            const unsigned w[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if ((w[k >> 2] >> (8 * (k & 3))) & 0xffu) {
+                    body[i * 16 + k] = E::nan();
+                    ++mine;
+                }
             }
         }
     }
@@ -78,7 +87,7 @@ __global__ void __launch_bounds__(256) apply_flags_inplace_kernel(typename Elem<
     count_flagged(mine, n_flagged);
 }
 
-// Out of place: out[i] = flag[i] ? NaN : data[i]
+// Out of place, any alignment: out[i] = flag[i] ? NaN : data[i]
 template <int KIND>
 __global__ void __launch_bounds__(256) apply_flags_copy_kernel(const typename Elem<KIND>::type *__restrict__ data,
                                                                typename Elem<KIND>::type *__restrict__ out,
@@ -112,6 +121,72 @@ __global__ void __launch_bounds__(256) apply_flags_copy_kernel(const typename El
     count_flagged(mine, n_flagged);
 }
 
+// Out of place, 16-byte vectors: a thread moves V = 16 / sizeof(element) consecutive elements per load (data, out
+// 16-byte aligned, flag V-byte aligned), four loads in flight.  The NaN pattern is assembled per 32-bit word.
+template <int KIND> __device__ __forceinline__ unsigned nan_word(int w)
+{
+    if (KIND == CNGI_ELEM_F32 || KIND == CNGI_ELEM_C64) return 0x7fc00000u;
+    return (w & 1) ? 0x7ff80000u : 0u;   // little-endian halves of the float64 quiet NaN
+}
+
+template <int V> __device__ __forceinline__ unsigned load_flags(const unsigned char *p);
+template <> __device__ __forceinline__ unsigned load_flags<1>(const unsigned char *p) { return *p; }
+template <> __device__ __forceinline__ unsigned load_flags<2>(const unsigned char *p)
+{
+    return *reinterpret_cast<const unsigned short *>(p);
+}
+template <> __device__ __forceinline__ unsigned load_flags<4>(const unsigned char *p)
+{
+    return *reinterpret_cast<const unsigned *>(p);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) apply_flags_copy_vec_kernel(const uint4 *__restrict__ data, uint4 *__restrict__ out,
+                                                                   const unsigned char *__restrict__ flag, long long n,
+                                                                   unsigned long long *n_flagged)
+{
+    using E = Elem<KIND>;
+    using T = typename E::type;
+    constexpr int WPE = sizeof(T) / 4;   // 32-bit words per element
+    constexpr int V = 4 / WPE;           // elements per 16-byte vector
+    const long long n_vec = n / V;
+    int mine = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += 4 * stride) {
+        uint4 v[4];
+        unsigned f[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long i = i0 + q * stride;
+            if (i < n_vec) {
+                f[q] = load_flags<V>(flag + i * V);
+                v[q] = data[i];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long i = i0 + q * stride;
+            if (i >= n_vec) break;
+            unsigned w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((f[q] >> (8 * (k / WPE))) & 0xffu) w[k] = nan_word<KIND>(k);
+#pragma unroll
+            for (int e = 0; e < V; ++e) mine += ((f[q] >> (8 * e)) & 0xffu) != 0;
+            out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    if (blockIdx.x == 0) {               // the n % V trailing elements
+        const T *ds = reinterpret_cast<const T *>(data);
+        T *os = reinterpret_cast<T *>(out);
+        for (long long j = n_vec * V + threadIdx.x; j < n; j += blockDim.x) {
+            os[j] = flag[j] ? E::nan() : ds[j];
+            mine += flag[j] != 0;
+        }
+    }
+    count_flagged(mine, n_flagged);
+}
+
 template <int KIND>
 int launch(const void *data, void *out, const unsigned char *flag, long long n, unsigned long long *n_flagged,
            cudaStream_t st)
@@ -128,9 +203,14 @@ int launch(const void *data, void *out, const unsigned char *flag, long long n, 
         const unsigned grid = (unsigned)(blocks < (long long)sms * 8 ? blocks : (long long)sms * 8);
         apply_flags_inplace_kernel<KIND><<<grid, 256, 0, st>>>((T *)out, flag, n, head, n_vec, n_flagged);
     } else {
-        const long long blocks = ceil_div(n, 256 * 4);
+        constexpr int V = 16 / (int)sizeof(T);
+        const bool vec_ok = ((uintptr_t)data % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)flag % V) == 0;
+        const long long blocks = ceil_div(vec_ok ? n / V + 1 : n, 256 * 4);
         const unsigned grid = (unsigned)(blocks < (long long)sms * 8 ? blocks : (long long)sms * 8);
-        apply_flags_copy_kernel<KIND><<<grid, 256, 0, st>>>((const T *)data, (T *)out, flag, n, n_flagged);
+        if (vec_ok)
+            apply_flags_copy_vec_kernel<KIND><<<grid, 256, 0, st>>>((const uint4 *)data, (uint4 *)out, flag, n, n_flagged);
+        else   // sliced views: element-wise
+            apply_flags_copy_kernel<KIND><<<grid, 256, 0, st>>>((const T *)data, (T *)out, flag, n, n_flagged);
     }
     CNGI_CUDA_TRY(cudaGetLastError());
     return CNGI_OK;

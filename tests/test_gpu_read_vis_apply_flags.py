@@ -40,6 +40,10 @@ def test_apply_flags_bit_exact_all_paths(oracle, dtype, n):
         assert r.data_ptr() == d.data_ptr()
         assert np.array_equal(_bits(d.cpu().numpy()), _bits(oracle.apply_flags_variable(x[off:off + n], flag[off:off + n])))
     assert int(cnt.item()) == int(flag[:n].sum() + flag[3:3 + n].sum())
+    # out of place on views that are not 16-byte aligned: the element-wise kernel
+    r = apply_flags_chunk(xd[1:1 + n], fd[1:1 + n])
+    assert np.array_equal(_bits(r.cpu().numpy()), _bits(oracle.apply_flags_variable(x[1:1 + n], flag[1:1 + n])))
+    assert np.array_equal(_bits(xd.cpu().numpy()), _bits(x))          # inputs untouched
 
 
 def test_apply_flags_all_and_none_flagged_and_errors(oracle):
