@@ -24,6 +24,9 @@ ncu --set full --import-source on --clock-control none -k regex:std_degrid_windo
 python tools/probe_fused.py 2> $O/r01_fused.err | tail -1 > $O/r01_fused.json
 python tools/probe_direction_rotate.py 2> $O/r01_dr.err | tail -1 > $O/r01_direction_rotate.json
 python tools/probe_gcf.py --cpu 2> $O/r01_gcf.err | tail -1 > $O/r01_gcf.json
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:apply_flags -c 80 --csv \
+    --log-file $O/r01_apply_flags_launches.csv python tools/probe_apply_flags.py --no-zarr > $O/r01_ncu_apply_flags.log 2>&1
+python tools/probe_apply_flags.py > $O/r01_apply_flags.json 2> $O/r01_apply_flags.err
 python tools/red_peak.py > $O/r01_red_peak.json 2> $O/r01_red_peak.err
 python bench.py > $O/r01_bench_line.json 2> $O/r01_bench.err
 python tools/bench_rows.py > $O/r01_rows.json 2> $O/r01_rows.err

@@ -35,6 +35,9 @@ summary("r01_fused.ncu-rep", "r01_std_grid_window_fused_image_psf_f32.txt")
 summary("r01_dr.ncu-rep", "r01_direction_rotate_phasor_f32.txt")
 shutil.copy(os.path.join(G, "r01_launches.csv"), os.path.join(P, "r01_launches_bench_steps2.csv"))
 shutil.copy(os.path.join(G, "r01_next_launches.csv"), os.path.join(P, "r01_gcf_launches.csv"))
+if os.path.exists(os.path.join(G, "r01_apply_flags_launches.csv")):
+    shutil.copy(os.path.join(G, "r01_apply_flags_launches.csv"), os.path.join(P, "r01_apply_flags_launches.csv"))
+    shutil.copy(os.path.join(G, "r01_apply_flags.json"), os.path.join(P, "r01_apply_flags.json"))
 for f in ("r01_bench_line.json", "r01_rows.json", "r01_red_peak.json", "r01_fused.json", "r01_direction_rotate.json",
           "r01_gcf.json"):
     shutil.copy(os.path.join(G, f), os.path.join(P, f))
