@@ -128,6 +128,13 @@ class PbArgs(C.Structure):
     ]
 
 
+class ZarrChunkJob(C.Structure):
+    _fields_ = [("path", C.c_char_p), ("chunk_shape", i64 * 8), ("src_start", i64 * 8), ("dst_start", i64 * 8),
+                ("extent", i64 * 8)]
+
+
+ZARR_RAW, ZARR_ZLIB, ZARR_BLOSC = 0, 1, 2
+
 # every symbol include/cngi_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "cngi_b200_abi_version", "cngi_b200_last_error", "cngi_b200_check_device",
@@ -137,7 +144,7 @@ EXPORTS = [
     "cngi_b200_grid_to_image", "cngi_b200_standard_grid_host", "cngi_b200_microbench_red",
     "cngi_b200_microbench_smem_atomics", "cngi_b200_direction_rotate", "cngi_b200_make_gcf",
     "cngi_b200_phase_gradient", "cngi_b200_image_to_grid", "cngi_b200_standard_grid_image_psf", "cngi_b200_make_pb",
-    "cngi_b200_apply_flags",
+    "cngi_b200_apply_flags", "cngi_b200_zarr_read_chunks",
 ]
 
 _lib = None
@@ -176,6 +183,7 @@ def lib():
         L.cngi_b200_make_pb.argtypes = [C.POINTER(PbArgs), vp]
         L.cngi_b200_make_gcf.argtypes = [C.POINTER(GcfArgs), vp]
         L.cngi_b200_phase_gradient.argtypes = [vp, i64, i64, i64, vp, vp]
+        L.cngi_b200_zarr_read_chunks.argtypes = [C.POINTER(ZarrChunkJob), i64, vp, C.POINTER(i64), i32, i32, i32, vp, i32]
         L.cngi_b200_apply_flags.argtypes = [vp, vp, vp, i64, i32, vp, vp]
         L.cngi_b200_microbench_red.argtypes = [vp, i64, i32, i32, i32, vp]
         L.cngi_b200_microbench_smem_atomics.argtypes = [vp, i32, i32, vp]

@@ -299,7 +299,38 @@ class ZarrArray:
                 raise NotImplementedError("only ints and slices index a zarr array")
         return bounds, tuple(squeeze)
 
-    def read(self, region=None, out=None, pool=None):
+    def _native_compressor(self):
+        from . import _lib
+        cid = None if self.compressor is None else self.compressor.get("id")
+        return {None: _lib.ZARR_RAW, "zlib": _lib.ZARR_ZLIB, "blosc": _lib.ZARR_BLOSC}.get(cid)
+
+    def _read_native(self, bounds, out, threads):
+        """The region through cngi_b200_zarr_read_chunks (csrc/zarr_chunk_reader.cu): file reads, decoding and the box
+        copies run on native threads without the GIL, straight into `out` (e.g. a pinned staging buffer)."""
+        import ctypes as C
+        from . import _lib
+        comp = self._native_compressor()
+        if comp is None or self.ndim > 8 or not out.flags.c_contiguous:
+            raise NotImplementedError("native chunk reader: compressor %r / layout not supported" % (self.compressor,))
+        ranges = [range(lo // c, (hi - 1) // c + 1) for (lo, hi), c in zip(bounds, self.chunks)]
+        todo = [()]
+        for r in ranges:
+            todo = [t + (i,) for t in todo for i in r]
+        jobs = (_lib.ZarrChunkJob * len(todo))()
+        for job, idx in zip(jobs, todo):
+            f = self.chunk_file(idx)
+            job.path = f.encode() if os.path.exists(f) else None
+            for ax, (i, c, (lo, hi)) in enumerate(zip(idx, self.chunks, bounds)):
+                a, b = max(lo, i * c), min(hi, (i + 1) * c)
+                job.chunk_shape[ax], job.src_start[ax], job.dst_start[ax], job.extent[ax] = c, a - i * c, a - lo, b - a
+        shape = (C.c_int64 * max(self.ndim, 1))(*out.shape)
+        fill = np.ascontiguousarray(self.fill_value.astype(self.dtype))
+        rc = _lib.lib().cngi_b200_zarr_read_chunks(jobs, len(todo), out.ctypes.data, shape, self.ndim, self.dtype.itemsize,
+                                                   comp, fill.ctypes.data, int(threads))
+        _lib.check(rc, "cngi_b200_zarr_read_chunks")
+
+    def read(self, region=None, out=None, pool=None, threads=0):
+        """threads > 0: decode on that many native threads (libcngi_b200.so); otherwise in Python (`pool` optional)."""
         bounds, squeeze = self._normalise(region)
         shape = tuple(hi - lo for lo, hi in bounds)
         if out is None:
@@ -307,7 +338,9 @@ class ZarrArray:
         elif tuple(out.shape) != shape or out.dtype != self.dtype:
             raise ValueError("out has shape %s / dtype %s, the region needs %s / %s"
                              % (tuple(out.shape), out.dtype, shape, self.dtype))
-        if out.size:
+        if out.size and threads:
+            self._read_native(bounds, out, threads)
+        elif out.size:
             ranges = [range(lo // c, (hi - 1) // c + 1) for (lo, hi), c in zip(bounds, self.chunks)]
             todo = [()]
             for r in ranges:

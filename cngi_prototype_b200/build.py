@@ -63,7 +63,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s" % src)
         objs.append(obj)
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
-    link = [nvcc, "-shared", "-o", LIB] + objs + ["-L", cuda_lib, "-lcufft", "-lcudart",
+    link = [nvcc, "-shared", "-o", LIB] + objs + ["-L", cuda_lib, "-lcufft", "-lcudart", "-ldl", "-lpthread",
                                                   "-Xlinker", "-rpath," + cuda_lib]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:

@@ -105,18 +105,23 @@ class VisDataset(Mapping):
                 raise ValueError("%s has dims %s: only variables with a leading time axis are streamed" % (k, a.dims))
         return names
 
-    def iter_host_chunks(self, names=None, time_chunk=0, workers=8):
-        """Yields (time slice, {name: numpy array}) per time block; chunk files are decoded on `workers` threads."""
+    def iter_host_chunks(self, names=None, time_chunk=0, workers=8, native=True):
+        """Yields (time slice, {name: numpy array}) per time block; chunk files are decoded on `workers` threads --
+        native ones (cngi_b200_zarr_read_chunks, no GIL) or, with native=False, a Python thread pool."""
         names = self._names(names)
         with zs.make_pool(workers) as pool:
             for sl in self.time_blocks(time_chunk):
-                yield sl, {k: self._arrays[k].read((sl,), pool=pool) for k in names}
+                if native:
+                    yield sl, {k: self._arrays[k].read((sl,), threads=workers) for k in names}
+                else:
+                    yield sl, {k: self._arrays[k].read((sl,), pool=pool) for k in names}
 
     # ---- device pipeline -------------------------------------------------------------------------------------
-    def iter_device_chunks(self, names=None, time_chunk=0, device=None, workers=8, depth=2):
+    def iter_device_chunks(self, names=None, time_chunk=0, device=None, workers=8, depth=2, native=True):
         """Yields (time slice, {name: CUDA tensor}) per time block.
 
-        Three stages overlap: zarr decode into pinned buffers (reader thread + `workers` decode threads), H2D on a
+        Three stages overlap: zarr decode into pinned buffers (reader thread + `workers` native decode threads,
+        cngi_b200_zarr_read_chunks; native=False decodes in Python instead), H2D on a
         copy stream, and the caller's kernels on the current stream.  `depth` buffer sets (pinned + device) rotate:
         the reader refills a pinned set once its copy has landed, and the copy stream overwrites a device set only
         behind the event recorded after the caller queued its kernels on it (i.e. when the caller asks for the next
@@ -161,7 +166,11 @@ class VisDataset(Mapping):
                         for k in names:
                             a = self._arrays[k]
                             out = pinned[s][k].numpy()[:n]
-                            a.read((sl,), out=out.view(np.bool_) if a.dtype == np.bool_ else out, pool=pool)
+                            out = out.view(np.bool_) if a.dtype == np.bool_ else out
+                            if native:
+                                a.read((sl,), out=out, threads=workers)
+                            else:
+                                a.read((sl,), out=out, pool=pool)
                         host_full[s].release()
             except BaseException as e:          # surfaced in the consumer; never swallowed
                 failure.append(e)

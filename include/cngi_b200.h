@@ -19,6 +19,7 @@
  *   ngcasa/imaging/direction_rotate.py:190-248            apply_rotation_matrix/apply_phasor -> cngi_b200_direction_rotate
  *   ngcasa/imaging/make_gridding_convolution_function.py:161-457  a_term GCF            -> cngi_b200_make_gcf, cngi_b200_phase_gradient
  *   cngi/vis/apply_flags.py:53                            apply_flags (where FLAG == 0)    -> cngi_b200_apply_flags
+ *   cngi/dio/read_vis.py:186-197                          zarr chunk reads (host)          -> cngi_b200_zarr_read_chunks
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer unless its name ends in _host.  Arrays are C-order and
@@ -374,6 +375,23 @@ int cngi_b200_make_pb(const cngi_pb_args *args, void *stream);
 enum { CNGI_ELEM_F32 = 0, CNGI_ELEM_F64 = 1, CNGI_ELEM_C64 = 2, CNGI_ELEM_C128 = 3 };
 int cngi_b200_apply_flags(const void *data, void *out, const uint8_t *flag, int64_t n_elem, int32_t elem_kind,
                           uint64_t *n_flagged, void *stream);
+
+/* N4, host side (no device work): decode zarr v2 chunk files into a box of a C-order HOST array (normally a pinned
+ * staging buffer of the chunk stream) on n_threads native threads -- the per-chunk reads xarray.open_zarr + dask issue in
+ * the reference (cngi/dio/read_vis.py:186-197; chunks written by cngi/dio/append_xds.py:69 with blosc/zstd).
+ * Each job names one chunk file (stored at the FULL chunk shape; NULL or a missing file = fill element) and the box to
+ * copy: decoded_chunk[src_start : src_start + extent] -> dst[dst_start : dst_start + extent].  compressor: RAW, ZLIB, or
+ * BLOSC (c-blosc 1.x frames; zstd / lz4 / zlib codecs, byte shuffle, split and unsplit blocks; bit shuffle, blosclz and
+ * snappy are refused).  Synchronous; all pointers are HOST pointers. */
+enum { CNGI_ZARR_RAW = 0, CNGI_ZARR_ZLIB = 1, CNGI_ZARR_BLOSC = 2 };
+typedef struct cngi_zarr_chunk_job {
+    const char *path;
+    int64_t chunk_shape[8];
+    int64_t src_start[8], dst_start[8], extent[8];
+} cngi_zarr_chunk_job;
+int cngi_b200_zarr_read_chunks(const cngi_zarr_chunk_job *jobs, int64_t n_jobs, void *dst_host, const int64_t *dst_shape,
+                               int32_t ndim, int32_t elem_bytes, int32_t compressor, const void *fill_elem,
+                               int32_t n_threads);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry point: what a ctypes / cgo-style binding calls with numpy-like HOST arrays.

@@ -57,7 +57,8 @@ def test_library_exports_every_declared_symbol(libpath):
                                           ("cngi_grid_to_image_args", "GridToImageArgs"),
                                           ("cngi_image_to_grid_args", "ImageToGridArgs"),
                                           ("cngi_direction_rotate_args", "DirectionRotateArgs"),
-                                          ("cngi_gcf_args", "GcfArgs"), ("cngi_pb_args", "PbArgs")])
+                                          ("cngi_gcf_args", "GcfArgs"), ("cngi_pb_args", "PbArgs"),
+                                          ("cngi_zarr_chunk_job", "ZarrChunkJob")])
 def test_ctypes_structs_match_header(cname, pyname):
     from cngi_prototype_b200 import _lib
     py = [f[0] for f in getattr(_lib, pyname)._fields_]

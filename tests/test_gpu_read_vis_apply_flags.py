@@ -79,8 +79,9 @@ def _store(tmp_path, n_time=30, n_chan=6, compressor="default"):
     return store, d, flag
 
 
+@pytest.mark.parametrize("native", [True, False], ids=["native", "python"])
 @pytest.mark.parametrize("depth", [2, 3])
-def test_device_chunk_pipeline_delivers_every_block(tmp_path, depth):
+def test_device_chunk_pipeline_delivers_every_block(tmp_path, depth, native):
     """Blocks arrive in order with the right contents although pinned / device buffer sets are recycled while the
     previous block's kernels may still be running; early exit does not hang the reader."""
     import torch
@@ -88,7 +89,7 @@ def test_device_chunk_pipeline_delivers_every_block(tmp_path, depth):
     store, d, flag = _store(tmp_path)
     xds = rv.read_vis(store, partition="xds0").xds0
     seen, acc = [], []
-    for sl, blk in xds.iter_device_chunks(["DATA", "UVW", "FLAG"], time_chunk=4, depth=depth, workers=4):
+    for sl, blk in xds.iter_device_chunks(["DATA", "UVW", "FLAG"], time_chunk=4, depth=depth, workers=4, native=native):
         assert all(t.is_cuda for t in blk.values()) and blk["FLAG"].dtype == torch.uint8
         seen.append(sl)
         acc.append({k: t.clone() for k, t in blk.items()})      # queued on the current stream before the set is reused

@@ -176,3 +176,97 @@ def test_oracle_apply_flags_variable_bits(oracle):
         assert (w.view(dt).view(bits).reshape(-1, 2)[flag] == nan).all() and np.array_equal(w[~flag], z[~flag])
     with pytest.raises(TypeError):
         oracle.apply_flags_variable(np.arange(4), np.zeros(4, bool))
+
+
+# ---- native chunk reader (cngi_b200_zarr_read_chunks, host-only code of libcngi_b200.so) ----------------------------
+@pytest.mark.parametrize("comp", COMPRESSORS, ids=lambda c: "raw" if c is None else c["id"] + c.get("cname", ""))
+def test_native_reader_equals_python_decoder(tmp_path, comp):
+    """Two independent decoders (Python + pyarrow/zlib; C++ + libzstd/libz/own lz4) agree byte for byte on full reads,
+    ragged regions, integer indices, several thread counts, every dtype the path stores."""
+    d = _vis()
+    for name, a in d.items():
+        if a.ndim < 2:
+            continue
+        ch = (4, 7, 2, 2)[:a.ndim] if a.ndim != 3 else (4, 7, 3)
+        zs.write_array(str(tmp_path / name), a, chunks=ch, compressor=comp)
+        za = zs.ZarrArray(str(tmp_path / name))
+        for threads in (1, 3):
+            got = za.read(threads=threads)
+            assert got.dtype == a.dtype and np.array_equal(got.view(np.uint8), np.ascontiguousarray(a).view(np.uint8)), name
+        assert np.array_equal(za.read((slice(3, 11),), threads=2), a[3:11])
+        assert np.array_equal(za.read((slice(2, 9), slice(1, 6)), threads=2), a[2:9, 1:6])
+        assert np.array_equal(za.read((-1, 2), threads=1), a[-1, 2])
+        assert za.read((slice(5, 5),), threads=2).shape == (0,) + a.shape[1:]
+
+
+def test_native_reader_split_frames_missing_chunks_and_errors(tmp_path):
+    from cngi_prototype_b200 import _lib
+    # the hand-assembled split / shuffled / stored / left-over frame of the test above, as a chunk file
+    rng = np.random.default_rng(5)
+    x = np.cumsum(rng.integers(0, 3, 300)).astype(np.float64)
+    raw = x.tobytes()
+    blocks = []
+    for b in range(3):
+        blk = np.frombuffer(raw[b * 1024:(b + 1) * 1024], np.uint8)
+        sh = blk.reshape(len(blk) // 8, 8).T.reshape(-1).tobytes()
+        if len(blk) == 1024:
+            enc = [zlib.compress(sh[k * 128:(k + 1) * 128]) for k in range(8)]
+            enc[0] = sh[:128]
+            blocks.append(enc)
+        else:
+            blocks.append([zlib.compress(sh)])
+    zs.write_array(str(tmp_path / "X"), x, chunks=(300,), compressor={"id": "blosc", "cname": "zlib", "clevel": 5, "shuffle": 1})
+    with open(tmp_path / "X" / "0", "wb") as f:
+        f.write(_frame((3 << 5) | 0x1, 8, raw, 1024, blocks))
+    za = zs.ZarrArray(str(tmp_path / "X"))
+    assert np.array_equal(za.read(threads=1), x) and np.array_equal(za.read(), x)
+    # lz4 frames with long literal / match runs (length bytes of 255) and overlapping matches
+    y = np.zeros(5000, np.int32)
+    y[::7] = 3
+    y[1000:1300] = np.arange(300)
+    zs.write_array(str(tmp_path / "Y"), y, chunks=(5000,), compressor={"id": "blosc", "cname": "lz4", "clevel": 5, "shuffle": 0})
+    assert np.array_equal(zs.ZarrArray(str(tmp_path / "Y")).read(threads=1), y)
+    # missing chunk -> fill value; NaN fill for floats
+    a = np.arange(24, dtype=np.float64).reshape(6, 4)
+    zs.write_array(str(tmp_path / "A"), a, chunks=(2, 4), fill_value=float("nan"), compressor=rv.DEFAULT_COMPRESSOR)
+    os.remove(tmp_path / "A" / "1.0")
+    got = zs.ZarrArray(str(tmp_path / "A")).read(threads=2)
+    assert np.array_equal(got[:2], a[:2]) and np.isnan(got[2:4]).all() and np.array_equal(got[4:], a[4:])
+    # corrupt frames are errors, not garbage
+    good = open(tmp_path / "A" / "0.0", "rb").read()
+    with open(tmp_path / "A" / "0.0", "wb") as f:
+        f.write(good[:-3])
+    with pytest.raises(_lib.CngiError, match="blosc header size"):
+        zs.ZarrArray(str(tmp_path / "A")).read(threads=1)
+    with open(tmp_path / "A" / "0.0", "wb") as f:
+        f.write(good[:2] + bytes([good[2] | 0x4]) + good[3:])                # bit shuffle
+    with pytest.raises(_lib.CngiError, match="bit shuffle"):
+        zs.ZarrArray(str(tmp_path / "A")).read(threads=1)
+    zs.write_array(str(tmp_path / "R"), a, chunks=(2, 4))
+    with open(tmp_path / "R" / "0.0", "ab") as f:
+        f.write(b"x")
+    with pytest.raises(_lib.CngiError, match="wrong size"):
+        zs.ZarrArray(str(tmp_path / "R")).read(threads=1)
+    # argument checks of the C entry point
+    L = _lib.lib()
+    job = (_lib.ZarrChunkJob * 1)()
+    job[0].chunk_shape[0], job[0].extent[0] = 4, 5                           # box leaves its chunk
+    out = np.zeros(8)
+    import ctypes as C
+    shape = (C.c_int64 * 1)(8)
+    assert L.cngi_b200_zarr_read_chunks(job, 1, out.ctypes.data, shape, 1, 8, _lib.ZARR_RAW, out.ctypes.data, 1) == 1
+    assert L.cngi_b200_zarr_read_chunks(job, 1, out.ctypes.data, shape, 1, 8, 7, out.ctypes.data, 1) == 1
+    assert L.cngi_b200_zarr_read_chunks(None, 0, None, None, 1, 8, 0, None, 1) == 0
+
+
+def test_host_chunk_walk_native_and_python_agree(tmp_path):
+    d = _vis()
+    store = rv.write_vis(str(tmp_path / "v.zarr"), d, chunks={"time": 4, "chan": 2})
+    xds = rv.read_vis(store, partition="xds0").xds0
+    a = list(xds.iter_host_chunks(time_chunk=5, workers=3, native=True))
+    b = list(xds.iter_host_chunks(time_chunk=5, workers=3, native=False))
+    assert [s for s, _ in a] == [s for s, _ in b]
+    for (_, x), (_, y) in zip(a, b):
+        assert set(x) == set(y) == {"DATA", "UVW", "WEIGHT", "FLAG", "FIELD_ID"}
+        for k in x:
+            assert x[k].dtype == y[k].dtype and np.array_equal(x[k], y[k]), k

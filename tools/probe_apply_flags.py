@@ -52,14 +52,15 @@ try:
     cell = d["cell"] / imaging.ARCSEC_TO_RAD
     gp = {"image_size": [1024, 1024], "cell_size": [cell, cell], "fft_padding": 1.2, "chan_mode": "continuum"}
     res = {}
-    for workers in (1, 4, 16):
-        imaging.make_image(xds, gp, weight_key="WEIGHT")          # warm (page cache, cuFFT plan)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _, blk in xds.iter_device_chunks(["DATA", "UVW", "WEIGHT", "FLAG"], workers=workers):
-            pass
-        torch.cuda.synchronize()
-        res["read_only_s_workers%d" % workers] = time.perf_counter() - t0
+    imaging.make_image(xds, gp, weight_key="WEIGHT")              # warm (page cache, cuFFT plan)
+    for native in (True, False):
+        for workers in (1, 4, 8, 16):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _, blk in xds.iter_device_chunks(["DATA", "UVW", "WEIGHT", "FLAG"], workers=workers, native=native):
+                pass
+            torch.cuda.synchronize()
+            res["read_only_s_%s_workers%d" % ("native" if native else "python", workers)] = time.perf_counter() - t0
     t0 = time.perf_counter()
     img = imaging.make_image(xds, gp, weight_key="WEIGHT")
     torch.cuda.synchronize()
