@@ -2,8 +2,8 @@
 
 Mirrors cngi/vis/apply_flags.py:53 -- `apply_flags(mxds, vis, flags='FLAG')`: every data variable of partition `vis`
 whose dims equal a flag variable's dims becomes `dv.where(flag == 0).astype(dv.dtype)`, i.e. NaN (complex: NaN + NaN j,
-xarray's fill value for complex dtypes) where flagged; the flag variables themselves and variables of other dims are passed through; a copy of the mxds with the
-new partition is returned (mxds_copier, cngi/_utils/_io.py:28).  The masking runs in cngi_b200_apply_flags
+xarray's fill value for complex dtypes) where flagged; the flag variables themselves and variables of other dims are
+passed through; a copy of the mxds with the new partition is returned (mxds_copier, cngi/_utils/_io.py:28).  The masking runs in cngi_b200_apply_flags
 (csrc/apply_flags.cu); outputs are CUDA tensors.  Integer / bool variables with FLAG's dims (the reference casts NaN
 back to int, undefined behaviour) raise instead of being guessed.
 """

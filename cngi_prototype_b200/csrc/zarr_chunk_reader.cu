@@ -14,6 +14,7 @@
 
 #include <atomic>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -90,6 +91,22 @@ bool lz4_block_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap)
     return op == oend;
 }
 
+// Scratch that grows without being zero-filled (std::vector::resize would add a memset pass over every chunk).
+struct Scratch {
+    std::unique_ptr<uint8_t[]> p;
+    size_t cap = 0, len = 0;
+    void resize(size_t n)
+    {
+        if (n > cap) {
+            p.reset(new uint8_t[n]);
+            cap = n;
+        }
+        len = n;
+    }
+    uint8_t *data() { return p.get(); }
+    size_t size() const { return len; }
+};
+
 enum { CODEC_LZ4 = 1, CODEC_ZLIB = 3, CODEC_ZSTD = 4 };
 
 // payload -> exactly n_out bytes at dst.  Returns an error text or nullptr.
@@ -116,7 +133,7 @@ const char *codec_decode(int codec, const uint8_t *payload, size_t n_in, uint8_t
 uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 
 // One c-blosc 1.x frame -> dst (exactly n_out bytes).  tmp is scratch for shuffled blocks.
-const char *blosc_decode(const uint8_t *f, size_t n, uint8_t *dst, size_t n_out, std::vector<uint8_t> &tmp)
+const char *blosc_decode(const uint8_t *f, size_t n, uint8_t *dst, size_t n_out, Scratch &tmp)
 {
     if (n < 16) return "blosc frame shorter than its header";
     const unsigned version = f[0], flags = f[2], typesize = f[3];
@@ -169,7 +186,7 @@ const char *blosc_decode(const uint8_t *f, size_t n, uint8_t *dst, size_t n_out,
     return nullptr;
 }
 
-bool read_file(const char *path, std::vector<uint8_t> &buf, bool &missing)
+bool read_file(const char *path, Scratch &buf, bool &missing)
 {
     missing = false;
     FILE *fh = fopen(path, "rb");
@@ -206,7 +223,7 @@ struct Reader {
 
     void run()
     {
-        std::vector<uint8_t> file, chunk, tmp;
+        Scratch file, chunk, tmp;
         for (;;) {
             const int64_t j = next.fetch_add(1);
             if (j >= n_jobs) return;

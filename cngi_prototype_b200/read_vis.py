@@ -143,7 +143,7 @@ class VisDataset(Mapping):
             return np.dtype(np.uint8) if a.dtype == np.bool_ else a.dtype
 
         pinned = [{k: torch.empty((max_t,) + self._arrays[k].shape[1:], dtype=torch.from_numpy(
-            np.empty(0, np_dtype(self._arrays[k]))).dtype).pin_memory() for k in names} for _ in range(depth)]
+            np.empty(0, np_dtype(self._arrays[k]))).dtype, pin_memory=True) for k in names} for _ in range(depth)]
         on_dev = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in pinned[0].items()} for _ in range(depth)]
         copy_stream = torch.cuda.Stream(device=dev)
         copied = [None] * depth          # event: H2D of the set finished (recorded on the copy stream)
@@ -156,14 +156,15 @@ class VisDataset(Mapping):
 
         def reader():
             try:
-                with zs.make_pool(workers) as pool:
+                with zs.make_pool(workers) as pool, zs.make_pool(len(names)) as var_pool:
                     for i, sl in enumerate(blocks):
                         s = i % depth
                         host_free[s].acquire()
                         if stop.is_set():
                             return
                         n = sl.stop - sl.start
-                        for k in names:
+
+                        def fill(k, s=s, n=n, sl=sl):
                             a = self._arrays[k]
                             out = pinned[s][k].numpy()[:n]
                             out = out.view(np.bool_) if a.dtype == np.bool_ else out
@@ -171,6 +172,12 @@ class VisDataset(Mapping):
                                 a.read((sl,), out=out, threads=workers)
                             else:
                                 a.read((sl,), out=out, pool=pool)
+
+                        if native:                     # the variables of a block are read concurrently (no GIL inside)
+                            list(var_pool.map(fill, names))
+                        else:
+                            for k in names:
+                                fill(k)
                         host_full[s].release()
             except BaseException as e:          # surfaced in the consumer; never swallowed
                 failure.append(e)

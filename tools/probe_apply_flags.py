@@ -39,47 +39,52 @@ for name, dt, kind, eb in (("c64", torch.complex64, _lib.ELEM_C64, 8), ("c128", 
 if "--no-zarr" in sys.argv:          # kernel launches only (the ncu launch list)
     print(json.dumps(out))
     sys.exit(0)
-d = synth.config_c1(n_time=200, n_chan=64)
+d = synth.config_c1(n_time=600, n_chan=64)
 fl = np.random.default_rng(2).random(d["vis"].shape) < 0.02
-tmp = tempfile.mkdtemp(prefix="cngi_zarr_")
-try:
-    t0 = time.perf_counter()
-    store = rv.write_vis(os.path.join(tmp, "c1.vis.zarr"), {"DATA": d["vis"], "UVW": d["uvw"], "WEIGHT": d["weight"], "FLAG": fl,
-                                                            "chan": d["freq_chan"]}, chunks={"time": 20, "chan": 16})
-    t_write = time.perf_counter() - t0
-    nbytes = sum(os.path.getsize(os.path.join(r, f)) for r, _, fs in os.walk(store) for f in fs)
-    xds = rv.read_vis(store, partition="xds0").xds0
-    cell = d["cell"] / imaging.ARCSEC_TO_RAD
-    gp = {"image_size": [1024, 1024], "cell_size": [cell, cell], "fft_padding": 1.2, "chan_mode": "continuum"}
-    res = {}
-    imaging.make_image(xds, gp, weight_key="WEIGHT")              # warm (page cache, cuFFT plan)
-    for native in (True, False):
-        for workers in (1, 4, 8, 16):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _, blk in xds.iter_device_chunks(["DATA", "UVW", "WEIGHT", "FLAG"], workers=workers, native=native):
-                pass
-            torch.cuda.synchronize()
-            res["read_only_s_%s_workers%d" % ("native" if native else "python", workers)] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    img = imaging.make_image(xds, gp, weight_key="WEIGHT")
-    torch.cuda.synchronize()
-    t_stream = time.perf_counter() - t0
-    mem = {"DATA": torch.as_tensor(d["vis"]).cuda(), "UVW": torch.as_tensor(d["uvw"]).cuda(),
-           "WEIGHT": torch.as_tensor(d["weight"]).cuda(), "FLAG": torch.as_tensor(fl).cuda().view(torch.uint8),
-           "chan": d["freq_chan"]}
-    imaging.make_image(mem, gp, weight_key="WEIGHT")
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    img2 = imaging.make_image(mem, gp, weight_key="WEIGHT")
-    torch.cuda.synchronize()
-    t_mem = time.perf_counter() - t0
-    a, b = img["IMAGE"], img2["IMAGE"].cpu().numpy()
-    res.update(samples=int(d["vis"].size), store_bytes=nbytes, raw_bytes=int(d["vis"].nbytes + d["weight"].nbytes + fl.nbytes + d["uvw"].nbytes),
-               write_s=t_write, make_image_streamed_s=t_stream, make_image_in_memory_s=t_mem,
-               streamed_Mvis_per_s=d["vis"].size / t_stream / 1e6, raw_GB_per_s=(d["vis"].nbytes + d["weight"].nbytes) / t_stream / 1e9,
-               rel_diff_streamed_vs_memory=float(np.abs(a - b).max() / np.abs(b).max()), host_cores=os.cpu_count())
-    out["read_vis"] = res
-finally:
-    shutil.rmtree(tmp, ignore_errors=True)
+cell = d["cell"] / imaging.ARCSEC_TO_RAD
+gp = {"image_size": [1024, 1024], "cell_size": [cell, cell], "fft_padding": 1.2, "chan_mode": "continuum"}
+NAMES = ["DATA", "UVW", "WEIGHT", "FLAG"]
+raw_bytes = int(d["vis"].nbytes + d["weight"].nbytes + fl.nbytes + d["uvw"].nbytes)
+mem = {"DATA": torch.as_tensor(d["vis"]).cuda(), "UVW": torch.as_tensor(d["uvw"]).cuda(),
+       "WEIGHT": torch.as_tensor(d["weight"]).cuda(), "FLAG": torch.as_tensor(fl).cuda().view(torch.uint8),
+       "chan": d["freq_chan"]}
+imaging.make_image(mem, gp, weight_key="WEIGHT")
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+img2 = imaging.make_image(mem, gp, weight_key="WEIGHT")
+torch.cuda.synchronize()
+t_mem = time.perf_counter() - t0
+out["read_vis"] = {"samples": int(d["vis"].size), "raw_bytes": raw_bytes, "host_cores": os.cpu_count(),
+                   "make_image_in_memory_s": t_mem, "time_block": 20, "stores": {}}
+# two chunkings of the same samples: 4 and 16 chunk files per variable and 20-integration block
+for label, chunks in (("chunks_20x351x16x2", {"time": 20, "chan": 16}), ("chunks_5x351x16x2", {"time": 5, "chan": 16})):
+    tmp = tempfile.mkdtemp(prefix="cngi_zarr_")
+    try:
+        t0 = time.perf_counter()
+        store = rv.write_vis(os.path.join(tmp, "c1.vis.zarr"), {"DATA": d["vis"], "UVW": d["uvw"], "WEIGHT": d["weight"],
+                                                                "FLAG": fl, "chan": d["freq_chan"]}, chunks=chunks)
+        t_write = time.perf_counter() - t0
+        nbytes = sum(os.path.getsize(os.path.join(r, f)) for r, _, fs in os.walk(store) for f in fs)
+        xds = rv.read_vis(store, partition="xds0").xds0
+        res = {"store_bytes": nbytes, "write_s": t_write}
+        imaging.make_image(xds, gp, weight_key="WEIGHT", time_chunk=20)      # warm (page cache, cuFFT plan)
+        for native in (True, False):
+            for workers in (1, 8, 16):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _, blk in xds.iter_device_chunks(NAMES, time_chunk=20, workers=workers, native=native):
+                    pass
+                torch.cuda.synchronize()
+                res["read_only_s_%s_workers%d" % ("native" if native else "python", workers)] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        img = imaging.make_image(xds, gp, weight_key="WEIGHT", time_chunk=20)
+        torch.cuda.synchronize()
+        t_stream = time.perf_counter() - t0
+        a, b = img["IMAGE"], img2["IMAGE"].cpu().numpy()
+        res.update(make_image_streamed_s=t_stream, streamed_Mvis_per_s=d["vis"].size / t_stream / 1e6,
+                   raw_GB_per_s=raw_bytes / t_stream / 1e9,
+                   rel_diff_streamed_vs_memory=float(np.abs(a - b).max() / np.abs(b).max()))
+        out["read_vis"]["stores"][label] = res
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 print(json.dumps(out))
