@@ -1,0 +1,105 @@
+"""BASELINE configs 2 and 4 at FULL size on the GPU, checked through size-independent properties (the oracle would take
+minutes to hours at these sizes; it covers the same code at small sizes in the other test files).
+
+  config 2: Briggs(0.5) imaging weights + standard gridding, ALMA-like 903 bl x 500 t x 128 ch x 2 pol = 115.6 M samples,
+            4096^2, fp32, continuum -- bench.py's workload.
+  config 4: degridding predict, 27 antennas (351 bl) x 1000 t x 64 ch x 2 pol = 44.9 M samples, 4096^2, S=7, fp64.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ALGO_NAIVE, ALGO_TRACK, ALGO_WINDOW = 1, 2, 4
+
+
+def test_full_size_config2_weights_and_gridding_properties():
+    import torch
+    from cngi_prototype_b200 import synth, _imaging_weight as iw, _standard_grid as sg
+    from cngi_prototype_b200._gridding_convolutional_kernels import _create_prolate_spheroidal_kernel_1D
+    d = synth.config_c2()
+    assert d["weight"].size == 500 * 903 * 128 * 2 and d["vis"].dtype == np.complex64
+    vis, uvw, w, freq = (torch.as_tensor(d[k]).cuda() for k in ("vis", "uvw", "weight", "freq_chan"))
+    n = 4096
+    gpw = synth.grid_parms_for(n, d["cell"], chan_mode="continuum", support=1, oversampling=0, do_psf=True,
+                               complex_grid=False, do_imaging_weight=True)
+    # A2: every on-grid sample adds its pol-averaged weight to its cell and to the conjugate cell, and twice to sum_weight
+    rho, sw = iw.imaging_weight_grid(uvw, w, freq, gpw)
+    assert rho.dtype == torch.float64 and tuple(rho.shape) == (1, 2, n, n)
+    assert float(((rho.sum(dim=(2, 3)) - sw).abs() / sw).max()) < 1e-12
+    assert torch.equal(rho[:, 0], rho[:, 1]) and float(rho.min()) >= 0
+    # A3: Briggs factors against their definition evaluated with torch on the same density
+    bf = iw.calculate_briggs_parms(rho, sw, {"weighting": "briggs", "robust": 0.5})
+    f0 = (5 * 10 ** -0.5) ** 2 / ((rho * rho).sum(dim=(2, 3)) / sw)
+    assert float(((bf[0] - f0).abs() / f0).max()) < 1e-12 and bool((bf[1] == 1).all())
+    # A4: imaging weight = pol-averaged natural weight / (f0 rho + 1) <= natural; 0 where the uv point is NaN;
+    #     per-sample, so a time slice on its own is bit-identical to the slice of the full result
+    iwt = iw._standard_imaging_weight_degrid_numpy_wrap(rho, uvw, w, bf, freq, gpw, kernel_side_layout=True)
+    avg = ((w[..., 0] + w[..., 1]) / 2)[..., None].expand_as(w)
+    fin = torch.isfinite(iwt) & torch.isfinite(avg)
+    assert bool((iwt[fin] >= 0).all()) and bool((iwt[fin] <= avg[fin] * (1 + 1e-6)).all())
+    assert float(fin.float().mean()) > 0.99
+    bad_uv = torch.isnan(uvw[..., 0]) | torch.isnan(uvw[..., 1])
+    assert bool(bad_uv.any()) and bool((iwt[bad_uv] == 0).all())
+    part = iw._standard_imaging_weight_degrid_numpy_wrap(rho, uvw[100:150], w[100:150], bf, freq, gpw, kernel_side_layout=True)
+    assert torch.equal(torch.nan_to_num(part, nan=-1.0), torch.nan_to_num(iwt[100:150], nan=-1.0))
+    del avg, fin, part
+    # A1 fp32 continuum with those weights: product (window), track and naive kernels agree, masks identical
+    cgk = _create_prolate_spheroidal_kernel_1D(100, 7)
+    gp = synth.grid_parms_for(n, d["cell"], chan_mode="continuum")
+    g_w, s_w = sg._standard_grid_numpy_wrap(vis, uvw, iwt, freq, cgk, gp, algorithm=ALGO_WINDOW)
+    assert g_w.dtype == torch.complex64 and tuple(g_w.shape) == (1, 2, n, n)
+    scale = float(g_w.abs().max())
+    for algo in (ALGO_TRACK, ALGO_NAIVE):
+        g_o, s_o = sg._standard_grid_numpy_wrap(vis, uvw, iwt, freq, cgk, gp, algorithm=algo)
+        assert bool(((g_o != 0) == (g_w != 0)).all()), algo
+        assert float((g_o - g_w).abs().max()) / scale < 1e-5, algo
+        assert float(((s_o - s_w).abs() / s_w.abs()).max()) < 1e-6, algo
+        del g_o
+    # time-chunked accumulation into one device grid == one call
+    g_c = s_c = None
+    for t0 in range(0, 500, 125):
+        g_c, s_c = sg.standard_grid(vis[t0:t0 + 125], uvw[t0:t0 + 125], iwt[t0:t0 + 125], freq, cgk, gp, False, True,
+                                    grid=g_c, sum_weight=s_c)
+    assert bool(((g_c != 0) == (g_w != 0)).all()) and float((g_c - g_w).abs().max()) / scale < 1e-5
+    assert float(((s_c - s_w).abs() / s_w.abs()).max()) < 1e-6
+    # linearity: power-of-two scaling commutes with every fp32 rounding (only the atomic order differs)
+    g_2, _ = sg._standard_grid_numpy_wrap(vis * 2, uvw, iwt, freq, cgk, gp, algorithm=ALGO_WINDOW)
+    assert float((g_2 - 2 * g_w).abs().max()) / scale < 1e-5
+    del g_2, g_c
+    # psf mode: the plane sum equals sum_weight (both are sum_samples w * sum_taps conv)
+    g_p, s_p = sg._standard_grid_psf_numpy_wrap(uvw, iwt, freq, cgk, dict(gp, do_psf=True, complex_grid=False))
+    assert g_p.dtype == torch.float32
+    assert float(((g_p.double().sum(dim=(2, 3)) - s_p).abs() / s_p).max()) < 1e-5
+
+
+def test_full_size_config4_degrid_is_the_adjoint_of_the_gridder():
+    """<grid(x), y> == <x, degrid(y)> at 4096^2 for 44.9 M fp64 samples (no reference implementation exists for the
+    predict, SURVEY section 8a A7: adjointness with the parity-checked gridder is the full-size check), window and
+    gather degrid kernels agree, samples the gridder would skip come back as exact zeros."""
+    import torch
+    from cngi_prototype_b200 import synth, _standard_grid as sg, _standard_degrid as sd
+    from cngi_prototype_b200._gridding_convolutional_kernels import _create_prolate_spheroidal_kernel_1D
+    d = synth.config_c4()
+    d["uvw"].reshape(-1, 3)[::997, 0] = np.nan                                   # a few rows without a uv point
+    uvw, freq = torch.as_tensor(d["uvw"]).cuda(), torch.as_tensor(d["freq_chan"]).cuda()
+    n_t, n_b, n_c, n_p = 1000, 351, 64, 2
+    n = 4096
+    cgk = _create_prolate_spheroidal_kernel_1D(100, 7)
+    gp = synth.grid_parms_for(n, d["cell"], chan_mode="continuum")
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    y = torch.randn((1, n_p, n, n, 2), dtype=torch.float64, device="cuda", generator=gen)
+    y = torch.view_as_complex(y)
+    v = sd._standard_degrid_numpy_wrap(y, uvw, freq, cgk, gp)                      # auto = window kernel
+    assert tuple(v.shape) == (n_t, n_b, n_c, n_p) and v.dtype == torch.complex128
+    v1 = sd._standard_degrid_numpy_wrap(y, uvw, freq, cgk, gp, algorithm=1)        # gather kernel
+    assert float((v - v1).abs().max() / v.abs().max()) < 1e-12
+    del v1
+    bad_uv = torch.isnan(uvw[..., 0]) | torch.isnan(uvw[..., 1])
+    assert bool(bad_uv.any()) and bool((v[bad_uv] == 0).all())
+    x = torch.view_as_complex(torch.randn((n_t, n_b, n_c, n_p, 2), dtype=torch.float64, device="cuda", generator=gen))
+    ones = torch.ones((n_t, n_b, n_c, n_p), dtype=torch.float64, device="cuda")
+    g, _ = sg._standard_grid_numpy_wrap(x, uvw, ones, freq, cgk, gp)
+    lhs = torch.vdot(y.reshape(-1), g.reshape(-1))
+    rhs = torch.vdot(v.reshape(-1), x.reshape(-1))
+    assert float((lhs - rhs).abs() / lhs.abs()) < 1e-11
