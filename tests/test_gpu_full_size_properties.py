@@ -103,3 +103,64 @@ def test_full_size_config4_degrid_is_the_adjoint_of_the_gridder():
     lhs = torch.vdot(y.reshape(-1), g.reshape(-1))
     rhs = torch.vdot(v.reshape(-1), x.reshape(-1))
     assert float((lhs - rhs).abs() / lhs.abs()) < 1e-11
+
+
+def test_config3_size_aperture_gridders_properties():
+    """BASELINE config 3 at the size DESIGN.md's rows quote (903 bl x 200 t x 64 ch x 2 pol = 23.1 M samples, 7-pointing
+    mosaic, CF 160^2 with supports 9..15, 2048^2, continuum):
+      * psf mode: Re(sum of a grid plane) == sum_weight of that plane (grid += conv * w, sum_weight += w * Re(sum conv),
+        _aperture_grid.py:496-511);
+      * fp32 agrees with fp64 to 1e-5 with identical support masks (index math is fp64 in both);
+      * time-chunked accumulation into one device grid == one call;
+      * the weight gridder touches at most max_support^2 cells per plane, centred on the grid (:276-287), and its
+        plane sum also equals sum_weight."""
+    import torch
+    from cngi_prototype_b200 import synth, _aperture_grid as ap
+    d32 = synth.config_c2(n_time=200, n_chan=64, dtype="f32")
+    gcf = synth.make_mosaic_gcf(d32["n_baseline"], 64, 2, n_field=7)
+    field = synth.mosaic_field_column(d32["uvw"].shape[0], d32["n_baseline"], gcf["field_id"])
+    n = 2048
+    gp = synth.grid_parms_for(n, d32["cell"] * 1.1, chan_mode="continuum")
+    gp["oversampling"], gp["field_id"] = gcf["oversampling"], gcf["field_id"]
+    uvw, freq, fld = (torch.as_tensor(x).cuda() for x in (d32["uvw"], d32["freq_chan"], field))
+    G = {k: torch.as_tensor(v).cuda() for k, v in gcf.items()}
+    maps = (G["cf_baseline_map"], G["cf_chan_map"], G["cf_pol_map"])
+    w32, v32 = torch.as_tensor(d32["weight"]).cuda(), torch.as_tensor(d32["vis"]).cuda()
+    w64, v64 = w32.double(), v32.to(torch.complex128)
+
+    def image(v, w, **kw):
+        return ap._aperture_grid_numpy_wrap(v, uvw, w, fld, *maps, G["conv_kernel"], gcf["weight_support"],
+                                            G["phase_gradient"], freq, gp, **kw)
+
+    def psf(w):
+        return ap._aperture_psf_grid_numpy_wrap(uvw, w, fld, *maps, G["conv_kernel"], gcf["weight_support"],
+                                                G["phase_gradient"], freq, gp)
+
+    p64, ps64 = psf(w64)
+    assert p64.dtype == torch.complex128 and tuple(p64.shape) == (1, 2, n, n)
+    assert float(((p64.sum(dim=(2, 3)).real - ps64).abs() / ps64).max()) < 1e-11
+    p32, ps32 = psf(w32)
+    assert float(((p32.to(torch.complex128).sum(dim=(2, 3)).real - ps32).abs() / ps32).max()) < 1e-5
+    del p64, p32
+    g64, s64 = image(v64, w64)
+    g32, s32 = image(v32, w32)
+    scale = float(g64.abs().max())
+    assert bool(((g32 != 0) == (g64 != 0)).all())
+    assert float((g32.to(torch.complex128) - g64).abs().max()) / scale < 1e-5
+    assert float(((s32 - s64).abs() / s64.abs()).max()) < 1e-6
+    del g32
+    gc = sc = None
+    for t0 in range(0, 200, 50):
+        sl = slice(t0, t0 + 50)
+        gc, sc = ap._aperture_grid_numpy_wrap(v64[sl], uvw[sl], w64[sl], fld[sl], *maps, G["conv_kernel"],
+                                              gcf["weight_support"], G["phase_gradient"], freq, gp, grid=gc, sum_weight=sc)
+    assert bool(((gc != 0) == (g64 != 0)).all()) and float((gc - g64).abs().max()) / scale < 1e-12
+    assert float(((sc - s64).abs() / s64.abs()).max()) < 1e-12
+    del gc, g64
+    gw, sw = ap._aperture_weight_grid_numpy_wrap(uvw, w64, fld, *maps, G["weight_conv_kernel"], gcf["weight_support"],
+                                                 G["phase_gradient"], freq, gp)
+    ms = int(np.max(gcf["weight_support"]))
+    nz = (gw != 0).nonzero()
+    assert 0 < nz.shape[0] <= 2 * ms * ms
+    assert int((nz[:, 2] - n // 2).abs().max()) <= ms // 2 and int((nz[:, 3] - n // 2).abs().max()) <= ms // 2
+    assert float(((gw.sum(dim=(2, 3)).real - sw).abs() / sw.abs()).max()) < 1e-11
