@@ -164,3 +164,32 @@ def test_config3_size_aperture_gridders_properties():
     assert 0 < nz.shape[0] <= 2 * ms * ms
     assert int((nz[:, 2] - n // 2).abs().max()) <= ms // 2 and int((nz[:, 3] - n // 2).abs().max()) <= ms // 2
     assert float(((gw.sum(dim=(2, 3)).real - sw).abs() / sw.abs()).max()) < 1e-11
+
+
+def test_config5_grid_size_cube_chunked_through_one_buffer():
+    """BASELINE config 5's grid (8192^2 image, padded to 9830 = 2 * 5 * 983 per side, fp32 cube) on a few channels:
+      * the cube driver that walks `chan_chunk` planes at a time through one grid buffer gives, channel for channel, the
+        image of that channel gridded on its own (chunk invariance -- what sharding the cube by channel relies on);
+      * PSF: the centre pixel of every plane is 1 / (PS correcting image at the centre): the plane sum of the uv-grid
+        equals sum_weight, so ifft -> / sum_weight is exactly 1 there (make_psf.py:117-130), and it is the plane's maximum."""
+    import torch
+    from cngi_prototype_b200 import synth, imaging
+    from cngi_prototype_b200._gridding_convolutional_kernels import correcting_function_1D
+    d = synth.config_c1(n_time=200, n_chan=6, dtype="f32")
+    cell_arcsec = d["cell"] / imaging.ARCSEC_TO_RAD
+    ds = {"DATA": torch.as_tensor(d["vis"]).cuda(), "UVW": torch.as_tensor(d["uvw"]).cuda(),
+          "WEIGHT": torch.as_tensor(d["weight"]).cuda(), "chan": d["freq_chan"]}
+    gp = {"image_size": [8192, 8192], "cell_size": [cell_arcsec, cell_arcsec], "fft_padding": 1.2, "chan_mode": "cube"}
+    psf = imaging.make_psf(ds, gp, weight_key="WEIGHT", chan_chunk=4)
+    P = psf["PSF"]
+    assert tuple(P.shape) == (8192, 8192, 6, 2) and P.dtype == torch.float32
+    cu, cv = correcting_function_1D(np.array([9830, 9830]), np.array([8192, 8192]))
+    centre = 1.0 / (cu[4096] * cv[4096])
+    assert float((P[4096, 4096] - centre).abs().max()) < 1e-5
+    assert float(P.amax(dim=(0, 1)).sub(P[4096, 4096]).abs().max()) == 0.0
+    img = imaging.make_image(ds, gp, weight_key="WEIGHT", chan_chunk=4)
+    one = {k: (v[5:6] if k == "chan" else (v[:, :, 5:6] if getattr(v, "ndim", 0) == 4 else v)) for k, v in ds.items()}
+    img5 = imaging.make_image(one, gp, weight_key="WEIGHT")
+    a, b = img["IMAGE"][:, :, 5], img5["IMAGE"][:, :, 0]
+    assert float((a - b).abs().max() / b.abs().max()) < 1e-5
+    assert float(((img["SUM_WEIGHT"][5] - img5["SUM_WEIGHT"][0]).abs() / img5["SUM_WEIGHT"][0]).max()) < 1e-6

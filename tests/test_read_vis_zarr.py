@@ -270,3 +270,38 @@ def test_host_chunk_walk_native_and_python_agree(tmp_path):
         assert set(x) == set(y) == {"DATA", "UVW", "WEIGHT", "FLAG", "FIELD_ID"}
         for k in x:
             assert x[k].dtype == y[k].dtype and np.array_equal(x[k], y[k]), k
+
+
+@pytest.mark.parametrize("world_size", [2, 3])
+def test_rank_shards_read_only_their_part_of_the_store(tmp_path, world_size, monkeypatch):
+    """distributed.time_shard / channel_shard slice lazy zarr arrays like in-memory ones, so each rank of a multi-GPU
+    job reads only the chunk files that intersect its shard (samples shard, nothing is exchanged
+    before the grid reduce)."""
+    from cngi_prototype_b200 import distributed as D
+    d = _vis(shape=(12, 7, 6, 2))
+    store = rv.write_vis(str(tmp_path / "v.zarr"), d, chunks={"time": 2, "chan": 2}, compressor=None)
+    xds = rv.read_vis(store, partition="xds0").xds0
+    lazy = {"vis": xds["DATA"], "uvw": xds["UVW"], "weight": xds["WEIGHT"], "freq_chan": xds["chan"]}
+    mem = {"vis": d["DATA"], "uvw": d["UVW"], "weight": d["WEIGHT"], "freq_chan": d["chan"]}
+    opened = []
+    real = zs.ZarrArray.read_chunk
+
+    def spy(self, idx):
+        opened.append((os.path.basename(self.path), idx))
+        return real(self, idx)
+
+    monkeypatch.setattr(zs.ZarrArray, "read_chunk", spy)
+    for rank in range(world_size):
+        a, b = D.time_shard(lazy, rank, world_size), D.time_shard(mem, rank, world_size)
+        for k in ("vis", "uvw", "weight"):
+            assert np.array_equal(np.asarray(a[k]), b[k]), k
+        lo, hi = D.shard_range(12, rank, world_size)
+        mine = {i for n, i in opened if n == "DATA"}
+        assert mine and all(lo // 2 <= i[0] <= (hi - 1) // 2 for i in mine)      # only this rank's time chunks
+        opened.clear()
+        a, b = D.channel_shard(lazy, rank, world_size), D.channel_shard(mem, rank, world_size)
+        assert np.array_equal(np.asarray(a["vis"]), b["vis"]) and np.array_equal(np.asarray(a["freq_chan"]), b["freq_chan"])
+        lo, hi = D.shard_range(6, rank, world_size)
+        mine = {i for n, i in opened if n == "DATA"}
+        assert mine and all(lo // 2 <= i[2] <= (hi - 1) // 2 for i in mine)      # only this rank's channel chunks
+        opened.clear()
