@@ -11,6 +11,12 @@
 #include "common.cuh"
 
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cerrno>
 
 #include <atomic>
 #include <cstring>
@@ -186,22 +192,41 @@ const char *blosc_decode(const uint8_t *f, size_t n, uint8_t *dst, size_t n_out,
     return nullptr;
 }
 
-bool read_file(const char *path, Scratch &buf, bool &missing)
-{
-    missing = false;
-    FILE *fh = fopen(path, "rb");
-    if (!fh) {
-        missing = true;
-        return true;
+// A chunk file mapped read-only: stored (uncompressed) payloads are then copied once, page cache -> destination.
+struct MappedFile {
+    const uint8_t *p = nullptr;
+    size_t n = 0;
+    bool open(const char *path, bool &missing)
+    {
+        missing = false;
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) {
+            missing = errno == ENOENT;
+            return missing;
+        }
+        struct stat st;
+        bool ok = fstat(fd, &st) == 0;
+        if (ok && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+            ok = m != MAP_FAILED;
+            if (ok) {
+                p = (const uint8_t *)m;
+                n = (size_t)st.st_size;
+            }
+        }
+        ::close(fd);
+        return ok;
     }
-    fseek(fh, 0, SEEK_END);
-    const long n = ftell(fh);
-    fseek(fh, 0, SEEK_SET);
-    buf.resize(n > 0 ? (size_t)n : 0);
-    const bool ok = n >= 0 && fread(buf.data(), 1, buf.size(), fh) == buf.size();
-    fclose(fh);
-    return ok;
-}
+    void close()
+    {
+        if (p) munmap((void *)p, n);
+        p = nullptr;
+        n = 0;
+    }
+    ~MappedFile() { close(); }
+    const uint8_t *data() const { return p; }
+    size_t size() const { return n; }
+};
 
 struct Reader {
     const cngi_zarr_chunk_job *jobs;
@@ -223,7 +248,7 @@ struct Reader {
 
     void run()
     {
-        Scratch file, chunk, tmp;
+        Scratch chunk, tmp;
         for (;;) {
             const int64_t j = next.fetch_add(1);
             if (j >= n_jobs) return;
@@ -236,13 +261,18 @@ struct Reader {
             for (int d = 0; d < ndim; ++d) chunk_elems *= (size_t)job.chunk_shape[d];
             const size_t chunk_bytes = chunk_elems * elem;
             bool missing = true;
-            if (job.path && !read_file(job.path, file, missing)) return fail(std::string("cannot read ") + job.path);
+            MappedFile file;
+            if (job.path && !file.open(job.path, missing)) return fail(std::string("cannot read ") + job.path);
             const uint8_t *src = nullptr;
             if (!missing) {
                 const char *e = nullptr;
                 if (compressor == CNGI_ZARR_RAW) {
                     if (file.size() != chunk_bytes) e = "raw chunk file has the wrong size";
                     src = file.data();
+                } else if (compressor == CNGI_ZARR_BLOSC && file.size() == 16 + chunk_bytes && file.size() >= 16 &&
+                           (file.data()[2] & 0x2) && file.data()[0] == 2 && rd32(file.data() + 4) == chunk_bytes &&
+                           rd32(file.data() + 12) == file.size()) {
+                    src = file.data() + 16;   // blosc kept the chunk uncompressed (memcpy frame): copy it once
                 } else {
                     chunk.resize(chunk_bytes);
                     src = chunk.data();

@@ -15,6 +15,7 @@ from cngi_prototype_b200 import _zarr_store as zs
 from cngi_prototype_b200 import read_vis as rv
 
 COMPRESSORS = [None, {"id": "zlib", "level": 1}, rv.DEFAULT_COMPRESSOR,
+               {"id": "blosc", "cname": "zstd", "clevel": 0, "shuffle": 0, "blocksize": 0},      # memcpy frames
                {"id": "blosc", "cname": "lz4", "clevel": 5, "shuffle": 1, "blocksize": 0},
                {"id": "blosc", "cname": "zlib", "clevel": 5, "shuffle": 1, "blocksize": 256}]
 
@@ -27,7 +28,7 @@ def _vis(seed=3, shape=(13, 7, 5, 2)):
             "chan": np.linspace(1.0e9, 1.1e9, shape[2])}
 
 
-@pytest.mark.parametrize("comp", COMPRESSORS, ids=lambda c: "raw" if c is None else c["id"] + c.get("cname", ""))
+@pytest.mark.parametrize("comp", COMPRESSORS, ids=lambda c: "raw" if c is None else c["id"] + c.get("cname", "") + str(c.get("clevel", "")))
 def test_array_round_trip_ragged_chunks_and_regions(tmp_path, comp):
     a = _vis()["DATA"]
     zs.write_array(str(tmp_path / "DATA"), a, chunks=(4, 7, 2, 2), compressor=comp, dims=rv.SAMPLE_DIMS)
@@ -179,7 +180,7 @@ def test_oracle_apply_flags_variable_bits(oracle):
 
 
 # ---- native chunk reader (cngi_b200_zarr_read_chunks, host-only code of libcngi_b200.so) ----------------------------
-@pytest.mark.parametrize("comp", COMPRESSORS, ids=lambda c: "raw" if c is None else c["id"] + c.get("cname", ""))
+@pytest.mark.parametrize("comp", COMPRESSORS, ids=lambda c: "raw" if c is None else c["id"] + c.get("cname", "") + str(c.get("clevel", "")))
 def test_native_reader_equals_python_decoder(tmp_path, comp):
     """Two independent decoders (Python + pyarrow/zlib; C++ + libzstd/libz/own lz4) agree byte for byte on full reads,
     ragged regions, integer indices, several thread counts, every dtype the path stores."""
