@@ -33,20 +33,17 @@ class VisDataset(Mapping):
     def __init__(self, path, chunks=None):
         self.path = path
         paths, self.attrs = zs.open_group(path)
-        self._arrays = {k: zs.ZarrArray(p) for k, p in paths.items() if self._readable(p)}
+        self._arrays = {}
+        for k, p in paths.items():
+            try:
+                self._arrays[k] = zs.ZarrArray(p)
+            except NotImplementedError:      # string tables (object dtype + vlen filter): not needed for imaging
+                pass
         self.dims = {}
         for a in self._arrays.values():
             for d, n in zip(a.dims, a.shape):
                 self.dims[d] = n
         self._chunks_override = dict(chunks or {})
-
-    @staticmethod
-    def _readable(p):
-        try:
-            zs.ZarrArray(p)
-            return True
-        except NotImplementedError:          # string tables (object dtype + vlen filter): not needed for imaging
-            return False
 
     # ---- mapping protocol ----------------------------------------------------------------------------------
     def __getitem__(self, key):
@@ -74,12 +71,9 @@ class VisDataset(Mapping):
         """{'time': n, 'baseline': n, 'chan': n, 'pol': n}: the zarr chunking of DATA (or of the first 4-d variable),
         overridden by read_vis(chunks=) -- what `IMAGING_WEIGHT.data.numblocks` encodes in the reference
         (_standard_grid.py:35)."""
-        out = {}
-        for a in self._arrays.values():
-            if a.dims == SAMPLE_DIMS:
-                out = dict(zip(a.dims, a.chunks))
-                if a is self._arrays.get("DATA"):
-                    break
+        sample_vars = [a for a in self._arrays.values() if a.dims == SAMPLE_DIMS]
+        first = self._arrays["DATA"] if "DATA" in self._arrays else (sample_vars[0] if sample_vars else None)
+        out = dict(zip(first.dims, first.chunks)) if first is not None else {}
         for a in self._arrays.values():
             for d, c in zip(a.dims, a.chunks):
                 out.setdefault(d, c)
