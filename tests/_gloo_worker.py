@@ -12,7 +12,7 @@ import torch.distributed as dist
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 
-from cngi_prototype_b200 import synth, distributed as D  # noqa: E402
+from cngi_prototype_b200 import synth, distributed as D, read_vis as rv  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 IW = dict(weighting="briggs", robust=0.5)
@@ -74,7 +74,18 @@ def main():
     cgk = O._create_prolate_spheroidal_kernel_1D(100, 7)
     full = {k: torch.from_numpy(np.ascontiguousarray(d[k])) for k in ("vis", "uvw", "weight", "freq_chan")}
     # continuum: time sharding + all-reduce(density) + reduce(grid)
-    shard = D.time_shard(full, rank, ws)
+    # ... read by every rank from a zarr store: lazy arrays, so a rank decodes only the chunk files of its time shard
+    store = os.path.join(out, "sim.vis.zarr")
+    if rank == 0:
+        rv.write_vis(store, {"DATA": d["vis"], "UVW": d["uvw"], "WEIGHT": d["weight"], "chan": d["freq_chan"]},
+                     chunks={"time": 5, "chan": 4})
+    dist.barrier()
+    xds = rv.read_vis(store, partition="xds0").xds0
+    lazy = {"vis": xds["DATA"], "uvw": xds["UVW"], "weight": xds["WEIGHT"], "freq_chan": xds["chan"]}
+    shard = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in D.time_shard(lazy, rank, ws).items()}
+    for k, v in D.time_shard(full, rank, ws).items():
+        assert torch.equal(torch.nan_to_num(shard[k].view(torch.float64) if shard[k].is_complex() else shard[k]),
+                           torch.nan_to_num(v.view(torch.float64) if v.is_complex() else v)), k
     bufs = SimpleNamespace(density=torch.zeros((1, 2, n, n), dtype=torch.float64), dsw=torch.zeros((1, 2), dtype=torch.float64),
                            grid=torch.zeros((1, 2, n, n), dtype=torch.complex128), gsw=torch.zeros((1, 2), dtype=torch.float64))
     iw = D.continuum_imaging_step(oracle_ops(), shard, gp, gp_iw, IW, cgk, bufs)
