@@ -97,42 +97,65 @@ def cpu_step(O, d, gp, gp_iw, cgk, n_threads):
                                               n_threads=n_threads)
     bf = O._calculate_briggs_parms(rho, sw, IW_PARMS)
     iw = O._standard_imaging_weight_degrid_numpy_wrap(np.moveaxis(rho, (0, 1), (2, 3)), d["uvw"], d["weight"], bf,
-                                                      d["freq_chan"], gp_iw)
+                                                      d["freq_chan"], gp_iw, n_threads=n_threads)
     g, s = O._standard_grid_numpy_wrap(d["vis"], d["uvw"], iw, d["freq_chan"], cgk, gp, n_threads=n_threads)
     return g, s
 
 
-def cpu_arm(a, steps, warmup, sample_times):
+def cpu_arm(a, steps, warmup, sample_times=0, budget_s=150.0):
+    """Times `steps` steps of the CPU path over the first `sample_times` integrations of the workload.
+    sample_times = 0: sized from two short calibration steps (t = fixed + slope * integrations; the fixed part is the
+    zero-fill and sum of the per-thread grids) so that steps + warmup fit in budget_s, capped at the whole workload."""
     from oracle import oracle as O
     from cngi_prototype_b200 import synth
     O.build()
     cores = os.cpu_count() or 1
     n_threads = max(1, min(cores, 32))   # continuum: one private 4096^2 c128 grid per thread (as the reference's chunks)
-    d = synth.config_c2(n_time=sample_times, n_chan=a.n_chan, dtype="f64", shard=0)
+    full = synth.config_c2(n_time=a.n_time if not sample_times else sample_times, n_chan=a.n_chan, dtype="f64", shard=0)
     cgk = O._create_prolate_spheroidal_kernel_1D(OVERSAMPLING, SUPPORT)
-    gp = synth.grid_parms_for(a.n_uv, d["cell"], chan_mode=a.chan_mode)
-    gp_iw = synth.grid_parms_for(a.n_uv, d["cell"], chan_mode=a.chan_mode, support=1, oversampling=0, do_psf=True,
+    gp = synth.grid_parms_for(a.n_uv, full["cell"], chan_mode=a.chan_mode)
+    gp_iw = synth.grid_parms_for(a.n_uv, full["cell"], chan_mode=a.chan_mode, support=1, oversampling=0, do_psf=True,
                                  complex_grid=False, do_imaging_weight=True)
+
+    def first(n):
+        d = dict(full)
+        for k in ("vis", "uvw", "weight"):
+            d[k] = full[k][:n]
+        return d
+
+    def run(d):
+        t0 = time.perf_counter()
+        cpu_step(O, d, gp, gp_iw, cgk, n_threads)
+        return time.perf_counter() - t0
+
+    n_all = full["weight"].shape[0]
+    how = "fixed by --cpu-sample-times"
+    if not sample_times:
+        n_a, n_b = min(8, n_all), min(40, n_all)
+        run(first(n_a))                                   # library load, thread start-up
+        t_a, t_b = run(first(n_a)), run(first(n_b))
+        slope = max((t_b - t_a) / max(n_b - n_a, 1), 1e-6)
+        fixed = max(t_a - slope * n_a, 0.0)
+        sample_times = int(max(n_b, min(n_all, (budget_s / max(steps + warmup, 1) - fixed) / slope)))
+        how = "sized for %d+%d steps in %.0f s from calibration steps of %d and %d integrations (%.2f s fixed + %.1f ms per integration)" % (
+            steps, warmup, budget_s, n_a, n_b, fixed, slope * 1e3)
+    d = first(sample_times)
     n_samples = d["weight"].size
     for _ in range(warmup):
-        cpu_step(O, d, gp, gp_iw, cgk, n_threads)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_step(O, d, gp, gp_iw, cgk, n_threads)
-    dt = (time.perf_counter() - t0) / steps
+        run(d)
+    dt = sum(run(d) for _ in range(steps)) / steps
     return dict(value=n_samples / dt, unit="vis/s", cores=n_threads, kind="port",
-                sample="%d of %d integrations of the same workload (%.1f M samples/step), C port of the reference "
+                sample="%d of %d integrations of the same workload (%.1f M samples/step; %s), C port of the reference "
                        "numba loops (oracle/cngi_oracle.c, fp64), %d pthreads over time chunks with private grids + "
                        "tree sum like the reference's dask graph; host has %d logical cores"
-                       % (sample_times, a.n_time, n_samples / 1e6, n_threads, cores)), dt
+                       % (sample_times, a.n_time, n_samples / 1e6, how, n_threads, cores)), dt
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_times = a.cpu_sample_times or 100
-    cb, dt = cpu_arm(a, a.steps, min(a.warmup, 1), sample_times)
+    cb, dt = cpu_arm(a, a.steps, min(a.warmup, 1), a.cpu_sample_times, budget_s=150.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "vis/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -416,7 +439,7 @@ def run_b200(a):
 
     cb = None
     if not a.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only (the N > 1 runs are the scaling series)
-        cb, _ = cpu_arm(a, 1, 1, a.cpu_sample_times or 100)
+        cb, _ = cpu_arm(a, 1, 1, a.cpu_sample_times, budget_s=12.0)   # the whole workload when one step fits in ~6 s
 
     line = {"metric": METRIC, "value": world * n_samples / (ms_step * 1e-3), "unit": "vis/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,

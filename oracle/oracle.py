@@ -209,7 +209,7 @@ def _calculate_briggs_parms(grid_of_imaging_weights, sum_weight, imaging_weights
 
 # --------------------------------------------------------------------------- A4
 def _standard_imaging_weight_degrid_numpy_wrap(grid_imaging_weight, uvw, natural_imaging_weight,
-                                               briggs_factors, freq_chan, grid_parms):
+                                               briggs_factors, freq_chan, grid_parms, n_threads=1):
     """_standard_grid.py:443-518.  grid_imaging_weight is API-side (n_u, n_v, n_chan, n_pol)."""
     nat = _f64(natural_imaging_weight)
     n_time, n_baseline, n_chan, n_pol = nat.shape
@@ -223,10 +223,10 @@ def _standard_imaging_weight_degrid_numpy_wrap(grid_imaging_weight, uvw, natural
     out = np.zeros(nat.shape, dtype=np.double)
     uvw = _f64(uvw)
     freq = _f64(freq_chan)
-    _lib().oracle_imaging_weight_degrid(
+    _lib().oracle_imaging_weight_degrid_mt(
         _p(out), _p(g), _p(bf), _p(uvw), _p(freq), _p(chan_map), _p(pol_map), _p(nat),
         _i64(n_time), _i64(n_baseline), _i64(n_chan), _i64(n_pol), _i64(n_ic), _i64(n_pol),
-        _i64(int(n_uv[0])), _i64(int(n_uv[1])), _p(delta_lm))
+        _i64(int(n_uv[0])), _i64(int(n_uv[1])), _p(delta_lm), ctypes.c_int(n_threads))
     return out
 
 

@@ -102,6 +102,20 @@ def test_mt_driver_matches_single_thread(oracle):
                                                   n_threads=4)
         assert np.max(np.abs(g1 - g4)) <= 1e-13 * np.max(np.abs(g1))
         np.testing.assert_allclose(s1, s4, rtol=1e-13)
+    # A2 -> A3 -> A4 with the threaded drivers (the CPU arm of bench.py): A4's tasks write disjoint rows -> bit-identical
+    gp_iw = synth.grid_parms_for(64, d["cell"], chan_mode="continuum", support=1, oversampling=0, do_psf=True,
+                                 complex_grid=False, do_imaging_weight=True)
+    rho1, sw1 = oracle._standard_grid_psf_numpy_wrap(d["uvw"], d["weight"], d["freq_chan"], np.ones(1), gp_iw)
+    rho3, sw3 = oracle._standard_grid_psf_numpy_wrap(d["uvw"], d["weight"], d["freq_chan"], np.ones(1), gp_iw, n_threads=3)
+    assert np.array_equal(rho1 != 0, rho3 != 0)
+    np.testing.assert_allclose(rho1, rho3, rtol=1e-13)
+    bf = oracle._calculate_briggs_parms(rho1, sw1, {"weighting": "briggs", "robust": 0.5})
+    g_api = np.moveaxis(rho1, (0, 1), (2, 3))
+    iw1 = oracle._standard_imaging_weight_degrid_numpy_wrap(g_api, d["uvw"], d["weight"], bf, d["freq_chan"], gp_iw)
+    for nt in (3, 16):   # 16 > n_time = 6: one task per integration
+        iwn = oracle._standard_imaging_weight_degrid_numpy_wrap(g_api, d["uvw"], d["weight"], bf, d["freq_chan"], gp_iw,
+                                                                n_threads=nt)
+        assert np.array_equal(iw1, iwn, equal_nan=True)
 
 
 # ---- N3 direction_rotate --------------------------------------------------------
