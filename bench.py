@@ -449,7 +449,10 @@ def run_b200(a):
                        "parallelism": ("time-sharded x%d, NCCL all-reduce(density plane 0) + reduce(grid), overlapped across steps" % world) if world > 1 else "single GPU"},
             "vis_tap_per_s": world * n_samples * SUPPORT * SUPPORT / (ms_step * 1e-3),
             "gridding_kernel_vis_per_s": n_samples / (kern_ms * 1e-3),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * a.steps, "roofline": roofline, "atomic_roofline": atomic,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * a.steps,
+            "gpu_launches_note": "per step: iw_grid, iw_sumsq, iw_briggs_finalize, iw_degrid, std_grid_window; the 128-thread "
+                                 "uv_scale table kernel in front of A2 / A4 / A1 and the memsets are not counted",
+            "roofline": roofline, "atomic_roofline": atomic,
             "cpu_baseline": cb}
     emit(line)
     if world > 1:
