@@ -8,11 +8,10 @@ import sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-def _run(env_extra=None):
+def _run(env_extra=None, args=("--steps", "1", "--warmup", "0", "--cpu-sample-times", "2")):
     env = dict(os.environ)
     env.update(env_extra or {})
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--cpu-sample-times", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", *args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env,
                        timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     return [l for l in r.stdout.splitlines() if l.strip()]
@@ -31,3 +30,12 @@ def test_reference_arm_line():
 
 def test_reference_arm_other_ranks_exit_quietly():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_reference_arm_sizes_its_sample_from_calibration_steps():
+    """Without --cpu-sample-times the sample is sized so that steps + warmup fit the time budget, capped at the whole
+    workload (a small one here: every integration is taken) and the line says what it took."""
+    lines = _run(args=("--steps", "2", "--warmup", "1", "--n-time", "48", "--n-chan", "8", "--n-uv", "512"))
+    d = json.loads(lines[0])
+    assert d["steps"] == 2 and d["value"] > 0
+    assert d["cpu_baseline"]["sample"].startswith("48 of 48 integrations") and "calibration steps of 8 and 40" in d["cpu_baseline"]["sample"]
