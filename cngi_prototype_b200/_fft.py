@@ -4,6 +4,7 @@ Mirrors make_image.py:116-130 (ifft2 + _remove_padding + correct_image), make_ps
 _imaging_utils/_normalize.py:39-89 of the reference.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -33,19 +34,27 @@ class FFTPlan:
             pass
 
 
-_plans = {}
+_plans = {}   # insertion-ordered: least recently used first
+_plans_lock = threading.Lock()
 
 
 def _plan_for(n_u, n_v, n_planes, precision, device):
+    """Cached plan of a geometry ON `device` (the plan, its work buffer and phase tables are allocated on the current
+    device, so creation happens inside `torch.cuda.device(device)`); least-recently-used eviction beyond 8 plans."""
     # bound the work buffer: at most ~2 GiB of complex planes per batch
     cb = 8 if precision == _lib.F32 else 16
     max_planes = max(1, min(int(n_planes), (2 << 30) // (int(n_u) * int(n_v) * cb)))
-    key = (int(n_u), int(n_v), max_planes, int(precision), str(device))
-    if key not in _plans:
-        if len(_plans) > 8:
-            _plans.popitem()[1].close()
-        _plans[key] = FFTPlan(n_u, n_v, max_planes, precision)
-    return _plans[key]
+    # a plan owns its work buffer, so two host threads (dask runs the chunk functions from a thread pool) must not share one
+    key = (int(n_u), int(n_v), max_planes, int(precision), str(device), threading.get_ident())
+    with _plans_lock:
+        plan = _plans.pop(key, None)
+        if plan is None:
+            while len(_plans) >= 8:
+                _plans.pop(next(iter(_plans))).close()
+            with torch.cuda.device(device):
+                plan = FFTPlan(n_u, n_v, max_planes, precision)
+        _plans[key] = plan   # (re)insert as the most recently used
+    return plan
 
 
 def grid_to_image(grid, image_size, sum_weight=None, corr_u=None, corr_v=None, norm_image=None, pb_image=None,

@@ -4,6 +4,7 @@ There is NO CPU fallback: if the library is missing or no sm_100 device is prese
 """
 import ctypes as C
 import os
+import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CNGI_B200_LIB") or os.path.join(HERE, "csrc", "libcngi_b200.so")   # env: tuning builds only
@@ -148,6 +149,7 @@ EXPORTS = [
 ]
 
 _lib = None
+_lib_lock = threading.Lock()
 
 
 class CngiError(RuntimeError):
@@ -157,7 +159,11 @@ class CngiError(RuntimeError):
 def lib():
     """Loads libcngi_b200.so.  Raises if it has not been built -- there is no fallback path."""
     global _lib
-    if _lib is None:
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
         if not os.path.exists(LIB_PATH):
             raise CngiError("%s not found: run `python -m cngi_prototype_b200.build` (needs nvcc). "
                             "cngi_prototype_b200 has no CPU fallback." % LIB_PATH)

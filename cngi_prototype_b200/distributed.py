@@ -233,6 +233,24 @@ class ContinuumPipeline:
         return iw
 
 
+def make_imaging_weight(vis_dataset_shard, imaging_weights_parms, grid_parms, time_chunk=0):
+    """imaging.make_imaging_weight on this rank's TIME SHARD of a continuum dataset: the density grid (pol plane 0: all
+    planes are identical) and its sum_weight are all-reduced before the Briggs factors are taken, so every rank degrids
+    its samples from the density of the whole observation (make_imaging_weight.py:144-247 over all dask chunks)."""
+    from . import imaging
+    return imaging.make_imaging_weight(vis_dataset_shard, imaging_weights_parms, grid_parms, time_chunk,
+                                       _density_hook=lambda rho, sw: allreduce_sum(rho, sw))
+
+
+def make_grid(vis_dataset_shard, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT", apply_flags=False, lazy=False, dst=0):
+    """imaging.make_grid on this rank's time shard; the partial uv-grids and sum_weight are summed onto rank `dst`
+    (the rank that runs the FFT) -- the role of the reference's tree sum over chunks (_standard_grid.py:109-120).  Only
+    `dst`'s result is the grid of the whole observation."""
+    from . import imaging
+    return imaging.make_grid(vis_dataset_shard, grid_parms, time_chunk, weight_key, apply_flags, lazy,
+                             _grid_hook=lambda g, sw: reduce_sum(dst, g, sw))
+
+
 def cube_layout(rank, world_size, time_split=1):
     """Ranks form a (channel group) x (time part) grid, time part fastest: returns (chan_group, n_chan_groups,
     time_part, root_rank_of_the_group).  time_split = 1 is pure channel sharding (no exchange at all)."""
@@ -250,7 +268,29 @@ def make_time_groups(world_size, time_split):
     return groups
 
 
-def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image_out=None, with_psf=False):
+class _PhaseTimer:
+    """CUDA events around the phases of cube_imaging (grid / reduce / image), summed per phase by .ms()."""
+
+    def __init__(self):
+        self.marks = []
+
+    def mark(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.marks.append((name, ev))
+
+    def ms(self):
+        """{phase: milliseconds}: the time between a mark and the next one is attributed to the LATER mark's name."""
+        torch.cuda.synchronize()
+        out = {}
+        for (_, e0), (name, e1) in zip(self.marks[:-1], self.marks[1:]):
+            if name != "begin":
+                out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image_out=None, with_psf=False,
+                 presharded=False, timer=None, keep_image=True):
     """Channel-sharded cube imaging with bounded memory (BASELINE config 5; synthesis_imaging_cube.py:105-124,171-220).
 
     Every rank holds (or can slice) the full sample arrays `d` = {vis, uvw, weight, freq_chan[, flag]}.  The image
@@ -270,12 +310,22 @@ def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image
     (synthesis_imaging_cube.py:195-211) -- through ops.grid_image_psf (ONE fused pass over the chunk's samples filling
     both grids) when the ops provide it, else through a second ops.standard_grid_psf pass; the psf grid goes through
     the same reduce and transform.  Returns (image, sum_weight, psf, psf_sum_weight, (chan_lo, chan_hi)) then.
+
+    presharded: `d` already holds ONLY this rank's share -- the channels of its channel group and the integrations of
+    its time part (how a rank that reads its own zarr chunks, or bench.py, holds the data); nothing is sliced then.
+    timer: a _PhaseTimer; CUDA events are recorded after each chunk's gridding ("grid"), reduce ("reduce") and
+    transform ("image").  keep_image=False drops each chunk's image after computing it (benchmarks of cubes whose
+    output would not fit next to the samples); sum_weight is still returned.
     """
+    assert keep_image or not with_psf, "keep_image=False is a benchmark mode of the image-only path"
     rank, ws = world()
     cg, n_cg, tp, root = cube_layout(rank, ws, time_split)
     n_time, n_chan = d["uvw"].shape[0], d["freq_chan"].shape[0]
-    clo, chi = shard_range(n_chan, cg, n_cg)
-    tlo, thi = shard_range(n_time, tp, time_split)
+    if presharded:
+        (clo, chi), (tlo, thi) = (0, n_chan), (0, n_time)
+    else:
+        clo, chi = shard_range(n_chan, cg, n_cg)
+        tlo, thi = shard_range(n_time, tp, time_split)
     n_pol = d["weight"].shape[3]
     n_u, n_v = (int(x) for x in gp["image_size_padded"])
     step = int(chan_chunk) if chan_chunk else max(chi - clo, 1)
@@ -290,6 +340,8 @@ def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image
     for c0 in range(clo, chi, step):
         c1 = min(chi, c0 + step)
         g, s = grid[:c1 - c0], gsw[:c1 - c0]
+        if timer is not None:
+            timer.mark("begin")
         g.zero_()
         s.zero_()
         kw = {}
@@ -308,14 +360,26 @@ def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image
                 ops.standard_grid(d["vis"][tlo:thi, :, c0:c1], *args, grid=g, sum_weight=s, **kw)
                 if with_psf:
                     ops.standard_grid_psf(*args, grid=pg, sum_weight=ps)
+        if timer is not None:
+            timer.mark("grid")
         if group is not None:
             dist.reduce(_as_real(g), root, group=group)
             dist.reduce(s, root, group=group)
             if with_psf:
                 dist.reduce(pg, root, group=group)
                 dist.reduce(ps, root, group=group)
+            if timer is not None:
+                timer.mark("reduce")
         if rank == root:
             img = ops.to_image(g, s, gpc)
+            if timer is not None:
+                timer.mark("image")
+            if not keep_image:
+                if sum_weight is None:
+                    sum_weight = ops.zeros((chi - clo, n_pol), False)
+                sum_weight[c0 - clo:c1 - clo] = s
+                del img
+                continue
             if image is None:
                 image = ops.zeros(tuple(img.shape[:2]) + (chi - clo, n_pol), False).to(img.dtype)
                 sum_weight = ops.zeros((chi - clo, n_pol), False)

@@ -24,6 +24,7 @@ from ._standard_grid import standard_grid
 from ._imaging_weight import (imaging_weight_grid, calculate_briggs_parms,
                               _standard_imaging_weight_degrid_numpy_wrap)
 from ._fft import grid_to_image
+from ._lazy import LazyDeviceArray, ChunkFeeder, streams, is_host
 
 ARCSEC_TO_RAD = np.pi / (3600 * 180)
 
@@ -83,6 +84,8 @@ def _time_chunks(n_time, time_chunk):
 
 def _dev(ds, key, device, dtype=None):
     x = ds[key]
+    if isinstance(x, LazyDeviceArray):
+        x = x.device_tensor()
     t = x if is_torch(x) else torch.as_tensor(np.ascontiguousarray(x))
     return t.to(device=device, dtype=dtype) if dtype is not None else t.to(device=device)
 
@@ -91,9 +94,52 @@ def _out(t, like_torch):
     return t if like_torch else t.cpu().numpy()
 
 
-def make_imaging_weight(vis_dataset, imaging_weights_parms, grid_parms, time_chunk=0):
+class _HostCall:
+    """Context of an API call on HOST arrays: kernels go to the calling thread's compute stream (so that calls made
+    from several threads overlap), results come back through page-locked memory.  For device inputs it is a no-op and
+    everything stays on the caller's current stream."""
+
+    def __init__(self, dev, host):
+        self.dev, self.host = dev, host
+        self._ctx = None
+
+    def __enter__(self):
+        if self.host:
+            self._dctx = torch.cuda.device(self.dev)
+            self._dctx.__enter__()
+            self._ctx = torch.cuda.stream(streams(self.dev).compute)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+            self._dctx.__exit__(*exc)
+        return False
+
+    def lazy(self, base, dims=None, sources=None, extra=None):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        return LazyDeviceArray(base, ev, dims, sources, extra)
+
+    def result(self, base, dims=None):
+        """Device tensor -> what the caller gets: the tensor (device inputs) or a numpy array (host inputs; one flat
+        D2H into page-locked memory, permuted as a view like the reference's moveaxis)."""
+        if not self.host:
+            return base if dims is None else base.permute(*dims)
+        return self.lazy(base, dims).numpy()
+
+
+def make_imaging_weight(vis_dataset, imaging_weights_parms, grid_parms, time_chunk=0, _density_hook=None):
     """Adds IMAGING_WEIGHT to a copy of the dataset (natural: aliases WEIGHT; uniform / briggs: density grid on the
-    UNPADDED image size, Briggs factors, degrid -- make_imaging_weight.py:95-104,144-247)."""
+    UNPADDED image size, Briggs factors, degrid -- make_imaging_weight.py:95-104,144-247).
+
+    Device (torch CUDA) variables: IMAGING_WEIGHT is a device tensor.  Host (numpy) variables: UVW and WEIGHT are fed to
+    the GPU in time chunks (copy of chunk k+1 under the density kernel of chunk k) and IMAGING_WEIGHT comes back as a
+    LazyDeviceArray -- the counterpart of the lazy dask variable the reference returns (:95-104): it reads like a numpy
+    array, and a following make_grid / make_psf / make_image uses the device copy without moving it.
+    _density_hook(density, sum_weight): called on the device accumulators before the Briggs factors are taken -- where
+    distributed.make_imaging_weight sums the density over the ranks that hold the other time shards."""
     _iw = copy.deepcopy(imaging_weights_parms)
     _gp = copy.deepcopy(grid_parms)
     assert _check_imaging_weights_parms(_iw), "######### ERROR: imaging_weights_parms checking failed"
@@ -104,56 +150,112 @@ def make_imaging_weight(vis_dataset, imaging_weights_parms, grid_parms, time_chu
     assert _check_grid_parms(_gp), "######### ERROR: grid_parms checking failed"
     _gp["image_size_padded"] = _gp["image_size"]          # no padding: no FFT follows (:153)
     _gp.update(oversampling=0, support=1, do_psf=True, complex_grid=False, do_imaging_weight=True)
-    like_torch = is_torch(vis_dataset["WEIGHT"])
+    host = is_host(vis_dataset["WEIGHT"])
     dev = device_of(vis_dataset["WEIGHT"], vis_dataset["UVW"])
-    w, uvw, freq = _dev(vis_dataset, "WEIGHT", dev), _dev(vis_dataset, "UVW", dev, torch.float64), \
-        _dev(vis_dataset, "chan", dev, torch.float64)
-    density = sw = None
-    for sl in _time_chunks(w.shape[0], time_chunk):        # the reference's chunk loop + tree sum, on one device grid
-        density, sw = imaging_weight_grid(uvw[sl], w[sl], freq, _gp, grid=density, sum_weight=sw)
-    bf = calculate_briggs_parms(density, sw, _iw)
-    iw = _standard_imaging_weight_degrid_numpy_wrap(density, uvw, w, bf, freq, _gp, kernel_side_layout=True)
-    out["IMAGING_WEIGHT"] = _out(iw, like_torch)
+    with _HostCall(dev, host) as call:
+        freq = _dev(vis_dataset, "chan", dev, torch.float64)
+        feeder = ChunkFeeder({"UVW": vis_dataset["UVW"], "WEIGHT": vis_dataset["WEIGHT"]},
+                             {"UVW": torch.float64, "WEIGHT": None}, dev, time_chunk)
+        n_pol = int(vis_dataset["WEIGHT"].shape[3])
+        density = sw = None
+        for _, blk in feeder:                                # the reference's chunk loop + tree sum, on one device grid
+            density, sw = imaging_weight_grid(blk["UVW"], blk["WEIGHT"], freq, _gp, grid=density, sum_weight=sw,
+                                              first_pol_only=n_pol >= 2)
+        uvw, w = feeder.full("UVW"), feeder.full("WEIGHT")
+        if _density_hook is not None:
+            _density_hook(density[:, :1] if n_pol >= 2 else density, sw[:, :1] if n_pol >= 2 else sw)
+        if n_pol >= 2:   # only pol plane 0 was gridded (all planes are identical, _standard_grid.py:328-330): the other
+            rho = density[:, :1].expand(-1, n_pol, -1, -1)   # planes are stride-0 views of it, no replication pass
+            bf = calculate_briggs_parms(density[:, :1], sw[:, :1], _iw).expand(-1, -1, n_pol)
+        else:
+            rho, bf = density, calculate_briggs_parms(density, sw, _iw)
+        iw = _standard_imaging_weight_degrid_numpy_wrap(rho, uvw, w, bf, freq, _gp, kernel_side_layout=True)
+        if host:
+            out["IMAGING_WEIGHT"] = call.lazy(iw, sources=feeder.sources({"UVW": vis_dataset["UVW"],
+                                                                          "WEIGHT": vis_dataset["WEIGHT"]}))
+        else:
+            out["IMAGING_WEIGHT"] = iw
     return out
 
 
-def _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key):
+def _flagged_weights(w, flag):
+    """apply_flags semantics for the weights (cngi/vis/apply_flags.py:53 NaNs every variable with FLAG's dims)."""
+    return torch.where(flag != 0, torch.full((), float("nan"), dtype=w.dtype, device=w.device), w)
+
+
+def _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key, apply_flags=False):
+    """Returns (grid, sum_weight, checked grid_parms) on the device, on the current stream."""
     _gp = copy.deepcopy(grid_parms)
     assert _check_grid_parms(_gp), "######### ERROR: grid_parms checking failed"
     _gp["oversampling"], _gp["support"] = 100, 7          # make_image.py:106-107
     _gp["complex_grid"], _gp["do_psf"], _gp["do_imaging_weight"] = (not do_psf), do_psf, False
     cgk_1D = _create_prolate_spheroidal_kernel_1D(_gp["oversampling"], _gp["support"])
     wkey = weight_key if weight_key in vis_dataset else "WEIGHT"
-    dev = device_of(vis_dataset[wkey], vis_dataset["UVW"])
+    use_flag = bool(apply_flags) and "FLAG" in vis_dataset
+    wsrc = vis_dataset[wkey]
+    dev = wsrc.base.device if isinstance(wsrc, LazyDeviceArray) else device_of(wsrc, vis_dataset["UVW"])
     if hasattr(vis_dataset, "iter_device_chunks"):
         # zarr-backed dataset (read_vis.VisDataset): time blocks are decoded into pinned buffers, copied on a copy stream
         # and gridded as they arrive -- the reference's per-chunk dask tasks as a three-stage pipeline on one GPU
-        names = [wkey, "UVW"] + ([] if do_psf else ["DATA"] + (["FLAG"] if "FLAG" in vis_dataset else []))
+        names = [wkey, "UVW"] + ([] if do_psf else ["DATA"]) + (["FLAG"] if use_flag else [])
         freq = _dev(vis_dataset, "chan", dev, torch.float64)
         grid = sw = None
         for _, blk in vis_dataset.iter_device_chunks(names, time_chunk, dev):
-            grid, sw = standard_grid(None if do_psf else blk["DATA"], blk["UVW"], blk[wkey], freq, cgk_1D, _gp, do_psf,
-                                     not do_psf, flag=blk.get("FLAG"), grid=grid, sum_weight=sw)
+            w = _flagged_weights(blk[wkey], blk["FLAG"]) if (use_flag and do_psf) else blk[wkey]
+            grid, sw = standard_grid(None if do_psf else blk["DATA"], blk["UVW"], w, freq, cgk_1D, _gp, do_psf,
+                                     not do_psf, flag=blk.get("FLAG") if not do_psf else None, grid=grid, sum_weight=sw)
         return grid, sw, _gp
-    w, uvw, freq = _dev(vis_dataset, wkey, dev), _dev(vis_dataset, "UVW", dev, torch.float64), \
-        _dev(vis_dataset, "chan", dev, torch.float64)
-    vis = None if do_psf else _dev(vis_dataset, "DATA", dev)
-    flag = _dev(vis_dataset, "FLAG", dev, torch.uint8) if (not do_psf and "FLAG" in vis_dataset) else None
+    freq = _dev(vis_dataset, "chan", dev, torch.float64)
+    arrays, dtypes, known = {"UVW": vis_dataset["UVW"], wkey: wsrc}, {"UVW": torch.float64, wkey: None}, {}
+    if isinstance(wsrc, LazyDeviceArray):   # weights made by make_imaging_weight on this dataset: already on the device,
+        known[wkey] = wsrc.device_tensor()  # together with the UVW they were computed from
+        known["UVW"] = wsrc.source("UVW", vis_dataset["UVW"])
+    if not do_psf:
+        arrays["DATA"], dtypes["DATA"] = vis_dataset["DATA"], None
+    if use_flag:
+        arrays["FLAG"], dtypes["FLAG"] = vis_dataset["FLAG"], torch.uint8
+    feeder = ChunkFeeder(arrays, dtypes, dev, time_chunk, known=known)
     grid = sw = None
-    for sl in _time_chunks(w.shape[0], time_chunk):
-        grid, sw = standard_grid(None if do_psf else vis[sl], uvw[sl], w[sl], freq, cgk_1D, _gp, do_psf, not do_psf,
-                                 flag=None if flag is None else flag[sl], grid=grid, sum_weight=sw)
+    for _, blk in feeder:
+        w = _flagged_weights(blk[wkey], blk["FLAG"]) if (use_flag and do_psf) else blk[wkey]
+        grid, sw = standard_grid(None if do_psf else blk["DATA"], blk["UVW"], w, freq, cgk_1D, _gp, do_psf, not do_psf,
+                                 flag=blk["FLAG"] if (use_flag and not do_psf) else None, grid=grid, sum_weight=sw)
     return grid, sw, _gp
 
 
-def make_grid(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT"):
-    """GRID (u, v, chan, pol) complex and SUM_WEIGHT (chan, pol): make_grid.py:112-137 (stops after gridding)."""
+def _host_call_for(vis_dataset, weight_key, data_key):
+    wkey = weight_key if weight_key in vis_dataset else "WEIGHT"
+    probe = vis_dataset[data_key] if data_key in vis_dataset else vis_dataset["UVW"]
+    wsrc = vis_dataset[wkey]
+    dev = wsrc.base.device if isinstance(wsrc, LazyDeviceArray) else device_of(wsrc, vis_dataset["UVW"], probe)
+    host = is_host(probe) and not hasattr(vis_dataset, "iter_device_chunks")
+    return _HostCall(dev, host)
+
+
+def make_grid(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT", apply_flags=False, lazy=False,
+              _grid_hook=None):
+    """GRID (u, v, chan, pol) complex and SUM_WEIGHT (chan, pol): make_grid.py:112-137 (stops after gridding).
+
+    Host (numpy) DATA is fed to the GPU in time chunks, each chunk's copy running under the gridding kernel of the chunk
+    before; the result returns through page-locked memory as numpy arrays (GRID as the permuted view of the kernel-side
+    array, like the reference's moveaxis).  apply_flags: see make_image.
+    lazy=True (host datasets): GRID and SUM_WEIGHT come back as LazyDeviceArrays -- the call returns as soon as the work
+    is queued, and the transfer to the host happens (on its own stream) when the caller first reads the values, the way
+    the reference's lazy result is moved by `.compute()`; a caller that walks many datasets can so read the result of
+    one while the next is being fed.  _grid_hook(grid, sum_weight): see distributed.make_grid."""
     like_torch = is_torch(vis_dataset["DATA"])
-    grid, sw, _ = _grid(vis_dataset, grid_parms, False, time_chunk, weight_key)
+    with _host_call_for(vis_dataset, weight_key, "DATA") as call:
+        grid, sw, _ = _grid(vis_dataset, grid_parms, False, time_chunk, weight_key, apply_flags)
+        if _grid_hook is not None:
+            _grid_hook(grid, sw)
+        if call.host and lazy:
+            return {"GRID": call.lazy(grid, (2, 3, 0, 1)), "SUM_WEIGHT": call.lazy(sw)}
+        if call.host:
+            return {"GRID": call.result(grid, (2, 3, 0, 1)), "SUM_WEIGHT": call.result(sw)}
     return {"GRID": _out(grid.permute(2, 3, 0, 1), like_torch), "SUM_WEIGHT": _out(sw, like_torch)}
 
 
-def _image(vis_dataset, grid_parms, do_psf, time_chunk, weight_key, chan_chunk=0):
+def _image(vis_dataset, grid_parms, do_psf, time_chunk, weight_key, chan_chunk=0, apply_flags=False):
     """grid -> ifft -> crop -> / sum_weight / PS image.  chan_chunk > 0 (cube mode only): the image channels are
     processed `chan_chunk` at a time, so that the padded uv-grids of one chunk, not of the whole cube, are resident
     (the per-channel independence synthesis_imaging_cube.py:105-124 exploits with dask chunks)."""
@@ -162,30 +264,44 @@ def _image(vis_dataset, grid_parms, do_psf, time_chunk, weight_key, chan_chunk=0
         images, sws = [], []
         for c0 in range(0, n_chan, int(chan_chunk)):
             sl = slice(c0, min(n_chan, c0 + int(chan_chunk)))
-            sub = {k: (v[sl] if k == "chan" else (v[:, :, sl] if getattr(v, "ndim", 0) == 4 else v))
+            sub = {k: (v[sl] if k == "chan" else
+                       ((v.device_tensor() if isinstance(v, LazyDeviceArray) else v)[:, :, sl] if getattr(v, "ndim", 0) == 4 else v))
                    for k, v in vis_dataset.items()}
-            img, sw = _image(sub, grid_parms, do_psf, time_chunk, weight_key)
+            img, sw = _image(sub, grid_parms, do_psf, time_chunk, weight_key, apply_flags=apply_flags)
             images.append(img)
             sws.append(sw)
         return torch.cat(images, dim=2), torch.cat(sws, dim=0)
-    grid, sw, gp = _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key)
+    grid, sw, gp = _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key, apply_flags)
     cu, cv = correcting_function_1D(gp["image_size_padded"], gp["image_size"])
     return grid_to_image(grid, gp["image_size"], sum_weight=sw, corr_u=cu, corr_v=cv), sw
 
 
-def make_psf(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT", chan_chunk=0):
+def make_psf(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT", chan_chunk=0, apply_flags=False):
     """PSF (l, m, chan, pol) and PSF_SUM_WEIGHT (chan, pol): real PS gridding of the weights, inverse FFT, crop,
-    / sum_weight / PS correcting image (make_psf.py:105-130).  The Gaussian beam fit (fit_gaussian) is out of scope."""
+    / sum_weight / PS correcting image (make_psf.py:105-130).  The Gaussian beam fit (fit_gaussian) is out of scope.
+    apply_flags: see make_image."""
     like_torch = is_torch(vis_dataset["UVW"])
-    img, sw = _image(vis_dataset, grid_parms, True, time_chunk, weight_key, chan_chunk)
+    with _host_call_for(vis_dataset, weight_key, "UVW") as call:
+        img, sw = _image(vis_dataset, grid_parms, True, time_chunk, weight_key, chan_chunk, apply_flags)
+        if call.host:
+            return {"PSF": call.result(img.contiguous()), "PSF_SUM_WEIGHT": call.result(sw)}
     return {"PSF": _out(img, like_torch), "PSF_SUM_WEIGHT": _out(sw, like_torch)}
 
 
-def make_image(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT", chan_chunk=0):
-    """IMAGE (l, m, chan, pol) and SUM_WEIGHT (chan, pol): complex PS gridding of DATA * weight (FLAG honoured as NaN,
-    cngi/vis/apply_flags.py:53), inverse FFT, crop, / sum_weight / PS correcting image (make_image.py:106-130)."""
+def make_image(vis_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT", chan_chunk=0, apply_flags=False):
+    """IMAGE (l, m, chan, pol) and SUM_WEIGHT (chan, pol): complex PS gridding of DATA * weight, inverse FFT, crop,
+    / sum_weight / PS correcting image (make_image.py:106-130).
+
+    FLAG: like the reference, make_image / make_psf / make_grid do NOT read FLAG -- the user runs cngi.vis.apply_flags
+    first (cngi/vis/apply_flags.py:53), which NaNs DATA and the weights together, and NaN samples are skipped
+    (_standard_grid.py:340).  apply_flags=True fuses that step: FLAG != 0 drops the sample from the image AND from the
+    psf (the weight is treated as NaN there), so IMAGE / SUM_WEIGHT and PSF / PSF_SUM_WEIGHT use the same sample set,
+    exactly as if apply_flags had been run."""
     like_torch = is_torch(vis_dataset["DATA"])
-    img, sw = _image(vis_dataset, grid_parms, False, time_chunk, weight_key, chan_chunk)
+    with _host_call_for(vis_dataset, weight_key, "DATA") as call:
+        img, sw = _image(vis_dataset, grid_parms, False, time_chunk, weight_key, chan_chunk, apply_flags)
+        if call.host:
+            return {"IMAGE": call.result(img.contiguous()), "SUM_WEIGHT": call.result(sw)}
     return {"IMAGE": _out(img, like_torch), "SUM_WEIGHT": _out(sw, like_torch)}
 
 

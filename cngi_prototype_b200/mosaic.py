@@ -41,7 +41,7 @@ def _gcf_host(gcf_dataset, key):
     return x.cpu().numpy() if is_torch(x) else np.asarray(x)
 
 
-def _aperture_graph(vis_dataset, gcf_dataset, grid_parms, mode, time_chunk, weight_key):
+def _aperture_graph(vis_dataset, gcf_dataset, grid_parms, mode, time_chunk, weight_key, apply_flags=False):
     """The role of _graph_aperture_grid (_aperture_grid.py:25-142): mode 'weight' -> A6 with WEIGHT_CONV_KERNEL,
     'psf' / 'image' -> A5 with CONV_KERNEL.  Returns kernel-side grid (n_chan, n_pol, n_u, n_v), sum_weight, parms."""
     _gp = copy.deepcopy(grid_parms)
@@ -55,7 +55,12 @@ def _aperture_graph(vis_dataset, gcf_dataset, grid_parms, mode, time_chunk, weig
     freq = _dev(vis_dataset, "chan", dev, torch.float64)
     field = _dev(vis_dataset, "FIELD_ID", dev, torch.int64).reshape(w.shape[0], w.shape[1])
     vis = _dev(vis_dataset, "DATA", dev) if mode == "image" else None
-    flag = _dev(vis_dataset, "FLAG", dev, torch.uint8) if (mode == "image" and "FLAG" in vis_dataset) else None
+    # like the reference, FLAG is not read unless asked (apply_flags is a separate step there, cngi/vis/apply_flags.py:53);
+    # when fused it drops the sample from every product (image, psf, weight) alike -- see imaging.make_image
+    flag = _dev(vis_dataset, "FLAG", dev, torch.uint8) if (apply_flags and "FLAG" in vis_dataset) else None
+    if flag is not None and mode != "image":
+        w = torch.where(flag != 0, torch.full((), float("nan"), dtype=w.dtype, device=dev), w)
+        flag = None
     entry = "cngi_b200_aperture_weight_grid" if mode == "weight" else "cngi_b200_aperture_grid"
     kernel = gcf_dataset["WEIGHT_CONV_KERNEL" if mode == "weight" else "CONV_KERNEL"]
     maps = [_gcf_host(gcf_dataset, k) for k in ("CF_BASELINE_MAP", "CF_CHAN_MAP", "CF_POL_MAP")]
@@ -68,11 +73,11 @@ def _aperture_graph(vis_dataset, gcf_dataset, grid_parms, mode, time_chunk, weig
     return grid, sw, _gp
 
 
-def make_mosaic_pb(vis_dataset, gcf_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT"):
+def make_mosaic_pb(vis_dataset, gcf_dataset, grid_parms, time_chunk=0, weight_key="IMAGING_WEIGHT", apply_flags=False):
     """WEIGHT_PB = ifft of the gridded weight CFs / sum_weight, PB = sqrt(|WEIGHT_PB|)  (make_mosaic_pb.py:115-129).
     Returns {'PB', 'WEIGHT_PB', 'WEIGHT_PB_SUM_WEIGHT'}; images are (l, m, chan, pol)."""
     like_torch = is_torch(vis_dataset["UVW"])
-    grid, sw, gp = _aperture_graph(vis_dataset, gcf_dataset, grid_parms, "weight", time_chunk, weight_key)
+    grid, sw, gp = _aperture_graph(vis_dataset, gcf_dataset, grid_parms, "weight", time_chunk, weight_key, apply_flags)
     weight_image = grid_to_image(grid, gp["image_size"], sum_weight=sw)
     return {"PB": _out(torch.sqrt(torch.abs(weight_image)), like_torch), "WEIGHT_PB": _out(weight_image, like_torch),
             "WEIGHT_PB_SUM_WEIGHT": _out(sw, like_torch)}
@@ -114,25 +119,26 @@ def _normalized(grid, sw, gp, gcf_dataset, img_dataset, norm_parms, divide_by_ce
 
 
 def make_image_with_gcf(vis_dataset, gcf_dataset, img_dataset, grid_parms, norm_parms, time_chunk=0,
-                        weight_key="IMAGING_WEIGHT"):
+                        weight_key="IMAGING_WEIGHT", apply_flags=False):
     """IMAGE (l, m, chan, pol), SUM_WEIGHT (chan, pol): A5 image mode -> ifft -> crop -> _normalize."""
     like_torch = is_torch(vis_dataset["DATA"])
-    grid, sw, gp = _aperture_graph(vis_dataset, gcf_dataset, grid_parms, "image", time_chunk, weight_key)
+    grid, sw, gp = _aperture_graph(vis_dataset, gcf_dataset, grid_parms, "image", time_chunk, weight_key, apply_flags)
     img = _normalized(grid, sw, gp, gcf_dataset, img_dataset, norm_parms, False)
     return {"IMAGE": _out(img, like_torch), "SUM_WEIGHT": _out(sw, like_torch)}
 
 
 def make_psf_with_gcf(vis_dataset, gcf_dataset, img_dataset, grid_parms, norm_parms, time_chunk=0,
-                      weight_key="IMAGING_WEIGHT"):
+                      weight_key="IMAGING_WEIGHT", apply_flags=False):
     """PSF (l, m, chan, pol) normalised to its centre pixel, PSF_SUM_WEIGHT: A5 psf mode (the Gaussian beam fit,
     make_psf_with_gcf.py:142-150, is image analysis and out of scope)."""
     like_torch = is_torch(vis_dataset["UVW"])
-    grid, sw, gp = _aperture_graph(vis_dataset, gcf_dataset, grid_parms, "psf", time_chunk, weight_key)
+    grid, sw, gp = _aperture_graph(vis_dataset, gcf_dataset, grid_parms, "psf", time_chunk, weight_key, apply_flags)
     img = _normalized(grid, sw, gp, gcf_dataset, img_dataset, norm_parms, True)
     return {"PSF": _out(img, like_torch), "PSF_SUM_WEIGHT": _out(sw, like_torch)}
 
 
-def mosaic_imaging(vis_dataset, field_dataset, rotation_parms, gcf_parms, grid_parms, norm_parms, time_chunk=0):
+def mosaic_imaging(vis_dataset, field_dataset, rotation_parms, gcf_parms, grid_parms, norm_parms, time_chunk=0,
+                   apply_flags=False):
     """BASELINE config 3 end to end on one device: rotate to the mosaic phase centre, build the A-term CFs, the
     mosaic PB, then the image and PSF.  Returns (img_dataset dict, gcf_dataset dict, rotated vis dataset)."""
     from .direction_rotate import direction_rotate
@@ -147,7 +153,7 @@ def mosaic_imaging(vis_dataset, field_dataset, rotation_parms, gcf_parms, grid_p
     g.setdefault("field_id", np.asarray(field_dataset["field_id"]))
     g.setdefault("phase_center", np.asarray(rotation_parms["new_phase_center"], dtype=np.float64))
     gcf = make_gridding_convolution_function(g, gp)
-    img = make_mosaic_pb(vis_rot, gcf, grid_parms, time_chunk)
-    img.update(make_image_with_gcf(vis_rot, gcf, img, grid_parms, norm_parms, time_chunk))
-    img.update(make_psf_with_gcf(vis_rot, gcf, img, grid_parms, norm_parms, time_chunk))
+    img = make_mosaic_pb(vis_rot, gcf, grid_parms, time_chunk, apply_flags=apply_flags)
+    img.update(make_image_with_gcf(vis_rot, gcf, img, grid_parms, norm_parms, time_chunk, apply_flags=apply_flags))
+    img.update(make_psf_with_gcf(vis_rot, gcf, img, grid_parms, norm_parms, time_chunk, apply_flags=apply_flags))
     return img, gcf, vis_rot

@@ -1,8 +1,9 @@
-"""Loads the UNMODIFIED reference numba gridders by file path (this container only).
+"""Loads the UNMODIFIED reference numba gridders by file path.
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so nothing that
-runs there may import this module; it is used by tests/golden/make_golden.py and
-oracle/check_against_reference.py to pin the C restatement, and is skipped otherwise.
+TEST / BENCH INFRASTRUCTURE.  In this container the files are read where they lie under /root/reference
+(tests/golden/make_golden.py pins the C restatement with them).  /root/reference does not exist on the GPU box:
+there the copy staged by oracle/make_ref.sh under the git-ignored oracle/_ref/ is loaded instead -- only by
+bench.py's CPU legs (cpu_baseline kind "reference", `--impl reference`) and by tests that skip when it is absent.
 Recipe from SURVEY.md Appendix A: register modules in sys.modules before exec (numba
 cache=True re-imports by name), writable NUMBA_CACHE_DIR, and the removed ``np.int`` alias.
 """
@@ -12,7 +13,20 @@ import sys
 
 import numpy as np
 
-REF_ROOT = os.environ.get("CNGI_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root():
+    env = os.environ.get("CNGI_REFERENCE_ROOT")
+    if env:
+        return env
+    for root in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(root, "ngcasa", "imaging", "_imaging_utils", "_standard_grid.py")):
+            return root
+    return "/root/reference"
+
+
+REF_ROOT = _pick_root()
 _UTILS = os.path.join(REF_ROOT, "ngcasa", "imaging", "_imaging_utils")
 
 

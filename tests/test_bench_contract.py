@@ -1,9 +1,12 @@
-"""CPU-only: the reference arm of bench.py (`--impl reference`: the oracle port on the host cores) prints one JSON line with
-the contract's keys; under torchrun semantics only rank 0 works."""
+"""CPU-only: the reference arm of bench.py (`--impl reference`: the reference's numba loops staged under oracle/_ref when
+present, else the oracle port, on the host cores) prints one JSON line with the contract's keys; under torchrun
+semantics only rank 0 works."""
 import json
 import os
 import subprocess
 import sys
+
+import pytest
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
@@ -17,13 +20,17 @@ def _run(env_extra=None, args=("--steps", "1", "--warmup", "0", "--cpu-sample-ti
     return [l for l in r.stdout.splitlines() if l.strip()]
 
 
-def test_reference_arm_line():
-    lines = _run()
+@pytest.mark.parametrize("engine", ["port", "auto"])
+def test_reference_arm_line(engine):
+    lines = _run(args=("--steps", "1", "--warmup", "0", "--cpu-sample-times", "2", "--cpu-engine", engine))
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "visibilities gridded/sec" and d["unit"] == "vis/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    staged = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "ngcasa", "imaging", "_imaging_utils", "_standard_grid.py")) \
+        or os.path.isdir("/root/reference")
+    want = "port" if engine == "port" or not staged else "reference"
+    assert d["cpu_baseline"]["kind"] == want and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "vis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 

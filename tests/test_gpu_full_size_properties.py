@@ -1,5 +1,6 @@
-"""BASELINE configs 2 and 4 at FULL size on the GPU, checked through size-independent properties (the oracle would take
-minutes to hours at these sizes; it covers the same code at small sizes in the other test files).
+"""BASELINE configs 2, 3, 4 and 5 at FULL size on the GPU, checked through size-independent properties (linearity, chunk
+invariance, adjointness, plane sums, kernel-variant agreement).  The value-for-value comparison with the CPU oracle at
+the same sizes is tests/test_gpu_full_size_parity.py.
 
   config 2: Briggs(0.5) imaging weights + standard gridding, ALMA-like 903 bl x 500 t x 128 ch x 2 pol = 115.6 M samples,
             4096^2, fp32, continuum -- bench.py's workload.

@@ -38,7 +38,7 @@ def _problem(seed=3, n_time=12, n_chan=4, n_pol=2):
     return vis_ds, field_ds, rotation_parms, gcf_parms
 
 
-def _oracle_chain(O, vis_ds, field_ds, rotation_parms, gcf_parms, grid_parms, norm_parms):
+def _oracle_chain(O, vis_ds, field_ds, rotation_parms, gcf_parms, grid_parms, norm_parms, apply_flags=False):
     gp = dict(grid_parms)
     gp["image_size"] = np.array(gp["image_size"])
     gp["image_size_padded"] = (gp["fft_padding"] * gp["image_size"]).astype(int)
@@ -49,11 +49,14 @@ def _oracle_chain(O, vis_ds, field_ds, rotation_parms, gcf_parms, grid_parms, no
     uvw = O.apply_rotation_matrix(vis_ds["UVW"], vis_ds["FIELD_ID"], R, rid)
     vis = O.apply_phasor(vis_ds["DATA"], uvw, vis_ds["FIELD_ID"], vis_ds["chan"], P, rid, ctr,
                          rotation_parms["single_precision"])
-    vis = np.where(vis_ds["FLAG"], np.nan, vis)             # apply_flags semantics (cngi/vis/apply_flags.py:53)
+    weight = vis_ds["WEIGHT"]
+    if apply_flags:       # cngi/vis/apply_flags.py:53 NaNs every variable with FLAG's dims: DATA and WEIGHT together
+        vis = np.where(vis_ds["FLAG"], np.nan, vis)
+        weight = np.where(vis_ds["FLAG"], np.nan, weight)
     g = O.make_gridding_convolution_function(dict(gcf_parms, freq_chan=vis_ds["chan"], field_phase_dir=field_ds["PHASE_DIR"],
                                                   phase_center=np.array(rotation_parms["new_phase_center"])), gp)
     agp = dict(gp, oversampling=g["oversampling"], field_id=np.asarray(field_ds["field_id"]), do_psf=False)
-    common = (uvw, vis_ds["WEIGHT"], vis_ds["FIELD_ID"], g["CF_BASELINE_MAP"], g["CF_CHAN_MAP"], g["CF_POL_MAP"])
+    common = (uvw, weight, vis_ds["FIELD_ID"], g["CF_BASELINE_MAP"], g["CF_CHAN_MAP"], g["CF_POL_MAP"])
     tail = (g["SUPPORT"], g["PHASE_GRADIENT"], vis_ds["chan"])
     wg, wsw = O._aperture_weight_grid_numpy_wrap(*common, g["WEIGHT_CONV_KERNEL"], *tail, agp)
     sw1 = wsw.copy()
@@ -77,15 +80,17 @@ def _oracle_chain(O, vis_ds, field_ds, rotation_parms, gcf_parms, grid_parms, no
     return out, g
 
 
-@pytest.mark.parametrize("chan_mode,norm_type,single", [("cube", "flat_sky", False), ("continuum", "flat_noise", False),
-                                                         ("cube", "none", True)])
-def test_mosaic_chain(oracle, chan_mode, norm_type, single):
+@pytest.mark.parametrize("chan_mode,norm_type,single,apply_flags", [("cube", "flat_sky", False, True),
+                                                                     ("continuum", "flat_noise", False, False),
+                                                                     ("cube", "none", True, True)])
+def test_mosaic_chain(oracle, chan_mode, norm_type, single, apply_flags):
     from cngi_prototype_b200 import mosaic
     vis_ds, field_ds, rotation_parms, gcf_parms = _problem()
     grid_parms = dict(image_size=[200, 200], cell_size=[0.55, 0.55], fft_padding=1.2, chan_mode=chan_mode)
     norm_parms = dict(norm_type=norm_type, pb_limit=0.2, single_precision=single)
-    img, gcf, _ = mosaic.mosaic_imaging(vis_ds, field_ds, rotation_parms, gcf_parms, grid_parms, norm_parms, time_chunk=5)
-    ref, g = _oracle_chain(oracle, vis_ds, field_ds, rotation_parms, gcf_parms, grid_parms, norm_parms)
+    img, gcf, _ = mosaic.mosaic_imaging(vis_ds, field_ds, rotation_parms, gcf_parms, grid_parms, norm_parms, time_chunk=5,
+                                        apply_flags=apply_flags)
+    ref, g = _oracle_chain(oracle, vis_ds, field_ds, rotation_parms, gcf_parms, grid_parms, norm_parms, apply_flags)
     assert np.array_equal(gcf["SUPPORT"].cpu().numpy(), g["SUPPORT"])
     for k in ("WEIGHT_PB_SUM_WEIGHT", "SUM_WEIGHT", "PSF_SUM_WEIGHT"):
         assert rel_err(img[k], ref[k]) < 1e-11, k

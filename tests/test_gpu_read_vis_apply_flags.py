@@ -113,8 +113,9 @@ def test_make_image_streamed_from_zarr_matches_oracle(oracle, tmp_path, mode):
     mxds = rv.read_vis(store, partition="xds0")
     cell_arcsec = d["cell"] / imaging.ARCSEC_TO_RAD
     gp = {"image_size": [144, 160], "cell_size": [cell_arcsec, cell_arcsec], "fft_padding": 1.25, "chan_mode": mode}
-    img = imaging.make_image(mxds.xds0, gp, weight_key="WEIGHT")
-    psf = imaging.make_psf(mxds.xds0, gp, weight_key="WEIGHT", time_chunk=5)
+    img = imaging.make_image(mxds.xds0, gp, weight_key="WEIGHT", apply_flags=True)
+    psf = imaging.make_psf(mxds.xds0, gp, weight_key="WEIGHT", time_chunk=5, apply_flags=True)
+    psf_noflag = imaging.make_psf(mxds.xds0, gp, weight_key="WEIGHT", time_chunk=5)   # the reference never reads FLAG
     # oracle chain on the flagged samples
     g = dict(gp)
     assert imaging._check_grid_parms(g)
@@ -129,9 +130,15 @@ def test_make_image_streamed_from_zarr_matches_oracle(oracle, tmp_path, mode):
     pgrid, psw = oracle._standard_grid_psf_numpy_wrap(d["uvw"], d["weight"], d["freq_chan"], cgk,
                                                       dict(g, do_psf=True, complex_grid=False, do_imaging_weight=False))
     pref = oracle.correct_image(oracle.grid_to_uncorrected_image(pgrid, g["image_size"]), psw, corr)
-    assert rel_err(psf["PSF"], pref) < 1e-12
+    assert rel_err(psf_noflag["PSF"], pref) < 1e-12 and rel_err(psf_noflag["PSF_SUM_WEIGHT"], psw) < 1e-13
+    # apply_flags=True == cngi.vis.apply_flags first: the weights are NaN where FLAG is set, for the psf too
+    w_f = oracle.apply_flags_variable(d["weight"], flag)
+    pgrid, psw = oracle._standard_grid_psf_numpy_wrap(d["uvw"], w_f, d["freq_chan"], cgk,
+                                                      dict(g, do_psf=True, complex_grid=False, do_imaging_weight=False))
+    pref = oracle.correct_image(oracle.grid_to_uncorrected_image(pgrid, g["image_size"]), psw, corr)
+    assert rel_err(psf["PSF"], pref) < 1e-12 and rel_err(psf["PSF_SUM_WEIGHT"], psw) < 1e-13
     # the grid itself: masks exact
-    gr = imaging.make_grid(mxds.xds0, gp, weight_key="WEIGHT")
+    gr = imaging.make_grid(mxds.xds0, gp, weight_key="WEIGHT", apply_flags=True)
     assert same_support(np.moveaxis(gr["GRID"], (2, 3), (0, 1)), grid)
     # apply_flags first, then the in-memory path without a FLAG variable
     fx = af.apply_flags(mxds, "xds0").attrs["xds0"]

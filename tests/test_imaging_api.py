@@ -150,3 +150,107 @@ def test_continuum_pipeline_side_stream_matches_single_stream():
     assert np.array_equal(np.isnan(a), np.isnan(b))
     m = np.isfinite(b)
     assert np.max(np.abs(a[m] - b[m])) <= 1e-6 * np.max(np.abs(b[m]))
+
+
+@pytest.mark.gpu
+def test_flag_policy_image_and_psf_use_the_same_samples(oracle):
+    """FLAG set on FINITE data, apply_flags not run.  Default (reference behaviour): FLAG is not read by either
+    function.  apply_flags=True: the flagged samples leave the image AND the psf, so SUM_WEIGHT == PSF_SUM_WEIGHT."""
+    from cngi_prototype_b200 import synth, imaging
+    d = synth.make_vis_set(9, 24, 5, 2, 1e9, 1.1e9, 300.0, 120.0, seed=77, flag_frac=0.0, bad_rows=False)
+    flag = np.random.default_rng(3).random(d["vis"].shape) < 0.1
+    cell_arcsec = d["cell"] / imaging.ARCSEC_TO_RAD * 1.25
+    ds = {"DATA": d["vis"], "UVW": d["uvw"], "WEIGHT": d["weight"], "FLAG": flag, "chan": d["freq_chan"]}
+    gp = {"image_size": [120, 120], "cell_size": [cell_arcsec, cell_arcsec], "fft_padding": 1.25, "chan_mode": "cube"}
+    img, psf = imaging.make_image(ds, gp, weight_key="WEIGHT"), imaging.make_psf(ds, gp, weight_key="WEIGHT")
+    assert rel_err(img["SUM_WEIGHT"], psf["PSF_SUM_WEIGHT"]) < 1e-13           # nothing flagged: same sample set
+    imgf = imaging.make_image(ds, gp, weight_key="WEIGHT", apply_flags=True)
+    psff = imaging.make_psf(ds, gp, weight_key="WEIGHT", apply_flags=True, time_chunk=7)
+    assert rel_err(imgf["SUM_WEIGHT"], psff["PSF_SUM_WEIGHT"]) < 1e-13          # flagged: still the same sample set
+    assert np.all(imgf["SUM_WEIGHT"] < img["SUM_WEIGHT"])
+    # == running apply_flags first (DATA and WEIGHT NaN where flagged), through the oracle
+    g = dict(gp)
+    assert imaging._check_grid_parms(g)
+    g.update(oversampling=100, support=7, do_imaging_weight=False)
+    cgk = oracle._create_prolate_spheroidal_kernel_1D(100, 7)
+    _, s_ref = oracle._standard_grid_numpy_wrap(oracle.apply_flags_variable(d["vis"], flag), d["uvw"],
+                                                oracle.apply_flags_variable(d["weight"], flag), d["freq_chan"], cgk,
+                                                dict(g, do_psf=False, complex_grid=True))
+    assert rel_err(imgf["SUM_WEIGHT"], s_ref) < 1e-13
+    gr = imaging.make_grid(ds, gp, weight_key="WEIGHT", apply_flags=True)
+    assert rel_err(gr["SUM_WEIGHT"], s_ref) < 1e-13
+
+
+@pytest.mark.gpu
+def test_host_datasets_lazy_weights_and_pinned_inputs(oracle):
+    """numpy datasets: make_imaging_weight returns IMAGING_WEIGHT as a LazyDeviceArray (the reference returns a lazy dask
+    variable), make_grid consumes the device copy; page-locked and pageable inputs, explicit and default time chunks,
+    and the all-device path give the same numbers."""
+    import torch
+    from cngi_prototype_b200 import synth, imaging
+    from cngi_prototype_b200._lazy import LazyDeviceArray
+    d = synth.config_c1(n_time=40, n_chan=6)
+    cell_arcsec = d["cell"] / imaging.ARCSEC_TO_RAD
+    gp = {"image_size": [160, 160], "cell_size": [cell_arcsec, cell_arcsec], "fft_padding": 1.2, "chan_mode": "continuum"}
+    iwp = {"weighting": "briggs", "robust": 0.5}
+    ds = {"DATA": d["vis"], "UVW": d["uvw"], "WEIGHT": d["weight"], "chan": d["freq_chan"]}
+    pinned = {k: torch.as_tensor(v).pin_memory().numpy() for k, v in ds.items()}
+    dev = {k: torch.as_tensor(v).cuda() for k, v in ds.items()}
+    ref_w = imaging.make_imaging_weight(dev, iwp, gp)
+    ref_g = imaging.make_grid(ref_w, gp)
+    for src, tc in ((ds, 0), (pinned, 0), (pinned, 7)):
+        w = imaging.make_imaging_weight(src, iwp, gp, time_chunk=tc)
+        assert isinstance(w["IMAGING_WEIGHT"], LazyDeviceArray) and w["IMAGING_WEIGHT"].shape == d["weight"].shape
+        g = imaging.make_grid(w, gp, time_chunk=tc)
+        assert isinstance(g["GRID"], np.ndarray) and g["GRID"].shape == (192, 192, 1, 2)
+        assert rel_err(g["GRID"], ref_g["GRID"].cpu().numpy()) < 1e-13
+        assert rel_err(g["SUM_WEIGHT"], ref_g["SUM_WEIGHT"].cpu().numpy()) < 1e-13
+        iw = np.asarray(w["IMAGING_WEIGHT"])                    # materialises once, reads like numpy
+        assert np.array_equal(np.nan_to_num(iw, nan=-1), np.nan_to_num(ref_w["IMAGING_WEIGHT"].cpu().numpy(), nan=-1))
+        assert w["IMAGING_WEIGHT"][3, 2].shape == (6, 2)
+        img = imaging.make_image(w, gp, time_chunk=tc)
+        psf = imaging.make_psf(w, gp, time_chunk=tc)
+        assert isinstance(img["IMAGE"], np.ndarray) and img["IMAGE"].shape == (160, 160, 1, 2)
+        assert abs(psf["PSF"][80, 80, 0, 0] - 1.0) < 1e-3
+    # a weight array the caller made by hand (not lazy) takes the upload path
+    w2 = dict(ds, IMAGING_WEIGHT=iw)
+    g2 = imaging.make_grid(w2, gp)
+    assert rel_err(g2["GRID"], ref_g["GRID"].cpu().numpy()) < 1e-13
+
+
+@pytest.mark.gpu
+def test_chunk_operators_and_api_from_several_threads(oracle):
+    """dask runs the reference's chunk functions from a thread pool (they are nogil, _standard_grid.py:242): the operators
+    and the host-array API must give the same result when called from several threads at once."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from cngi_prototype_b200 import synth, imaging, _standard_grid as sg
+    d = synth.config_c1(n_time=30, n_chan=6)
+    cgk = oracle._create_prolate_spheroidal_kernel_1D(100, 7)
+    gp = synth.grid_parms_for(160, d["cell"], chan_mode="cube")
+    g_ref, s_ref = oracle._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp)
+    chunks = [slice(t, t + 5) for t in range(0, 30, 5)]
+
+    def chunk_task(sl):
+        torch.cuda.set_device(0)
+        return sg._standard_grid_numpy_wrap(d["vis"][sl], d["uvw"][sl], d["weight"][sl], d["freq_chan"], cgk, gp)
+
+    with ThreadPoolExecutor(6) as pool:
+        for _ in range(3):
+            parts = list(pool.map(chunk_task, chunks))
+            g = sum(p[0].astype(np.complex128) for p in parts)
+            s = sum(p[1] for p in parts)
+            assert rel_err(g, g_ref) < 1e-12 and rel_err(s, s_ref) < 1e-12 and np.array_equal(g != 0, g_ref != 0)
+    cell_arcsec = d["cell"] / imaging.ARCSEC_TO_RAD
+    agp = {"image_size": [160, 160], "cell_size": [cell_arcsec, cell_arcsec], "fft_padding": 1.0, "chan_mode": "cube"}
+    ds = {"DATA": d["vis"], "UVW": d["uvw"], "WEIGHT": d["weight"], "chan": d["freq_chan"]}
+
+    def api_task(_):
+        torch.cuda.set_device(0)
+        w = imaging.make_imaging_weight(ds, {"weighting": "briggs", "robust": 0.5}, agp)
+        return imaging.make_grid(w, agp, time_chunk=4)
+
+    one = api_task(0)
+    with ThreadPoolExecutor(4) as pool:
+        for r in pool.map(api_task, range(8)):
+            assert rel_err(r["GRID"], one["GRID"]) < 1e-12 and rel_err(r["SUM_WEIGHT"], one["SUM_WEIGHT"]) < 1e-13
