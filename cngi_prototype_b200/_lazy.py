@@ -74,18 +74,43 @@ class LazyDeviceArray:
     `sources` carries the device copies of the host inputs the result was computed from -- {name: (host object, device
     tensor)} -- so that the next API call on the same dataset does not upload them again."""
 
-    def __init__(self, base, ready=None, dims=None, sources=None, extra=None):
-        self.base, self.ready, self.dims = base, ready, dims
+    def __init__(self, base, ready=None, dims=None, sources=None, deferred=None):
+        """deferred: the array has not been computed yet -- a dict with `make` (callable returning the contiguous device
+        tensor, run on the then-current stream), `shape`, `dtype` (torch), `device`, plus whatever a consumer needs to
+        avoid the computation altogether (make_imaging_weight stores the density / Briggs factors / natural weights there,
+        and make_grid forms the imaging weights inside the gridder instead of materialising them)."""
+        self._base, self.ready, self.dims = base, ready, dims
         self.sources = sources or {}
-        self.extra = extra or {}
+        self.deferred = deferred
         self._host = None
+
+    @property
+    def base(self):
+        if self._base is None:
+            dev = self.deferred["device"]
+            with torch.cuda.device(dev):
+                if self.ready is not None:
+                    torch.cuda.current_stream(dev).wait_event(self.ready)
+                self._base = self.deferred["make"]()
+                self.ready = torch.cuda.Event()
+                self.ready.record(torch.cuda.current_stream(dev))
+        return self._base
+
+    @property
+    def computed(self):
+        return self._base is not None
+
+    @property
+    def device(self):
+        return self._base.device if self._base is not None else self.deferred["device"]
 
     # ---- device side ------------------------------------------------------------------------------------------
     def device_tensor(self):
-        """The device tensor (API-side view), safe to use on the CURRENT stream."""
+        """The device tensor (API-side view), safe to use on the CURRENT stream (computed now if it was deferred)."""
+        base = self.base
         if self.ready is not None:
-            torch.cuda.current_stream(self.base.device).wait_event(self.ready)
-        return self.base if self.dims is None else self.base.permute(*self.dims)
+            torch.cuda.current_stream(base.device).wait_event(self.ready)
+        return base if self.dims is None else base.permute(*self.dims)
 
     def source(self, name, host_obj):
         """Device copy of `host_obj` if this result was computed from that very object, else None."""
@@ -95,8 +120,11 @@ class LazyDeviceArray:
     # ---- host side --------------------------------------------------------------------------------------------
     def numpy(self):
         if self._host is None:
-            dev = self.base.device
+            dev = self.device
             s = streams(dev)
+            if self._base is None:   # deferred: compute on the thread's compute stream first
+                with torch.cuda.device(dev), torch.cuda.stream(s.compute):
+                    self.base
             with torch.cuda.device(dev), torch.cuda.stream(s.d2h):
                 # its own stream: only `ready` is waited for, so the copy overlaps whatever the caller queued since
                 # (e.g. the next dataset's feeding and kernels)
@@ -122,20 +150,21 @@ class LazyDeviceArray:
 
     @property
     def shape(self):
-        s = tuple(self.base.shape)
+        s = tuple(self._base.shape) if self._base is not None else tuple(self.deferred["shape"])
         return s if self.dims is None else tuple(s[d] for d in self.dims)
 
     @property
     def ndim(self):
-        return self.base.dim()
+        return len(self.shape)
 
     @property
     def dtype(self):
-        return np.dtype(str(self.base.dtype).replace("torch.", ""))
+        tdt = self._base.dtype if self._base is not None else self.deferred["dtype"]
+        return np.dtype(str(tdt).replace("torch.", ""))
 
     def __repr__(self):
-        return "LazyDeviceArray(shape=%s, dtype=%s, device=%s, materialised=%s)" % (
-            self.shape, self.dtype, self.base.device, self._host is not None)
+        return "LazyDeviceArray(shape=%s, dtype=%s, device=%s, computed=%s, on_host=%s)" % (
+            self.shape, self.dtype, self.device, self.computed, self._host is not None)
 
 
 def materialise(x):
@@ -178,10 +207,17 @@ class ChunkFeeder:
             step = self.n_time if not self.host else max(1, -(-self.n_time // min_chunks))
         self.slices = [slice(t, min(self.n_time, t + step)) for t in range(0, self.n_time, max(step, 1))]
         self.streams = streams(device) if self.host else None
-        for name, h in self.host.items():   # allocated on the compute stream, written by the copy stream
-            t = torch.empty(h.shape, dtype=h.dtype, device=device)
-            t.record_stream(self.streams.copy)
-            self.dev[name] = t
+        if self.host:
+            # The device buffers belong to the COPY stream (allocated under it, so the caching allocator orders their reuse
+            # against that stream): the feeding of this call can then start while the kernels of the previous call are
+            # still running -- a copy.wait_stream(compute) here would insert a bubble of one kernel tail per call.  They
+            # are used by the kernels of the compute stream, hence record_stream.
+            main = torch.cuda.current_stream(device)
+            with torch.cuda.stream(self.streams.copy):
+                for name, h in self.host.items():
+                    t = torch.empty(h.shape, dtype=h.dtype, device=device)
+                    t.record_stream(main)
+                    self.dev[name] = t
 
     def full(self, name):
         return self.dev[name]
@@ -205,7 +241,6 @@ class ChunkFeeder:
                 yield sl, {n: self.dev[n][sl] for n in self.names}
             return
         main = torch.cuda.current_stream(self.device)
-        self.streams.copy.wait_stream(main)          # the device buffers were allocated on the compute stream
         evs = [self._copy(sl) for sl in self.slices]  # the copy queue runs ahead; each chunk's kernels wait for its event
         for sl, ev in zip(self.slices, evs):
             main.wait_event(ev)

@@ -30,6 +30,13 @@ class StdGridArgs(C.Structure):
     ]
 
 
+class IwFusedArgs(C.Structure):
+    _fields_ = [
+        ("density", vp), ("density_stride", i64 * 4), ("briggs_factors", vp), ("imaging_weight", vp),
+        ("n_u", i64), ("n_v", i64), ("delta_lm", f64 * 2),
+    ]
+
+
 class IwGridArgs(C.Structure):
     _fields_ = [
         ("n_time", i64), ("n_baseline", i64), ("n_chan", i64), ("n_pol", i64),
@@ -145,7 +152,7 @@ EXPORTS = [
     "cngi_b200_grid_to_image", "cngi_b200_standard_grid_host", "cngi_b200_microbench_red",
     "cngi_b200_microbench_smem_atomics", "cngi_b200_direction_rotate", "cngi_b200_make_gcf",
     "cngi_b200_phase_gradient", "cngi_b200_image_to_grid", "cngi_b200_standard_grid_image_psf", "cngi_b200_make_pb",
-    "cngi_b200_apply_flags", "cngi_b200_zarr_read_chunks",
+    "cngi_b200_apply_flags", "cngi_b200_zarr_read_chunks", "cngi_b200_standard_grid_weighted",
 ]
 
 _lib = None
@@ -178,6 +185,7 @@ def lib():
         L.cngi_b200_grid_to_image.argtypes = [vp, C.POINTER(GridToImageArgs), vp]
         L.cngi_b200_standard_grid.argtypes = [C.POINTER(StdGridArgs), vp]
         L.cngi_b200_standard_grid_image_psf.argtypes = [C.POINTER(StdGridArgs), vp, vp, vp]
+        L.cngi_b200_standard_grid_weighted.argtypes = [C.POINTER(StdGridArgs), C.POINTER(IwFusedArgs), vp]
         L.cngi_b200_standard_grid_host.argtypes = [C.POINTER(StdGridArgs), i64]
         L.cngi_b200_imaging_weight_grid.argtypes = [C.POINTER(IwGridArgs), vp]
         L.cngi_b200_imaging_weight_degrid.argtypes = [C.POINTER(IwDegridArgs), vp]

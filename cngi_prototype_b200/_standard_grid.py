@@ -86,11 +86,19 @@ def _fill_common(a, shape4, n_ic, n_uv, grid_parms):
 
 
 def standard_grid(vis_data, uvw, weight, freq_chan, cgk_1D, grid_parms, do_psf, complex_grid, flag=None,
-                  algorithm=ALGO_AUTO, chan_group=0, time_segment=0, grid=None, sum_weight=None, time_chunk=0):
+                  algorithm=ALGO_AUTO, chan_group=0, time_segment=0, grid=None, sum_weight=None, time_chunk=0,
+                  imaging_weight_from=None):
     """Shared body of the two reference wrappers (adds optional fused flags and accumulate-into buffers).
 
     Device path (torch CUDA tensors): `grid`/`sum_weight`, if given, are accumulated into (the device
     resident accumulator the graph level uses); otherwise fresh zeroed tensors are returned.
+
+    imaging_weight_from (device path, image mode, support 7): `weight` holds the NATURAL weights and the imaging weights
+    are formed inside the gridder (cngi_b200_standard_grid_weighted: _standard_imaging_weight_degrid_jit,
+    _standard_grid.py:466-518, folded into phase 1) from a dict with
+        density (n_imag_chan, n_pol, n_u', n_v') float64, kernel-side, any strides (e.g. pol planes expanded with stride 0),
+        briggs_factors (2, n_imag_chan, n_pol), grid_parms (the density grid's: image_size_padded, cell_size),
+        out (optional tensor like `weight` that receives the imaging weights).
     """
     L = _lib.lib()
     on_torch = _is_torch(weight)
@@ -132,11 +140,37 @@ def standard_grid(vis_data, uvw, weight, freq_chan, cgk_1D, grid_parms, do_psf, 
         assert grid.is_contiguous() and grid.dtype == gdt and sum_weight.dtype == torch.float64
         a.vis, a.weight, a.flag, a.uvw = _ptr(v), _ptr(w), _ptr(f), _ptr(uvw_t)
         a.freq_chan, a.cgk_1D, a.grid, a.sum_weight = _ptr(freq_t), _ptr(cgk_t), _ptr(grid), _ptr(sum_weight)
+        if imaging_weight_from is not None:
+            assert not do_psf and complex_grid, "imaging_weight_from: image mode only"
+            src = imaging_weight_from
+            rho = src["density"]
+            n_uv_iw = np.asarray(src["grid_parms"]["image_size_padded"]).astype(np.int64)
+            assert rho.dtype == torch.float64 and tuple(rho.shape) == (n_ic, n_pol, int(n_uv_iw[0]), int(n_uv_iw[1])), \
+                tuple(rho.shape)
+            bf = dev_t(src["briggs_factors"], torch.float64)
+            assert tuple(bf.shape) == (2, n_ic, n_pol), tuple(bf.shape)
+            f = _lib.IwFusedArgs()
+            f.density, f.briggs_factors = _ptr(rho), _ptr(bf)
+            st = rho.stride()
+            for i, v in enumerate((st[2], st[3], st[0], st[1])):
+                f.density_stride[i] = int(v)
+            out = src.get("out")
+            if out is not None:
+                assert out.is_contiguous() and out.dtype == rdt and tuple(out.shape) == shape4
+            f.imaging_weight = _ptr(out)
+            f.n_u, f.n_v = int(n_uv_iw[0]), int(n_uv_iw[1])
+            cell_iw = src["grid_parms"]["cell_size"]
+            f.delta_lm[0], f.delta_lm[1] = float(cell_iw[0]), float(cell_iw[1])
+            with torch.cuda.device(dev):
+                _lib.check(L.cngi_b200_standard_grid_weighted(C.byref(a), C.byref(f), _stream()),
+                           "cngi_b200_standard_grid_weighted")
+            return grid, sum_weight
         with torch.cuda.device(dev):
             _lib.check(L.cngi_b200_standard_grid(C.byref(a), _stream()), "cngi_b200_standard_grid")
         return grid, sum_weight
 
     # host path
+    assert imaging_weight_from is None, "imaging_weight_from needs device-resident inputs"
     w = _np_c(weight, rdt)
     v = None if do_psf else _np_c(vis_data, cdt)
     f = None if (flag is None or do_psf) else _np_c(flag, np.uint8)

@@ -726,3 +726,26 @@ extern "C" int cngi_b200_standard_grid_image_psf(const cngi_std_grid_args *a, vo
     p.psf_grid = psf_grid, p.psf_sum_weight = psf_sum_weight;
     return launch_window_dual(p, a, (cudaStream_t)stream);
 }
+
+// A4 folded into A1 (see include/cngi_b200.h): natural weights in, imaging weights formed in the gridder's phase 1.
+extern "C" int cngi_b200_standard_grid_weighted(const cngi_std_grid_args *a, const cngi_iw_fused_args *w, void *stream)
+{
+    using namespace cngi;
+    int rc = validate(a);
+    if (rc != CNGI_OK) return rc;
+    CNGI_REQUIRE(w != nullptr && w->density && w->briggs_factors, "standard_grid_weighted: null density / briggs_factors");
+    CNGI_REQUIRE(!a->do_psf && a->complex_grid, "standard_grid_weighted: args describe the image pass (do_psf 0, complex grid)");
+    CNGI_REQUIRE(w->n_u > 0 && w->n_v > 0 && w->n_u < (1 << 24) && w->n_v < (1 << 24), "standard_grid_weighted: bad density grid size");
+    StdParams p = make_params(a);
+    if (a->support != 7 || !window_kernel_supported(a, p.table_len)) {
+        set_error("standard_grid_weighted: the fused pass needs support 7 and tap tables that fit shared memory; "
+                  "call cngi_b200_imaging_weight_degrid and cngi_b200_standard_grid instead");
+        return CNGI_ERR_UNSUPPORTED;
+    }
+    p.iw_density = w->density, p.iw_bf = w->briggs_factors, p.iw_out = w->imaging_weight;
+    p.iw_ds_u = w->density_stride[0], p.iw_ds_v = w->density_stride[1];
+    p.iw_ds_c = w->density_stride[2], p.iw_ds_p = w->density_stride[3];
+    p.iw_n_u = (int)w->n_u, p.iw_n_v = (int)w->n_v, p.iw_dl = w->delta_lm[0], p.iw_dm = w->delta_lm[1];
+    p.iw_own_scale = !(p.iw_n_u == p.n_u && p.iw_n_v == p.n_v && p.iw_dl == p.dl && p.iw_dm == p.dm);
+    return launch_window_iw(p, a, (cudaStream_t)stream);
+}

@@ -28,6 +28,14 @@ struct StdParams {
     int c_lo, c_n;         // channel window handled by this launch (bounds the shared-memory channel table)
     long long n_tasks;
     const double *scale;   // naive kernel: [2, n_chan] uv_scale table
+    // fused imaging weights (window kernel, IWF): the weight handed in is the NATURAL weight; the imaging weight of
+    // _standard_imaging_weight_degrid_jit (_standard_grid.py:466-518) is formed per sample in phase 1 from the density grid
+    const double *iw_density;                        // element strides below: (u, v, imaging chan, imaging pol)
+    long long iw_ds_u, iw_ds_v, iw_ds_c, iw_ds_p;
+    const double *iw_bf;                             // Briggs factors [2, n_ic, n_ip], contiguous
+    void *iw_out;                                    // optional: imaging weights written like A4 would (sample layout)
+    int iw_n_u, iw_n_v, iw_own_scale;                // geometry of the density grid (make_imaging_weight does not pad)
+    double iw_dl, iw_dm;
 };
 
 __device__ __forceinline__ int chan_of(const StdParams &p, int c)
@@ -74,5 +82,6 @@ int launch_shift(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
 bool window_kernel_supported(const cngi_std_grid_args *a, int table_len);
 int launch_window(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
 int launch_window_dual(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
+int launch_window_iw(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
 
 }  // namespace cngi

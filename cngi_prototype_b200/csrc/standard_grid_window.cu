@@ -31,7 +31,7 @@
 
 namespace cngi {
 
-template <typename T, bool CPLX, int S, int PP, bool DUAL = false> struct WinCfg {
+template <typename T, bool CPLX, int S, int PP, bool DUAL = false, bool IWF = false> struct WinCfg {
     static constexpr int W = (S < 4) ? 4 : 8;                    // lanes per item == columns == rows of the register window
     static constexpr int SPARE = W - S;                          // hysteresis: cells the stamp can move without a slide
     static constexpr int IPW = 32 / W;                           // items per warp
@@ -53,15 +53,21 @@ template <typename T, bool CPLX, int S, int PP, bool DUAL = false> struct WinCfg
     static constexpr int REC_BYTES = IDX_BYTES + WD_BYTES;
     // two raw-sample buffers per warp (cp.async targets): vis, weight, (u, v)
     static constexpr int RAW_BYTES = 32 * (PP * 3 * (int)sizeof(T)) + ITER * 16;
-    static constexpr int WARP_BYTES = REC_BYTES + 2 * RAW_BYTES;
+    // fused imaging weights: a two-slot (u, v) ring -- the uv of round r + 1 is in flight while round r is staged, so that
+    // the density gather of round r + 1 can be ISSUED one round ahead of its use -- and two buffers of gathered density
+    // values (one double per pol of each of the 32 samples of a round)
+    static constexpr int IW_UV_BYTES = IWF ? ITER * 16 : 0;       // per ring slot
+    static constexpr int IW_RHO_BYTES = IWF ? 32 * PP * 8 : 0;    // per buffer
+    static constexpr int WARP_BYTES = REC_BYTES + 2 * RAW_BYTES + 2 * IW_UV_BYTES + 2 * IW_RHO_BYTES;
     static constexpr int ROW_BYTES = W * (int)sizeof(T);
 };
 
 struct WinSmem {
-    int tap, tapsum, scale, wbuf, total;
+    int tap, tapsum, scale, scale_iw, wbuf, total;
 };
 
-template <typename Cfg, typename T> __host__ __device__ inline WinSmem win_smem_layout(int oversampling, int c_n, int warps)
+template <typename Cfg, typename T>
+__host__ __device__ inline WinSmem win_smem_layout(int oversampling, int c_n, int warps, bool iw_own_scale = false)
 {
     WinSmem L;
     const int n_off = oversampling + 3;
@@ -69,7 +75,8 @@ template <typename Cfg, typename T> __host__ __device__ inline WinSmem win_smem_
     L.tap = 0;
     L.tapsum = L.tap + up16(Cfg::W * n_off * Cfg::ROW_BYTES);
     L.scale = L.tapsum + up16(n_off * (int)sizeof(double));
-    L.wbuf = L.scale + up16(2 * c_n * (int)sizeof(double));
+    L.scale_iw = L.scale + up16(2 * c_n * (int)sizeof(double));
+    L.wbuf = L.scale_iw + (iw_own_scale ? up16(2 * c_n * (int)sizeof(double)) : 0);
     L.total = L.wbuf + warps * Cfg::WARP_BYTES;
     return L;
 }
@@ -79,6 +86,13 @@ template <typename Cfg, typename T> __host__ __device__ inline WinSmem win_smem_
 #endif
 #ifndef CNGI_WIN_MINB_F64
 #define CNGI_WIN_MINB_F64 3
+#endif
+
+#ifndef CNGI_WIN_IW_MINB_F32
+#define CNGI_WIN_IW_MINB_F32 4
+#endif
+#ifndef CNGI_WIN_IW_MINB_F64
+#define CNGI_WIN_IW_MINB_F64 3
 #endif
 
 #ifndef CNGI_WIN_DUAL_MINB_F32
@@ -126,12 +140,21 @@ __device__ __forceinline__ void cp_async_bytes(unsigned dst, const void *src, st
 // DUAL: one pass grids the image (complex, vis * weight) AND the psf (real, weight) of the same samples -- they share
 // every cell index and tap (synthesis_imaging_cube.py:195-211 calls _make_psf and _make_image back to back on the
 // same uvw and weights); the psf accumulators ride along as extra (pol 2m, pol 2m+1) pairs of every window cell.
-template <typename T, bool CPLX, int S, int PP, int BLK, bool NZ, bool DUAL = false>
-__global__ void __launch_bounds__(BLK, DUAL ? (sizeof(T) == 4 ? CNGI_WIN_DUAL_MINB_F32 : CNGI_WIN_DUAL_MINB_F64) : (sizeof(T) == 4 ? CNGI_WIN_MINB_F32 : CNGI_WIN_MINB_F64))
+//
+// IWF: the weight array holds NATURAL weights and the imaging weight is formed in phase 1 (the weight-degrid pass A4,
+// _standard_grid.py:466-518, folded into the gridder): w_img = avg(w) / (f0 * rho[cell] + f1).  The density value is a
+// dependent gather (uv -> cell -> rho) that would sit on phase 1's critical path, so it is software-pipelined: the (u, v)
+// of round r + 1 is copied (cp.async) while round r is staged, the gather of round r + 1 is issued (cp.async again)
+// right after, and lands while the 32 samples of round r are consumed by phase 2.  The imaging weights are never
+// written unless the caller asks for them (p.iw_out).
+template <typename T, bool CPLX, int S, int PP, int BLK, bool NZ, bool DUAL = false, bool IWF = false>
+__global__ void __launch_bounds__(BLK, DUAL ? (sizeof(T) == 4 ? CNGI_WIN_DUAL_MINB_F32 : CNGI_WIN_DUAL_MINB_F64)
+                                        : IWF ? (sizeof(T) == 4 ? CNGI_WIN_IW_MINB_F32 : CNGI_WIN_IW_MINB_F64)
+                                              : (sizeof(T) == 4 ? CNGI_WIN_MINB_F32 : CNGI_WIN_MINB_F64))
 std_grid_window_kernel(StdParams p)
 {
     static_assert(!DUAL || CPLX, "the fused image + psf pass grids a complex image");
-    using Cfg = WinCfg<T, CPLX, S, PP, DUAL>;
+    using Cfg = WinCfg<T, CPLX, S, PP, DUAL, IWF>;
     constexpr int NVC = Cfg::NVC;
     using CT = typename Cplx<T>::type;
     using P2 = typename Pair<T>::type;
@@ -145,7 +168,7 @@ std_grid_window_kernel(StdParams p)
     const unsigned FULL = 0xffffffffu;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    const WinSmem L = win_smem_layout<Cfg, T>(p.oversampling, p.c_n, BLK / 32);
+    const WinSmem L = win_smem_layout<Cfg, T>(p.oversampling, p.c_n, BLK / 32, IWF && p.iw_own_scale);
     T *tap = reinterpret_cast<T *>(smem + L.tap);
     double *tapsum = reinterpret_cast<double *>(smem + L.tapsum);
     double *scale = reinterpret_cast<double *>(smem + L.scale);
@@ -173,6 +196,18 @@ std_grid_window_kernel(StdParams p)
         scale[i] = uv_scale_of(f, p.dl, p.n_u);
         scale[p.c_n + i] = uv_scale_of(f, p.dm, p.n_v);
     }
+    const double *scale_iw = scale;   // uv scale of the density grid: the gridder's own unless the geometries differ
+    if constexpr (IWF) {
+        if (p.iw_own_scale) {
+            double *tbl = reinterpret_cast<double *>(smem + L.scale_iw);
+            for (int i = threadIdx.x; i < p.c_n; i += BLK) {
+                const double f = p.freq[p.c_lo + i];
+                tbl[i] = uv_scale_of(f, p.iw_dl, p.iw_n_u);
+                tbl[p.c_n + i] = uv_scale_of(f, p.iw_dm, p.iw_n_v);
+            }
+            scale_iw = tbl;
+        }
+    }
     __syncthreads();   // the only block-wide barrier
 
     const int lane = threadIdx.x & 31;
@@ -182,6 +217,8 @@ std_grid_window_kernel(StdParams p)
     const unsigned idx_s = wbuf_s;
     const unsigned wd_s = wbuf_s + Cfg::IDX_BYTES;
     const unsigned raw_s = wbuf_s + Cfg::REC_BYTES;
+    const unsigned uvr_s = raw_s + 2 * Cfg::RAW_BYTES;            // IWF: (u, v) ring, two slots
+    const unsigned rho_s = uvr_s + 2 * Cfg::IW_UV_BYTES;          // IWF: gathered density, two buffers
     const unsigned tap_s = (unsigned)__cvta_generic_to_shared(tap);
     const int rot_stride = n_off * ROW_BYTES;   // bytes between two rotations of the tap table
     const int G = p.G;
@@ -279,6 +316,17 @@ std_grid_window_kernel(StdParams p)
         int apol[PP];
 #pragma unroll
         for (int ip = 0; ip < PP; ++ip) apol[ip] = (ip < npol) ? pol_of(p, p0 + ip) : 0;
+        double bf0[PP], bf1[PP];   // IWF: Briggs factors of this lane's (imaging channel, pol) planes
+        bool iw_ok = false;        // IWF: the sample's cell of the density grid exists (set when its gather is issued)
+#pragma unroll
+        for (int ip = 0; ip < PP; ++ip) {
+            bf0[ip] = bf1[ip] = 0.0;
+            if constexpr (IWF) {
+                const int q = a_chan1 * p.n_ip + apol[ip];
+                bf0[ip] = p.iw_bf[q];
+                bf1[ip] = p.iw_bf[p.n_ic * p.n_ip + q];
+            }
+        }
         const int c_item = c_base + k2 * G;   // every channel of an item maps to one image plane (G > 1 only in continuum)
         const int plane2 = (c_item < c_end) ? chan_of(p, c_item) : 0;
         // plane (plane2, apol[ip]) of the grid as T elements; a missing pol (odd pol count) aliases the first one: its
@@ -408,11 +456,37 @@ std_grid_window_kernel(StdParams p)
         const long long uvw_step = (long long)spr * p.n_baseline * 3;
         const bool vec2 = (PP == 2) && npol == 2 && (p.n_pol & 1) == 0;
         unsigned raw_flag = 0;   // flag bytes of the prefetched sample (2-byte loads cannot go through cp.async)
+        auto load_uv = [&](int t0, int slot, const double *src) {   // IWF: (u, v) of the round starting at t0 into a ring slot
+            if (uv_lane && chan_ok && (t0 + row1 < t_hi)) {
+                cp_async_bytes(uvr_s + slot * Cfg::IW_UV_BYTES + row1 * 16, src, std::integral_constant<int, 8>{});
+                cp_async_bytes(uvr_s + slot * Cfg::IW_UV_BYTES + row1 * 16 + 8, src + 1, std::integral_constant<int, 8>{});
+            }
+        };
         auto load_raw = [&](int t0, int buf) {
             raw_flag = 0;
+            if constexpr (IWF) {
+                // (u, v) of the round after this one; then the density values of THIS round's samples, whose (u, v) landed
+                // before the previous wait (ring slot `buf`): cell of the density grid -> one 8-byte gather per pol
+                load_uv(t0 + spr, buf ^ 1, uvw_next + uvw_step);
+                iw_ok = false;
+                if (chan_ok && (t0 + row1 < t_hi)) {
+                    const double2 uv = lds_f64x2(uvr_s + buf * Cfg::IW_UV_BYTES + row1 * 16);
+                    CellPos cq;
+                    if (locate_centre(uv.x, uv.y, scale_iw[sc1], scale_iw[p.c_n + sc1], p.iw_n_u, p.iw_n_v, cq) &&
+                        stamp_inside(cq.uc, cq.vc, 0, p.iw_n_u, p.iw_n_v)) {
+                        iw_ok = true;
+                        const double *src = p.iw_density + cq.uc * p.iw_ds_u + cq.vc * p.iw_ds_v + a_chan1 * p.iw_ds_c;
+#pragma unroll
+                        for (int ip = 0; ip < PP; ++ip)
+                            if (ip < npol)
+                                cp_async_bytes(rho_s + buf * Cfg::IW_RHO_BYTES + (lane * PP + ip) * 8, src + apol[ip] * p.iw_ds_p,
+                                               std::integral_constant<int, 8>{});
+                    }
+                }
+            }
             if (chan_ok && (t0 + row1 < t_hi)) {
                 const unsigned base = raw_s + buf * RAW_BUF;
-                if (uv_lane) {   // one (u, v) per time step of the round: one lane copies it, the row's lanes all read it
+                if (!IWF && uv_lane) {   // one (u, v) per time step of the round: one lane copies it, the row's lanes all read it
                     cp_async_bytes(base + VIS_RAW + W_RAW + row1 * 16, uvw_next, std::integral_constant<int, 8>{});
                     cp_async_bytes(base + VIS_RAW + W_RAW + row1 * 16 + 8, uvw_next + 1, std::integral_constant<int, 8>{});
                 }
@@ -458,20 +532,53 @@ std_grid_window_kernel(StdParams p)
             CellPos cp;
             bool ok = chan_ok && (t0 + row1 < t_hi);
             const unsigned base = raw_s + buf * RAW_BUF;
+            const T *wsrc = reinterpret_cast<const T *>(smem + (base - (unsigned)__cvta_generic_to_shared(smem)) + VIS_RAW) + lane * PP;
+            T raw_w[PP];
+#pragma unroll
+            for (int ip = 0; ip < PP; ++ip) raw_w[ip] = (T)0;
             if (ok) {
-                const double2 uv = lds_f64x2(base + VIS_RAW + W_RAW + row1 * 16);
+                const double2 uv = lds_f64x2(IWF ? uvr_s + buf * Cfg::IW_UV_BYTES + row1 * 16 : base + VIS_RAW + W_RAW + row1 * 16);
+                if constexpr (IWF) {
+                    // imaging weights of the sample, operation for operation what iw_degrid_kernel (A4) computes:
+                    // off the density grid or NaN uv -> 0; else avg of the two pols (n_pol == 2) or the natural weight,
+                    // divided by f0 * rho + f1 where the natural weight and rho are both finite and non-zero
+                    const double avg = (p.n_pol == 2) ? __dmul_rn(__dadd_rn((double)wsrc[0], (double)wsrc[PP - 1]), 0.5) : 0.0;
+#pragma unroll
+                    for (int ip = 0; ip < PP; ++ip) {
+                        if (ip < npol) {
+                            double iw = 0.0;
+                            if (iw_ok) {
+                                const double w = (double)wsrc[ip];
+                                iw = (p.n_pol == 2) ? avg : w;
+                                if (!isnan(w) && w != 0.0) {
+                                    double r;
+                                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(rho_s + buf * Cfg::IW_RHO_BYTES + (lane * PP + ip) * 8));
+                                    if (!isnan(r) && r != 0.0) {
+                                        const double den = __dadd_rn(__dmul_rn(bf0[ip], r), bf1[ip]);
+                                        iw = sizeof(T) == 4 ? (double)__fdiv_rn((float)iw, (float)den) : __ddiv_rn(iw, den);
+                                    }
+                                }
+                            }
+                            raw_w[ip] = (T)iw;
+                        }
+                    }
+                    if (p.iw_out) {   // the caller wants IMAGING_WEIGHT too (s_next already points at the next round)
+                        T *dst = (T *)p.iw_out + (s_next - s_step);
+#pragma unroll
+                        for (int ip = 0; ip < PP; ++ip)
+                            if (ip < npol) dst[ip] = raw_w[ip];
+                    }
+                }
                 ok = locate_centre(uv.x, uv.y, scale[sc1], scale[p.c_n + sc1], p.n_u, p.n_v, cp);
             }
             if (ok) ok = stamp_inside(cp.uc, cp.vc, HALF, p.n_u, p.n_v);
             if (ok) {
-                T raw_w[PP];
                 CT raw_vis[PP];
                 {
-                    const T *wsrc = reinterpret_cast<const T *>(smem + (base - (unsigned)__cvta_generic_to_shared(smem)) + VIS_RAW) + lane * PP;
                     const CT *vsrc = reinterpret_cast<const CT *>(smem + (base - (unsigned)__cvta_generic_to_shared(smem))) + lane * PP;
 #pragma unroll
                     for (int ip = 0; ip < PP; ++ip) {
-                        raw_w[ip] = wsrc[ip];
+                        if (!IWF) raw_w[ip] = wsrc[ip];
                         if (!p.do_psf) raw_vis[ip] = vsrc[ip];
                     }
                 }
@@ -609,6 +716,12 @@ std_grid_window_kernel(StdParams p)
 
         // ---- main loop over rounds ---------------------------------------------------------------------
         int buf = 0;
+        if constexpr (IWF) {   // the first round's (u, v) must have landed before its density gather can be issued
+            load_uv(t_lo, 0, uvw_next);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+        }
         load_raw(t_lo, 0);
         for (int t0 = t_lo; t0 < t_hi; t0 += spr) {
             stage(t0, buf);
@@ -646,14 +759,14 @@ static int env_knob(const char *name, int dflt)   // development knobs (tools/pr
     return e ? atoi(e) : dflt;
 }
 
-template <typename T, bool CPLX, int S, int PP, bool NZ, bool DUAL = false>
+template <typename T, bool CPLX, int S, int PP, bool NZ, bool DUAL = false, bool IWF = false>
 static int launch_window_t(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
 {
-    using Cfg = WinCfg<T, CPLX, S, PP, DUAL>;
+    using Cfg = WinCfg<T, CPLX, S, PP, DUAL, IWF>;
     constexpr int BLK = 128;
     if (p.n_time == 0 || p.n_baseline == 0 || p.n_chan == 0 || p.n_pol == 0) return CNGI_OK;
     constexpr int kMaxChanWindow = 2048;   // 32 KB of uv-scale table per block at most
-    auto kern = std_grid_window_kernel<T, CPLX, S, PP, BLK, NZ, DUAL>;
+    auto kern = std_grid_window_kernel<T, CPLX, S, PP, BLK, NZ, DUAL, IWF>;
     static const int persist = env_knob("CNGI_WIN_PERSIST", 0);
     for (int c_lo = 0; c_lo < p.n_chan; c_lo += kMaxChanWindow) {
         p.c_lo = c_lo;
@@ -672,7 +785,7 @@ static int launch_window_t(StdParams p, const cngi_std_grid_args *a, cudaStream_
         p.n_cspan = (int)ceil_div(p.c_n, Cfg::IPW * G);
         p.n_pgrp = (int)ceil_div(p.n_pol, PP);
         const long long per_seg = (long long)p.n_baseline * p.n_cspan * p.n_pgrp;
-        const size_t smem = (size_t)win_smem_layout<Cfg, T>(p.oversampling, p.c_n, BLK / 32).total;
+        const size_t smem = (size_t)win_smem_layout<Cfg, T>(p.oversampling, p.c_n, BLK / 32, IWF && p.iw_own_scale).total;
         CNGI_REQUIRE(smem <= 227 * 1024, "standard_grid: tap tables too large for shared memory (%zu bytes)", smem);
         CNGI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
@@ -751,6 +864,20 @@ int launch_window_dual(StdParams p, const cngi_std_grid_args *a, cudaStream_t st
                             : launch_window_t<float, true, 7, 2, false, true>(p, a, st);
     return p.n_pol == 1 ? launch_window_t<double, true, 7, 1, false, true>(p, a, st)
                         : launch_window_t<double, true, 7, 2, false, true>(p, a, st);
+#endif
+}
+
+// imaging weights formed inside the gridder (support 7, complex image grid: what make_image runs after make_imaging_weight)
+int launch_window_iw(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
+{
+#ifdef CNGI_WIN_MINIMAL
+    return CNGI_ERR_UNSUPPORTED;
+#else
+    if (a->precision == CNGI_F32)
+        return p.n_pol == 1 ? launch_window_t<float, true, 7, 1, false, false, true>(p, a, st)
+                            : launch_window_t<float, true, 7, 2, false, false, true>(p, a, st);
+    return p.n_pol == 1 ? launch_window_t<double, true, 7, 1, false, false, true>(p, a, st)
+                        : launch_window_t<double, true, 7, 2, false, false, true>(p, a, st);
 #endif
 }
 

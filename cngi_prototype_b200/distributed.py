@@ -116,7 +116,7 @@ class ContinuumPipeline:
         pipe.flush()            # results of the last step: pipe.last (grid, gsw valid on rank 0)
     """
 
-    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs, side_stream=None):
+    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs, side_stream=None, fuse_weights=True):
         """side_stream (a high-priority CUDA stream, device tensors only): the whole imaging-weight chain of step k+1
         (density grid, all-reduce, Briggs factors, weight degrid -- memory-latency bound kernels) is issued there and
         runs CONCURRENTLY with the gridding kernel of step k on the current stream (issue bound): whenever a gridder
@@ -124,6 +124,9 @@ class ContinuumPipeline:
         other's stalls."""
         self.ops, self.gp, self.gp_iw, self.iw_parms, self.cgk = ops, gp, gp_iw, iw_parms, cgk
         self.side = side_stream
+        # fuse_weights: the weight degrid (A4) runs inside the gridder (ops.standard_grid_weighted) when the ops have it and
+        # the support is 7 -- the imaging weights are then never written or re-read
+        self.fuse_weights = bool(fuse_weights) and side_stream is None and int(gp.get("support", 7)) == 7
         self.bufs = [make_bufs(), make_bufs()]
         self.pend_density = [[], []]
         self.pend_grid = [[], []]
@@ -161,16 +164,32 @@ class ContinuumPipeline:
             bf, rho = self.ops.briggs(b.density, b.dsw, self.iw_parms), b.density
         return self.ops.degrid(rho, d["uvw"], d["weight"], bf, d["freq_chan"], self.gp_iw)
 
+    def _weight_source(self, b):
+        """The fused form of _weights: Briggs factors + what the gridder needs to form the imaging weights itself."""
+        n_pol = b.density.shape[1]
+        if n_pol >= 2:
+            rho0, sw0 = b.density[:, :1], b.dsw[:, :1]
+            bf = self.ops.briggs(rho0, sw0, self.iw_parms).expand(-1, -1, n_pol)
+            rho = rho0.expand(-1, n_pol, -1, -1)
+        else:
+            bf, rho = self.ops.briggs(b.density, b.dsw, self.iw_parms), b.density
+        return dict(density=rho, briggs_factors=bf, grid_parms=self.gp_iw)
+
     def _stage_b(self, d, slot, grid_hook):
         b = self.bufs[slot]
         self._wait(self.pend_density[slot])
-        iw = self._weights(d, b)
+        fused = self.fuse_weights and hasattr(self.ops, "standard_grid_weighted")
+        iw = self._weight_source(b) if fused else self._weights(d, b)
         self._wait(self.pend_grid[slot])   # the reduce that last read this grid buffer
         b.grid.zero_()
         b.gsw.zero_()
         if grid_hook is not None:
             grid_hook("begin")
-        self.ops.standard_grid(d["vis"], d["uvw"], iw, d["freq_chan"], self.cgk, self.gp, grid=b.grid, sum_weight=b.gsw)
+        if fused:   # imaging weights are formed inside the gridder from the natural weights + density (never materialised)
+            self.ops.standard_grid_weighted(d["vis"], d["uvw"], d["weight"], d["freq_chan"], self.cgk, self.gp, iw,
+                                            grid=b.grid, sum_weight=b.gsw)
+        else:
+            self.ops.standard_grid(d["vis"], d["uvw"], iw, d["freq_chan"], self.cgk, self.gp, grid=b.grid, sum_weight=b.gsw)
         if grid_hook is not None:
             grid_hook("end")
         if world()[1] > 1:   # partial uv-grids -> the rank that runs the FFT
@@ -411,6 +430,10 @@ def cuda_ops():
     def grid(vis, uvw, w, freq, cgk, gp, grid=None, sum_weight=None, flag=None):
         return standard_grid(vis, uvw, w, freq, cgk, gp, False, True, grid=grid, sum_weight=sum_weight, flag=flag)
 
+    def grid_weighted(vis, uvw, w_nat, freq, cgk, gp, source, grid=None, sum_weight=None, flag=None):
+        return standard_grid(vis, uvw, w_nat, freq, cgk, gp, False, True, grid=grid, sum_weight=sum_weight, flag=flag,
+                             imaging_weight_from=source)
+
     def grid_image_psf(vis, uvw, w, freq, cgk, gp, grid=None, sum_weight=None, psf_grid=None, psf_sum_weight=None, flag=None):
         from ._standard_grid import standard_grid_image_psf
         return standard_grid_image_psf(vis, uvw, w, freq, cgk, gp, flag=flag, grid=grid, sum_weight=sum_weight,
@@ -431,5 +454,5 @@ def cuda_ops():
         return grid_to_image(g, gp["image_size"], sum_weight=s, corr_u=cu, corr_v=cv)
 
     return SimpleNamespace(imaging_weight_grid=imaging_weight_grid, briggs=calculate_briggs_parms, degrid=degrid,
-                           standard_grid=grid, standard_grid_psf=grid_psf, grid_image_psf=grid_image_psf, zeros=zeros,
+                           standard_grid=grid, standard_grid_weighted=grid_weighted, standard_grid_psf=grid_psf, grid_image_psf=grid_image_psf, zeros=zeros,
                            to_image=to_image)

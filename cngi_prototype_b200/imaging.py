@@ -117,10 +117,10 @@ class _HostCall:
             self._dctx.__exit__(*exc)
         return False
 
-    def lazy(self, base, dims=None, sources=None, extra=None):
+    def lazy(self, base, dims=None, sources=None, deferred=None):
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
-        return LazyDeviceArray(base, ev, dims, sources, extra)
+        return LazyDeviceArray(base, ev, dims, sources, deferred)
 
     def result(self, base, dims=None):
         """Device tensor -> what the caller gets: the tensor (device inputs) or a numpy array (host inputs; one flat
@@ -169,12 +169,19 @@ def make_imaging_weight(vis_dataset, imaging_weights_parms, grid_parms, time_chu
             bf = calculate_briggs_parms(density[:, :1], sw[:, :1], _iw).expand(-1, -1, n_pol)
         else:
             rho, bf = density, calculate_briggs_parms(density, sw, _iw)
-        iw = _standard_imaging_weight_degrid_numpy_wrap(rho, uvw, w, bf, freq, _gp, kernel_side_layout=True)
+        def degrid():
+            return _standard_imaging_weight_degrid_numpy_wrap(rho, uvw, w, bf, freq, _gp, kernel_side_layout=True)
+
         if host:
-            out["IMAGING_WEIGHT"] = call.lazy(iw, sources=feeder.sources({"UVW": vis_dataset["UVW"],
-                                                                          "WEIGHT": vis_dataset["WEIGHT"]}))
+            # Deferred: the weight degrid runs only if somebody reads IMAGING_WEIGHT (or make_psf needs it); make_grid /
+            # make_image form the weights inside the gridder from what is stored here (cngi_b200_standard_grid_weighted)
+            out["IMAGING_WEIGHT"] = call.lazy(None, sources=feeder.sources({"UVW": vis_dataset["UVW"],
+                                                                            "WEIGHT": vis_dataset["WEIGHT"]}),
+                                              deferred=dict(make=degrid, shape=tuple(w.shape), dtype=w.dtype, device=dev,
+                                                            natural=w, density=rho, briggs_factors=bf.contiguous(),
+                                                            grid_parms=_gp))
         else:
-            out["IMAGING_WEIGHT"] = iw
+            out["IMAGING_WEIGHT"] = degrid()
     return out
 
 
@@ -193,7 +200,7 @@ def _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key, apply_flags=F
     wkey = weight_key if weight_key in vis_dataset else "WEIGHT"
     use_flag = bool(apply_flags) and "FLAG" in vis_dataset
     wsrc = vis_dataset[wkey]
-    dev = wsrc.base.device if isinstance(wsrc, LazyDeviceArray) else device_of(wsrc, vis_dataset["UVW"])
+    dev = wsrc.device if isinstance(wsrc, LazyDeviceArray) else device_of(wsrc, vis_dataset["UVW"])
     if hasattr(vis_dataset, "iter_device_chunks"):
         # zarr-backed dataset (read_vis.VisDataset): time blocks are decoded into pinned buffers, copied on a copy stream
         # and gridded as they arrive -- the reference's per-chunk dask tasks as a three-stage pipeline on one GPU
@@ -207,8 +214,15 @@ def _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key, apply_flags=F
         return grid, sw, _gp
     freq = _dev(vis_dataset, "chan", dev, torch.float64)
     arrays, dtypes, known = {"UVW": vis_dataset["UVW"], wkey: wsrc}, {"UVW": torch.float64, wkey: None}, {}
+    fused = None
     if isinstance(wsrc, LazyDeviceArray):   # weights made by make_imaging_weight on this dataset: already on the device,
-        known[wkey] = wsrc.device_tensor()  # together with the UVW they were computed from
+        if not do_psf and not wsrc.computed and wsrc.deferred is not None:   # together with the UVW they were computed from
+            # not materialised yet: grid with the NATURAL weights and let the gridder form the imaging weights (A4 in A1)
+            fused = {k: wsrc.deferred[k] for k in ("density", "briggs_factors", "grid_parms")}
+            torch.cuda.current_stream(dev).wait_event(wsrc.ready)
+            known[wkey] = wsrc.deferred["natural"]
+        else:
+            known[wkey] = wsrc.device_tensor()
         known["UVW"] = wsrc.source("UVW", vis_dataset["UVW"])
     if not do_psf:
         arrays["DATA"], dtypes["DATA"] = vis_dataset["DATA"], None
@@ -219,7 +233,8 @@ def _grid(vis_dataset, grid_parms, do_psf, time_chunk, weight_key, apply_flags=F
     for _, blk in feeder:
         w = _flagged_weights(blk[wkey], blk["FLAG"]) if (use_flag and do_psf) else blk[wkey]
         grid, sw = standard_grid(None if do_psf else blk["DATA"], blk["UVW"], w, freq, cgk_1D, _gp, do_psf, not do_psf,
-                                 flag=blk["FLAG"] if (use_flag and not do_psf) else None, grid=grid, sum_weight=sw)
+                                 flag=blk["FLAG"] if (use_flag and not do_psf) else None, grid=grid, sum_weight=sw,
+                                 imaging_weight_from=fused)
     return grid, sw, _gp
 
 
@@ -227,7 +242,7 @@ def _host_call_for(vis_dataset, weight_key, data_key):
     wkey = weight_key if weight_key in vis_dataset else "WEIGHT"
     probe = vis_dataset[data_key] if data_key in vis_dataset else vis_dataset["UVW"]
     wsrc = vis_dataset[wkey]
-    dev = wsrc.base.device if isinstance(wsrc, LazyDeviceArray) else device_of(wsrc, vis_dataset["UVW"], probe)
+    dev = wsrc.device if isinstance(wsrc, LazyDeviceArray) else device_of(wsrc, vis_dataset["UVW"], probe)
     host = is_host(probe) and not hasattr(vis_dataset, "iter_device_chunks")
     return _HostCall(dev, host)
 

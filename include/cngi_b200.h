@@ -110,6 +110,26 @@ int cngi_b200_standard_grid(const cngi_std_grid_args *args, void *stream);
    cngi_b200_standard_grid twice then. */
 int cngi_b200_standard_grid_image_psf(const cngi_std_grid_args *args, void *psf_grid, double *psf_sum_weight, void *stream);
 
+/* A4 folded into A1: make_imaging_weight's degrid (_standard_imaging_weight_degrid_jit, _standard_grid.py:466-518) and
+   make_grid / make_image's gridding (_standard_grid_jit :242-371) in ONE pass over the samples.  args describes the image
+   pass (do_psf 0, complex_grid 1, support 7) but args->weight holds the NATURAL weights (the `natural_imaging_weight` of
+   :443); per sample the kernel forms  w_img = (n_pol == 2 ? (w0 + w1) / 2 : w) / (f0 * rho[cell] + f1)  with exactly the
+   masks and arithmetic of cngi_b200_imaging_weight_degrid -- 0 off the density grid or for NaN uv, undivided where the
+   natural weight or rho is 0 / NaN -- and grids vis * w_img.  The density gather is software-pipelined one round ahead
+   (cp.async), so the pass costs about what the gridding alone costs, and the imaging weights are neither written nor
+   re-read (imaging_weight may be NULL; give a buffer to receive them as cngi_b200_imaging_weight_degrid would write
+   them).  The density grid has its own geometry (make_imaging_weight does not pad, make_imaging_weight.py:153). */
+typedef struct cngi_iw_fused_args {
+    const double *density;      /* float64 density grid (output of cngi_b200_imaging_weight_grid)     */
+    int64_t density_stride[4];  /* element strides of (u, v, imaging chan, imaging pol), as in cngi_iw_degrid_args */
+    const double *briggs_factors; /* [2, n_imag_chan, n_imag_pol] float64, contiguous                   */
+    void *imaging_weight;       /* optional out: real [n_time,n_baseline,n_chan,n_pol]; NULL = not written */
+    int64_t n_u, n_v;           /* density grid size                                                   */
+    double delta_lm[2];         /* its cell size (radians, x negated)                                  */
+} cngi_iw_fused_args;
+
+int cngi_b200_standard_grid_weighted(const cngi_std_grid_args *args, const cngi_iw_fused_args *iw, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * A2  imaging-weight density grid: support 1, nearest cell + conjugate cell, pol-averaged weight when
  *     n_pol >= 2, sum_weight doubled.   _standard_grid.py:306-318,328-330,362-369 as called from

@@ -51,6 +51,7 @@ def test_library_exports_every_declared_symbol(libpath):
 
 
 @pytest.mark.parametrize("cname,pyname", [("cngi_std_grid_args", "StdGridArgs"), ("cngi_iw_grid_args", "IwGridArgs"),
+                                          ("cngi_iw_fused_args", "IwFusedArgs"),
                                           ("cngi_iw_degrid_args", "IwDegridArgs"),
                                           ("cngi_aperture_grid_args", "ApertureGridArgs"),
                                           ("cngi_std_degrid_args", "StdDegridArgs"),

@@ -100,6 +100,14 @@ def test_config2_full_size_weights_and_gridding_vs_oracle(oracle):
     gh = g.cpu().numpy()
     assert same_support(gh, g_ref)
     assert rel_err(gh, g_ref) <= 1e-5 and rel_err(s.cpu().numpy(), s_ref) <= 1e-6
+    del gh, g
+    # the same step with the weight degrid folded into the gridder (what bench.py's pipeline and the host-array API run)
+    out = torch.empty_like(w)
+    g2, s2 = sg.standard_grid(vis, uvw, w, freq, cgk, gp, False, True,
+                              imaging_weight_from=dict(density=rho, briggs_factors=bf, grid_parms=gpw, out=out))
+    assert torch.equal(torch.nan_to_num(out, nan=-1.0), torch.nan_to_num(iwt, nan=-1.0))
+    gh = g2.cpu().numpy()
+    assert same_support(gh, g_ref) and rel_err(gh, g_ref) <= 1e-5 and rel_err(s2.cpu().numpy(), s_ref) <= 1e-6
     torch.cuda.empty_cache()
 
 
