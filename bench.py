@@ -71,6 +71,8 @@ def parse():
     ap.add_argument("--cube-steps", type=int, default=2)
     ap.add_argument("--side-stream", action="store_true",
                     help="issue the imaging-weight chain of step k+1 on a concurrent high-priority stream")
+    ap.add_argument("--fuse-weights", action="store_true",
+                    help="form the imaging weights inside the gridder (cngi_b200_standard_grid_weighted) instead of the A4 pass")
     return ap.parse_args()
 
 
@@ -469,7 +471,8 @@ def run_b200(a):
 
     # the sharding / collective control flow is the one tests/test_distributed_gloo.py exercises on CPU with gloo
     side = torch.cuda.Stream(device=dev, priority=-1) if a.side_stream else None
-    pipe = D.ContinuumPipeline(ops, gp, gp_iw, IW_PARMS, cgk_t, make_bufs_for(torch.complex64), side_stream=side)
+    pipe = D.ContinuumPipeline(ops, gp, gp_iw, IW_PARMS, cgk_t, make_bufs_for(torch.complex64), side_stream=side,
+                               fuse_weights=a.fuse_weights)
 
     def grid_hook(what):   # CUDA events around the dominant kernel, on the stream it is launched on
         ev = torch.cuda.Event(enable_timing=True)

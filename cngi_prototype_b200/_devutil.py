@@ -1,5 +1,6 @@
 """Small helpers shared by the operator wrappers: numpy <-> device plumbing through torch."""
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -44,6 +45,37 @@ def device_of(*xs):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_CONST_MAX_BYTES = 256 * 1024
+_const_cache = {}            # (device, dtype, shape, content hash) -> device tensor; insertion-ordered, oldest evicted
+_const_lock = threading.Lock()
+
+
+def small_constant(x, dtype, device):
+    """Device copy of a SMALL host array (channel frequencies, tap tables, correcting functions, index maps), cached by
+    content.  Uploading a pageable numpy array is a synchronous cudaMemcpy that first drains the stream, so doing it on
+    every call would serialise a caller that queues several datasets back to back; the cached tensor is read-only."""
+    a = np.ascontiguousarray(x)
+    key = (str(device), str(dtype), a.shape, a.dtype.str, hash(a.tobytes()))
+    with _const_lock:
+        t = _const_cache.get(key)
+        if t is None:
+            t = torch.as_tensor(a).to(device=device, dtype=dtype).contiguous()
+            while len(_const_cache) >= 256:
+                _const_cache.pop(next(iter(_const_cache)))
+            _const_cache[key] = t
+    return t
+
+
+def to_device(x, dtype, device):
+    """numpy / torch -> contiguous tensor of `dtype` on `device` (small host arrays through the constant cache)."""
+    if is_torch(x):
+        return x.to(device=device, dtype=dtype).contiguous()
+    a = np.asarray(x)
+    if a.nbytes <= _CONST_MAX_BYTES:
+        return small_constant(a, dtype, device)
+    return torch.as_tensor(np.ascontiguousarray(a)).to(device=device, dtype=dtype).contiguous()
+
+
 class Uploader:
     """Moves inputs to one device with the wanted dtype and keeps them alive until the launch is queued."""
 
@@ -54,8 +86,7 @@ class Uploader:
     def __call__(self, x, dtype):
         if x is None:
             return None
-        t = x if is_torch(x) else torch.as_tensor(np.ascontiguousarray(x))
-        t = t.to(device=self.device, dtype=dtype).contiguous()
+        t = to_device(x, dtype, self.device)
         self.keep.append(t)
         return t
 

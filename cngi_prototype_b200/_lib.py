@@ -33,7 +33,7 @@ class StdGridArgs(C.Structure):
 class IwFusedArgs(C.Structure):
     _fields_ = [
         ("density", vp), ("density_stride", i64 * 4), ("briggs_factors", vp), ("imaging_weight", vp),
-        ("n_u", i64), ("n_v", i64), ("delta_lm", f64 * 2),
+        ("n_u", i64), ("n_v", i64), ("delta_lm", f64 * 2), ("pol_shared", i32), ("reserved", i32),
     ]
 
 

@@ -18,6 +18,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import F32, F64, CHAN_CUBE, CHAN_CONTINUUM, ALGO_AUTO
+from ._devutil import to_device
 
 try:
     import torch
@@ -122,8 +123,7 @@ def standard_grid(vis_data, uvw, weight, freq_chan, cgk_1D, grid_parms, do_psf, 
         keep = []  # keep converted tensors alive until the launch is queued
 
         def dev_t(x, dt):
-            t = x if _is_torch(x) else torch.as_tensor(np.asarray(x))
-            t = t.to(device=dev, dtype=dt).contiguous()
+            t = to_device(x, dt, dev)
             keep.append(t)
             return t
 
@@ -147,9 +147,14 @@ def standard_grid(vis_data, uvw, weight, freq_chan, cgk_1D, grid_parms, do_psf, 
             n_uv_iw = np.asarray(src["grid_parms"]["image_size_padded"]).astype(np.int64)
             assert rho.dtype == torch.float64 and tuple(rho.shape) == (n_ic, n_pol, int(n_uv_iw[0]), int(n_uv_iw[1])), \
                 tuple(rho.shape)
-            bf = dev_t(src["briggs_factors"], torch.float64)
+            bf = src["briggs_factors"]
             assert tuple(bf.shape) == (2, n_ic, n_pol), tuple(bf.shape)
             f = _lib.IwFusedArgs()
+            # pol planes that are stride-0 views of one plane (how the pipeline / make_imaging_weight hand them in after
+            # gridding pol plane 0 only) are identical by construction: the kernel gathers and divides once per sample
+            f.pol_shared = int(n_pol >= 2 and _is_torch(bf) and bf.stride(2) == 0 and rho.stride(1) == 0) \
+                if src.get("pol_shared") is None else int(bool(src["pol_shared"]))
+            bf = dev_t(bf, torch.float64)
             f.density, f.briggs_factors = _ptr(rho), _ptr(bf)
             st = rho.stride()
             for i, v in enumerate((st[2], st[3], st[0], st[1])):
@@ -218,8 +223,7 @@ def standard_grid_image_psf(vis_data, uvw, weight, freq_chan, cgk_1D, grid_parms
     keep = []
 
     def dev_t(x, dt):
-        t = x if _is_torch(x) else torch.as_tensor(np.asarray(x))
-        t = t.to(device=dev, dtype=dt).contiguous()
+        t = to_device(x, dt, dev)
         keep.append(t)
         return t
 

@@ -746,6 +746,7 @@ extern "C" int cngi_b200_standard_grid_weighted(const cngi_std_grid_args *a, con
     p.iw_ds_u = w->density_stride[0], p.iw_ds_v = w->density_stride[1];
     p.iw_ds_c = w->density_stride[2], p.iw_ds_p = w->density_stride[3];
     p.iw_n_u = (int)w->n_u, p.iw_n_v = (int)w->n_v, p.iw_dl = w->delta_lm[0], p.iw_dm = w->delta_lm[1];
+    p.iw_pol_shared = w->pol_shared != 0;
     p.iw_own_scale = !(p.iw_n_u == p.n_u && p.iw_n_v == p.n_v && p.iw_dl == p.dl && p.iw_dm == p.dm);
     return launch_window_iw(p, a, (cudaStream_t)stream);
 }

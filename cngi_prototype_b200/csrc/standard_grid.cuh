@@ -34,7 +34,7 @@ struct StdParams {
     long long iw_ds_u, iw_ds_v, iw_ds_c, iw_ds_p;
     const double *iw_bf;                             // Briggs factors [2, n_ic, n_ip], contiguous
     void *iw_out;                                    // optional: imaging weights written like A4 would (sample layout)
-    int iw_n_u, iw_n_v, iw_own_scale;                // geometry of the density grid (make_imaging_weight does not pad)
+    int iw_n_u, iw_n_v, iw_own_scale, iw_pol_shared;                // geometry of the density grid (make_imaging_weight does not pad)
     double iw_dl, iw_dm;
 };
 

@@ -54,11 +54,10 @@ template <typename T, bool CPLX, int S, int PP, bool DUAL = false, bool IWF = fa
     // two raw-sample buffers per warp (cp.async targets): vis, weight, (u, v)
     static constexpr int RAW_BYTES = 32 * (PP * 3 * (int)sizeof(T)) + ITER * 16;
     // fused imaging weights: a two-slot (u, v) ring -- the uv of round r + 1 is in flight while round r is staged, so that
-    // the density gather of round r + 1 can be ISSUED one round ahead of its use -- and two buffers of gathered density
-    // values (one double per pol of each of the 32 samples of a round)
+    // the density gather of round r + 1 can be ISSUED one round ahead of its use (it lands in registers: a cp.async gather
+    // costs one shared-memory wavefront per lane, measured +64 wavefronts per round on the pipe that co-limits this kernel)
     static constexpr int IW_UV_BYTES = IWF ? ITER * 16 : 0;       // per ring slot
-    static constexpr int IW_RHO_BYTES = IWF ? 32 * PP * 8 : 0;    // per buffer
-    static constexpr int WARP_BYTES = REC_BYTES + 2 * RAW_BYTES + 2 * IW_UV_BYTES + 2 * IW_RHO_BYTES;
+    static constexpr int WARP_BYTES = REC_BYTES + 2 * RAW_BYTES + 2 * IW_UV_BYTES;
     static constexpr int ROW_BYTES = W * (int)sizeof(T);
 };
 
@@ -80,6 +79,14 @@ __host__ __device__ inline WinSmem win_smem_layout(int oversampling, int c_n, in
     L.total = L.wbuf + warps * Cfg::WARP_BYTES;
     return L;
 }
+
+// unroll factor of the phase-2 sample loop (development knob: tools/build_variant.sh ... -DCNGI_WIN_UNROLL=2)
+#ifndef CNGI_WIN_UNROLL
+#define CNGI_WIN_UNROLL 1
+#endif
+#define CNGI_STR2(x) #x
+#define CNGI_STR(x) CNGI_STR2(x)
+#define CNGI_WIN_CONSUME_UNROLL _Pragma(CNGI_STR(unroll CNGI_WIN_UNROLL))
 
 #ifndef CNGI_WIN_MINB_F32
 #define CNGI_WIN_MINB_F32 4
@@ -218,7 +225,6 @@ std_grid_window_kernel(StdParams p)
     const unsigned wd_s = wbuf_s + Cfg::IDX_BYTES;
     const unsigned raw_s = wbuf_s + Cfg::REC_BYTES;
     const unsigned uvr_s = raw_s + 2 * Cfg::RAW_BYTES;            // IWF: (u, v) ring, two slots
-    const unsigned rho_s = uvr_s + 2 * Cfg::IW_UV_BYTES;          // IWF: gathered density, two buffers
     const unsigned tap_s = (unsigned)__cvta_generic_to_shared(tap);
     const int rot_stride = n_off * ROW_BYTES;   // bytes between two rotations of the tap table
     const int G = p.G;
@@ -318,9 +324,11 @@ std_grid_window_kernel(StdParams p)
         for (int ip = 0; ip < PP; ++ip) apol[ip] = (ip < npol) ? pol_of(p, p0 + ip) : 0;
         double bf0[PP], bf1[PP];   // IWF: Briggs factors of this lane's (imaging channel, pol) planes
         bool iw_ok = false;        // IWF: the sample's cell of the density grid exists (set when its gather is issued)
+        double rho_reg[PP];        // IWF: the gathered density values of the NEXT sample to be staged (in flight during phase 2)
 #pragma unroll
         for (int ip = 0; ip < PP; ++ip) {
             bf0[ip] = bf1[ip] = 0.0;
+            rho_reg[ip] = 0.0;
             if constexpr (IWF) {
                 const int q = a_chan1 * p.n_ip + apol[ip];
                 bf0[ip] = p.iw_bf[q];
@@ -476,11 +484,8 @@ std_grid_window_kernel(StdParams p)
                         stamp_inside(cq.uc, cq.vc, 0, p.iw_n_u, p.iw_n_v)) {
                         iw_ok = true;
                         const double *src = p.iw_density + cq.uc * p.iw_ds_u + cq.vc * p.iw_ds_v + a_chan1 * p.iw_ds_c;
-#pragma unroll
-                        for (int ip = 0; ip < PP; ++ip)
-                            if (ip < npol)
-                                cp_async_bytes(rho_s + buf * Cfg::IW_RHO_BYTES + (lane * PP + ip) * 8, src + apol[ip] * p.iw_ds_p,
-                                               std::integral_constant<int, 8>{});
+                        rho_reg[0] = __ldg(src + apol[0] * p.iw_ds_p);
+                        if (PP > 1 && !p.iw_pol_shared && npol > 1) rho_reg[PP - 1] = __ldg(src + apol[PP - 1] * p.iw_ds_p);
                     }
                 }
             }
@@ -542,24 +547,33 @@ std_grid_window_kernel(StdParams p)
                     // imaging weights of the sample, operation for operation what iw_degrid_kernel (A4) computes:
                     // off the density grid or NaN uv -> 0; else avg of the two pols (n_pol == 2) or the natural weight,
                     // divided by f0 * rho + f1 where the natural weight and rho are both finite and non-zero
-                    const double avg = (p.n_pol == 2) ? __dmul_rn(__dadd_rn((double)wsrc[0], (double)wsrc[PP - 1]), 0.5) : 0.0;
+                    auto quotient = [](double num, double den) -> double {
+                        return sizeof(T) == 4 ? (double)__fdiv_rn((float)num, (float)den) : __ddiv_rn(num, den);
+                    };
+                    if (PP == 2 && p.iw_pol_shared && p.n_pol == 2) {
+                        // both pols see the same density value and Briggs factors (pol-averaged weights): one division
+                        const double w0 = (double)wsrc[0], w1 = (double)wsrc[PP - 1];
+                        const double avg = __dmul_rn(__dadd_rn(w0, w1), 0.5);
+                        double q = avg;
+                        const double r = rho_reg[0];
+                        if (iw_ok && !isnan(r) && r != 0.0) q = quotient(avg, __dadd_rn(__dmul_rn(bf0[0], r), bf1[0]));
+                        raw_w[0] = (T)(iw_ok ? ((!isnan(w0) && w0 != 0.0) ? q : avg) : 0.0);
+                        raw_w[PP - 1] = (T)(iw_ok ? ((!isnan(w1) && w1 != 0.0) ? q : avg) : 0.0);
+                    } else {
+                        const double avg = (p.n_pol == 2) ? __dmul_rn(__dadd_rn((double)wsrc[0], (double)wsrc[PP - 1]), 0.5) : 0.0;
 #pragma unroll
-                    for (int ip = 0; ip < PP; ++ip) {
-                        if (ip < npol) {
-                            double iw = 0.0;
-                            if (iw_ok) {
-                                const double w = (double)wsrc[ip];
-                                iw = (p.n_pol == 2) ? avg : w;
-                                if (!isnan(w) && w != 0.0) {
-                                    double r;
-                                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(rho_s + buf * Cfg::IW_RHO_BYTES + (lane * PP + ip) * 8));
-                                    if (!isnan(r) && r != 0.0) {
-                                        const double den = __dadd_rn(__dmul_rn(bf0[ip], r), bf1[ip]);
-                                        iw = sizeof(T) == 4 ? (double)__fdiv_rn((float)iw, (float)den) : __ddiv_rn(iw, den);
-                                    }
+                        for (int ip = 0; ip < PP; ++ip) {
+                            if (ip < npol) {
+                                double iw = 0.0;
+                                if (iw_ok) {
+                                    const double w = (double)wsrc[ip];
+                                    iw = (p.n_pol == 2) ? avg : w;
+                                    const double r = p.iw_pol_shared ? rho_reg[0] : rho_reg[ip];
+                                    if (!isnan(w) && w != 0.0 && !isnan(r) && r != 0.0)
+                                        iw = quotient(iw, __dadd_rn(__dmul_rn(bf0[ip], r), bf1[ip]));
                                 }
+                                raw_w[ip] = (T)iw;
                             }
-                            raw_w[ip] = (T)iw;
                         }
                     }
                     if (p.iw_out) {   // the caller wants IMAGING_WEIGHT too (s_next already points at the next round)
@@ -679,7 +693,7 @@ std_grid_window_kernel(StdParams p)
             }
         };
         auto consume = [&]() {
-#pragma unroll 1
+            CNGI_WIN_CONSUME_UNROLL
             for (int i = 0; i < ITER; i += NS) {
                 int4 idx[NS];
                 T wd[NS][WD], cu[NS], cv[NS][W];

@@ -116,7 +116,7 @@ class ContinuumPipeline:
         pipe.flush()            # results of the last step: pipe.last (grid, gsw valid on rank 0)
     """
 
-    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs, side_stream=None, fuse_weights=True):
+    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs, side_stream=None, fuse_weights=False):
         """side_stream (a high-priority CUDA stream, device tensors only): the whole imaging-weight chain of step k+1
         (density grid, all-reduce, Briggs factors, weight degrid -- memory-latency bound kernels) is issued there and
         runs CONCURRENTLY with the gridding kernel of step k on the current stream (issue bound): whenever a gridder
@@ -125,8 +125,10 @@ class ContinuumPipeline:
         self.ops, self.gp, self.gp_iw, self.iw_parms, self.cgk = ops, gp, gp_iw, iw_parms, cgk
         self.side = side_stream
         # fuse_weights: the weight degrid (A4) runs inside the gridder (ops.standard_grid_weighted) when the ops have it and
-        # the support is 7 -- the imaging weights are then never written or re-read
-        self.fuse_weights = bool(fuse_weights) and side_stream is None and int(gp.get("support", 7)) == 7
+        # the support is 7 -- the imaging weights are then never written or re-read.  Measured on C2 (B200, fp32): the
+        # gridder is issue bound, so the folded-in work costs what the separate pass costs (2.53 vs 2.50 ms per step): off
+        # by default here, used by the host-array API where it saves a 0.46 GB intermediate (imaging._grid)
+        self.fuse_weights = bool(fuse_weights) and int(gp.get("support", 7)) == 7 and hasattr(ops, "standard_grid_weighted")
         self.bufs = [make_bufs(), make_bufs()]
         self.pend_density = [[], []]
         self.pend_grid = [[], []]
@@ -178,7 +180,7 @@ class ContinuumPipeline:
     def _stage_b(self, d, slot, grid_hook):
         b = self.bufs[slot]
         self._wait(self.pend_density[slot])
-        fused = self.fuse_weights and hasattr(self.ops, "standard_grid_weighted")
+        fused = self.fuse_weights
         iw = self._weight_source(b) if fused else self._weights(d, b)
         self._wait(self.pend_grid[slot])   # the reduce that last read this grid buffer
         b.grid.zero_()
@@ -195,7 +197,7 @@ class ContinuumPipeline:
         if world()[1] > 1:   # partial uv-grids -> the rank that runs the FFT
             self.pend_grid[slot] = [dist.reduce(_as_real(b.grid), 0, async_op=True), dist.reduce(b.gsw, 0, async_op=True)]
         self.last = b
-        return iw
+        return None if fused else iw
 
     def _weights_on_side(self, d, slot):
         """The whole weight chain of a step on the side stream; returns (imaging weights, event that marks them ready)."""
@@ -205,10 +207,12 @@ class ContinuumPipeline:
             self._stage_a(d, slot)
             b = self.bufs[slot]
             self._wait(self.pend_density[slot])
-            iw = self._weights(d, b)
+            iw = self._weight_source(b) if self.fuse_weights else self._weights(d, b)
             ev = torch.cuda.Event()
             ev.record(self.side)
-        iw.record_stream(main)
+        for t in (iw.values() if isinstance(iw, dict) else (iw,)):
+            if torch.is_tensor(t):
+                t.record_stream(main)
         return iw, ev
 
     def _grid_on_main(self, d, slot, grid_hook, iw, ev):
@@ -219,13 +223,17 @@ class ContinuumPipeline:
         b.gsw.zero_()
         if grid_hook is not None:
             grid_hook("begin")
-        self.ops.standard_grid(d["vis"], d["uvw"], iw, d["freq_chan"], self.cgk, self.gp, grid=b.grid, sum_weight=b.gsw)
+        if isinstance(iw, dict):
+            self.ops.standard_grid_weighted(d["vis"], d["uvw"], d["weight"], d["freq_chan"], self.cgk, self.gp, iw,
+                                            grid=b.grid, sum_weight=b.gsw)
+        else:
+            self.ops.standard_grid(d["vis"], d["uvw"], iw, d["freq_chan"], self.cgk, self.gp, grid=b.grid, sum_weight=b.gsw)
         if grid_hook is not None:
             grid_hook("end")
         if world()[1] > 1:   # partial uv-grids -> the rank that runs the FFT
             self.pend_grid[slot] = [dist.reduce(_as_real(b.grid), 0, async_op=True), dist.reduce(b.gsw, 0, async_op=True)]
         self.last = b
-        return iw
+        return None if isinstance(iw, dict) else iw
 
     def step(self, d, grid_hook=None):
         slot = self.k & 1

@@ -18,7 +18,7 @@ import numbers
 
 import numpy as np
 
-from ._devutil import torch, is_torch, device_of
+from ._devutil import torch, is_torch, device_of, small_constant
 from ._gridding_convolutional_kernels import _create_prolate_spheroidal_kernel_1D, correcting_function_1D
 from ._standard_grid import standard_grid
 from ._imaging_weight import (imaging_weight_grid, calculate_briggs_parms,
@@ -86,6 +86,8 @@ def _dev(ds, key, device, dtype=None):
     x = ds[key]
     if isinstance(x, LazyDeviceArray):
         x = x.device_tensor()
+    if not is_torch(x) and dtype is not None and np.asarray(x).nbytes <= 256 * 1024:
+        return small_constant(x, dtype, device)     # e.g. the channel frequencies: no synchronous copy per call
     t = x if is_torch(x) else torch.as_tensor(np.ascontiguousarray(x))
     return t.to(device=device, dtype=dtype) if dtype is not None else t.to(device=device)
 

@@ -126,6 +126,11 @@ typedef struct cngi_iw_fused_args {
     void *imaging_weight;       /* optional out: real [n_time,n_baseline,n_chan,n_pol]; NULL = not written */
     int64_t n_u, n_v;           /* density grid size                                                   */
     double delta_lm[2];         /* its cell size (radians, x negated)                                  */
+    int32_t pol_shared;         /* the caller GUARANTEES that all pol planes of density and all pol columns of
+                                   briggs_factors are identical (true for what cngi_b200_imaging_weight_grid and
+                                   cngi_b200_briggs_factors produce when n_pol >= 2: the weights are pol-averaged,
+                                   _standard_grid.py:328-330): one gather and one division per sample instead of one per pol */
+    int32_t reserved;
 } cngi_iw_fused_args;
 
 int cngi_b200_standard_grid_weighted(const cngi_std_grid_args *args, const cngi_iw_fused_args *iw, void *stream);

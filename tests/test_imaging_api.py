@@ -117,8 +117,9 @@ def test_channel_chunked_cube_equals_unchunked(oracle):
 
 
 @pytest.mark.gpu
-def test_continuum_pipeline_side_stream_matches_single_stream():
-    """ContinuumPipeline with the weight chain on a concurrent high-priority stream == the single-stream pipeline."""
+def test_continuum_pipeline_side_stream_and_fused_weights_match_the_plain_pipeline():
+    """ContinuumPipeline with the weight chain on a concurrent high-priority stream, and with the weight degrid folded
+    into the gridder (fuse_weights, the default), == the single-stream pipeline that materialises the imaging weights."""
     import torch
     from types import SimpleNamespace
     from cngi_prototype_b200 import synth, distributed as D
@@ -137,15 +138,19 @@ def test_continuum_pipeline_side_stream_matches_single_stream():
                                grid=torch.empty((1, 2, n, n), dtype=torch.complex64, device="cuda"),
                                gsw=torch.empty((1, 2), dtype=torch.float64, device="cuda"))
     res = []
-    for side in (None, torch.cuda.Stream(priority=-1)):
+    for side, fuse in ((None, False), (torch.cuda.Stream(priority=-1), False), (None, True)):
         pipe = D.ContinuumPipeline(D.cuda_ops(), gp, gp_iw, dict(weighting="briggs", robust=0.5), cgk, make_bufs,
-                                   side_stream=side)
+                                   side_stream=side, fuse_weights=fuse)
+        assert pipe.fuse_weights == fuse
         for _ in range(4):
             pipe.step(T)
         iw = pipe.flush()
         torch.cuda.synchronize()
-        res.append((pipe.last.grid.cpu().numpy().copy(), pipe.last.gsw.cpu().numpy().copy(), iw.cpu().numpy().copy()))
+        res.append((pipe.last.grid.cpu().numpy().copy(), pipe.last.gsw.cpu().numpy().copy(),
+                    None if fuse else iw.cpu().numpy().copy()))
     assert rel_err(res[1][0], res[0][0]) <= 1e-5 and rel_err(res[1][1], res[0][1]) <= 1e-12
+    assert rel_err(res[2][0], res[0][0]) <= 1e-5 and rel_err(res[2][1], res[0][1]) <= 1e-12
+    assert np.array_equal(res[2][0] != 0, res[0][0] != 0)
     a, b = res[1][2], res[0][2]   # fp64 atomics land in a different order: equal to rounding, not bitwise
     assert np.array_equal(np.isnan(a), np.isnan(b))
     m = np.isfinite(b)
