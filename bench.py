@@ -338,7 +338,8 @@ def cube_record(a, dev, rank, world, dist, time_split, groups):
     GPU (1024 channels / 2e10 samples on 8 GPUs), fp32, channel-sharded (synthesis_imaging_cube.py:105-124).
     time_split = 1: a rank owns its channels end to end, no exchange.  time_split = 2: pairs of ranks share a channel
     block of twice the size, each grids half of the integrations, and every chunk of planes is summed onto the pair's
-    root with an NCCL reduce over the sub-group before the FFT (the "NCCL grid reduce" of config 5)."""
+    root with an NCCL reduce over the sub-group before the FFT (the "NCCL grid reduce" of config 5); the root of a chunk
+    rotates over the pair (distributed.cube_imaging(rotate_roots=True)) so that both GPUs run FFTs."""
     import torch
     from cngi_prototype_b200 import synth, distributed as D
     from cngi_prototype_b200._gridding_convolutional_kernels import _create_prolate_spheroidal_kernel_1D
@@ -378,7 +379,7 @@ def cube_record(a, dev, rank, world, dist, time_split, groups):
 
     def one(tm=None):
         return D.cube_imaging(ops, d, gp, cgk, chan_chunk=a.cube_chan_chunk, time_split=time_split, groups=groups,
-                              presharded=True, timer=tm, keep_image=False)
+                              presharded=True, timer=tm, keep_image=False, rotate_roots=True)
 
     one()                                    # warm-up: cuFFT plan, allocator pools
     torch.cuda.synchronize()
@@ -411,7 +412,7 @@ def cube_record(a, dev, rank, world, dist, time_split, groups):
     rec = {"time_split": time_split, "ms_per_step": ms, "value": world * n_samples / (ms * 1e-3), "unit": "vis/s",
            "samples_per_gpu": n_samples, "n_chan_total": n_chan_total, "chan_per_group": n_chan_grp,
            "integrations_per_gpu": n_time, "chan_chunk": a.cube_chan_chunk, "steps": a.cube_steps, "warmup": 1,
-           "phase_ms_max_over_ranks": {"grid": g_ms, "reduce": r_ms, "image_fft_crop_correct": i_ms},
+           "phase_ms_max_over_ranks": {"grid": g_ms, "reduce_incl_wait_for_partner": r_ms, "image_fft_crop_correct": i_ms},
            "fft_share": i_ms / ms if ms else None,
            "gridding_vis_per_s_per_gpu": n_samples / (g_ms * 1e-3) if g_ms else None,
            "sum_weight_finite_positive": ok}

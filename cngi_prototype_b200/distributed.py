@@ -317,7 +317,7 @@ class _PhaseTimer:
 
 
 def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image_out=None, with_psf=False,
-                 presharded=False, timer=None, keep_image=True):
+                 presharded=False, timer=None, keep_image=True, rotate_roots=False):
     """Channel-sharded cube imaging with bounded memory (BASELINE config 5; synthesis_imaging_cube.py:105-124,171-220).
 
     Every rank holds (or can slice) the full sample arrays `d` = {vis, uvw, weight, freq_chan[, flag]}.  The image
@@ -343,6 +343,10 @@ def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image
     timer: a _PhaseTimer; CUDA events are recorded after each chunk's gridding ("grid"), reduce ("reduce") and
     transform ("image").  keep_image=False drops each chunk's image after computing it (benchmarks of cubes whose
     output would not fit next to the samples); sum_weight is still returned.
+    rotate_roots (time_split > 1): the root of a chunk rotates over the ranks of the group (chunk j -> member j mod
+    time_split) and the group walks `time_split` chunks per round through as many grid buffers: after the reduces every
+    member transforms ITS chunk, so the FFTs -- 90 % of a config-5 step -- run on all GPUs instead of on one per group.
+    Each rank then returns the planes it owns: the last element of the result is the list of their (chan_lo, chan_hi).
     """
     assert keep_image or not with_psf, "keep_image=False is a benchmark mode of the image-only path"
     rank, ws = world()
@@ -357,73 +361,97 @@ def cube_imaging(ops, d, gp, cgk, chan_chunk=0, time_split=1, groups=None, image
     n_u, n_v = (int(x) for x in gp["image_size_padded"])
     step = int(chan_chunk) if chan_chunk else max(chi - clo, 1)
     gpc = dict(gp, chan_mode="cube")
-    grid = ops.zeros((min(step, max(chi - clo, 1)), n_pol, n_u, n_v), True)
-    gsw = ops.zeros((grid.shape[0], n_pol), False)
-    pgrid = torch.zeros(tuple(grid.shape), dtype=grid.real.dtype, device=grid.device) if with_psf else None
-    pgsw = ops.zeros((grid.shape[0], n_pol), False) if with_psf else None
-    psf, psf_sum_weight = None, None
-    image, sum_weight = image_out, None
     group = groups[cg] if groups else None
-    for c0 in range(clo, chi, step):
-        c1 = min(chi, c0 + step)
-        g, s = grid[:c1 - c0], gsw[:c1 - c0]
+    rotate = bool(rotate_roots) and group is not None and time_split > 1
+    n_buf = time_split if rotate else 1
+    n_planes = min(step, max(chi - clo, 1))
+
+    def make_buf():
+        b = SimpleNamespace(grid=ops.zeros((n_planes, n_pol, n_u, n_v), True), gsw=ops.zeros((n_planes, n_pol), False),
+                            pgrid=None, pgsw=None)
+        if with_psf:
+            b.pgrid = torch.zeros(tuple(b.grid.shape), dtype=b.grid.real.dtype, device=b.grid.device)
+            b.pgsw = ops.zeros((n_planes, n_pol), False)
+        return b
+
+    bufs = [make_buf() for _ in range(n_buf)]
+    out = SimpleNamespace(image=image_out, sum_weight=None, psf=None, psf_sum_weight=None, owned=[])
+
+    def mark(name):
         if timer is not None:
-            timer.mark("begin")
+            timer.mark(name)
+
+    def grid_chunk(c0, c1, b):
+        g, s = b.grid[:c1 - c0], b.gsw[:c1 - c0]
         g.zero_()
         s.zero_()
         kw = {}
         if d.get("flag") is not None:
             kw["flag"] = d["flag"][tlo:thi, :, c0:c1]
         if with_psf:
-            pg, ps = pgrid[:c1 - c0], pgsw[:c1 - c0]
-            pg.zero_()
-            ps.zero_()
+            b.pgrid[:c1 - c0].zero_()
+            b.pgsw[:c1 - c0].zero_()
         if thi > tlo:
             args = (d["uvw"][tlo:thi], d["weight"][tlo:thi, :, c0:c1], d["freq_chan"][c0:c1], cgk, gpc)
             if with_psf and hasattr(ops, "grid_image_psf"):
-                ops.grid_image_psf(d["vis"][tlo:thi, :, c0:c1], *args, grid=g, sum_weight=s, psf_grid=pg,
-                                   psf_sum_weight=ps, **kw)
+                ops.grid_image_psf(d["vis"][tlo:thi, :, c0:c1], *args, grid=g, sum_weight=s, psf_grid=b.pgrid[:c1 - c0],
+                                   psf_sum_weight=b.pgsw[:c1 - c0], **kw)
             else:
                 ops.standard_grid(d["vis"][tlo:thi, :, c0:c1], *args, grid=g, sum_weight=s, **kw)
                 if with_psf:
-                    ops.standard_grid_psf(*args, grid=pg, sum_weight=ps)
-        if timer is not None:
-            timer.mark("grid")
-        if group is not None:
-            dist.reduce(_as_real(g), root, group=group)
-            dist.reduce(s, root, group=group)
-            if with_psf:
-                dist.reduce(pg, root, group=group)
-                dist.reduce(ps, root, group=group)
-            if timer is not None:
-                timer.mark("reduce")
-        if rank == root:
-            img = ops.to_image(g, s, gpc)
-            if timer is not None:
-                timer.mark("image")
-            if not keep_image:
-                if sum_weight is None:
-                    sum_weight = ops.zeros((chi - clo, n_pol), False)
-                sum_weight[c0 - clo:c1 - clo] = s
-                del img
-                continue
-            if image is None:
-                image = ops.zeros(tuple(img.shape[:2]) + (chi - clo, n_pol), False).to(img.dtype)
-                sum_weight = ops.zeros((chi - clo, n_pol), False)
-            elif sum_weight is None:
-                sum_weight = ops.zeros((chi - clo, n_pol), False)
-            image[:, :, c0 - clo:c1 - clo] = img
-            sum_weight[c0 - clo:c1 - clo] = s
-            if with_psf:
-                pimg = ops.to_image(pg, ps, gpc)
-                if psf is None:
-                    psf = ops.zeros(tuple(pimg.shape[:2]) + (chi - clo, n_pol), False).to(pimg.dtype)
-                    psf_sum_weight = ops.zeros((chi - clo, n_pol), False)
-                psf[:, :, c0 - clo:c1 - clo] = pimg
-                psf_sum_weight[c0 - clo:c1 - clo] = ps
+                    ops.standard_grid_psf(*args, grid=b.pgrid[:c1 - c0], sum_weight=b.pgsw[:c1 - c0])
+
+    def reduce_chunk(c0, c1, b, dst):
+        if group is None:
+            return
+        dist.reduce(_as_real(b.grid[:c1 - c0]), dst, group=group)
+        dist.reduce(b.gsw[:c1 - c0], dst, group=group)
+        if with_psf:
+            dist.reduce(b.pgrid[:c1 - c0], dst, group=group)
+            dist.reduce(b.pgsw[:c1 - c0], dst, group=group)
+
+    def image_chunk(c0, c1, b):
+        g, s = b.grid[:c1 - c0], b.gsw[:c1 - c0]
+        img = ops.to_image(g, s, gpc)
+        out.owned.append((c0, c1))
+        if out.sum_weight is None:
+            out.sum_weight = ops.zeros((chi - clo, n_pol), False)
+        out.sum_weight[c0 - clo:c1 - clo] = s
+        if not keep_image:
+            return
+        if out.image is None:
+            out.image = ops.zeros(tuple(img.shape[:2]) + (chi - clo, n_pol), False).to(img.dtype)
+        out.image[:, :, c0 - clo:c1 - clo] = img
+        if with_psf:
+            pimg = ops.to_image(b.pgrid[:c1 - c0], b.pgsw[:c1 - c0], gpc)
+            if out.psf is None:
+                out.psf = ops.zeros(tuple(pimg.shape[:2]) + (chi - clo, n_pol), False).to(pimg.dtype)
+                out.psf_sum_weight = ops.zeros((chi - clo, n_pol), False)
+            out.psf[:, :, c0 - clo:c1 - clo] = pimg
+            out.psf_sum_weight[c0 - clo:c1 - clo] = b.pgsw[:c1 - c0]
+
+    chunks = [(c0, min(chi, c0 + step)) for c0 in range(clo, chi, step)]
+    for j0 in range(0, len(chunks), n_buf):
+        todo = chunks[j0:j0 + n_buf]
+        mark("begin")
+        mine = []
+        for i, (c0, c1) in enumerate(todo):          # every rank of the group grids its time part of each chunk ...
+            grid_chunk(c0, c1, bufs[i])
+            mark("grid")
+            dst = root + ((j0 + i) % time_split if rotate else 0)
+            reduce_chunk(c0, c1, bufs[i], dst)       # ... and the partial grids are summed onto that chunk's root
+            if group is not None:
+                mark("reduce")
+            if rank == dst:
+                mine.append((c0, c1, bufs[i]))
+        for c0, c1, b in mine:                        # the roots transform their chunks at the same time
+            image_chunk(c0, c1, b)
+            mark("image")
+    owner = bool(out.owned) or rank == root
+    rng = out.owned if rotate else (clo, chi)
     if with_psf:
-        return (image, sum_weight, psf, psf_sum_weight, (clo, chi)) if rank == root else (None, None, None, None, (clo, chi))
-    return (image, sum_weight, (clo, chi)) if rank == root else (None, None, (clo, chi))
+        return (out.image, out.sum_weight, out.psf, out.psf_sum_weight, rng) if owner else (None, None, None, None, rng)
+    return (out.image, out.sum_weight, rng) if owner else (None, None, rng)
 
 
 def cuda_ops():

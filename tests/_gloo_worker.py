@@ -110,7 +110,12 @@ def main():
     groups = D.make_time_groups(ws, ws)
     img2, sw2, psf2, psw2, cr2 = D.cube_imaging(oracle_ops(), full, gpi, cgk, chan_chunk=4, time_split=ws, groups=groups,
                                                 with_psf=True)
-    extra = dict(cube_img=img1.numpy(), cube_img_sw=sw1.numpy(), cube_img_range=np.array(cr1))
+    # rotating roots: chunk j of the single group is reduced onto rank j mod ws, every rank transforms the chunks it owns
+    img3, sw3, own3 = D.cube_imaging(oracle_ops(), full, gpi, cgk, chan_chunk=1, time_split=ws, groups=groups, rotate_roots=True)
+    extra = dict(cube_img=img1.numpy(), cube_img_sw=sw1.numpy(), cube_img_range=np.array(cr1),
+                 cube_rot_owned=np.array(own3).reshape(-1, 2))
+    if img3 is not None:
+        extra.update(cube_rot_img=img3.numpy(), cube_rot_sw=sw3.numpy())
     if img2 is not None:
         extra.update(cube_img_ts=img2.numpy(), cube_img_ts_sw=sw2.numpy(), cube_psf_ts=psf2.numpy(), cube_psf_ts_sw=psw2.numpy())
     np.savez(os.path.join(out, "rank%d.npz" % rank), **extra, grid=bufs.grid.numpy(), gsw=bufs.gsw.numpy(), iw=iw.numpy(),

@@ -86,3 +86,14 @@ def test_sharded_step_matches_single_process(tmp_path, oracle, world_size):
     ref_psf = oracle.correct_image(oracle.grid_to_uncorrected_image(pg, gpi["image_size"]), ps, corr)
     assert np.max(np.abs(ranks[0]["cube_psf_ts"] - ref_psf)) <= 1e-12 * np.max(np.abs(ref_psf))
     assert np.max(np.abs(ranks[0]["cube_psf_ts_sw"] - ps)) <= 1e-12 * np.max(np.abs(ps))
+    # rotating roots: every rank owns the chunks j with j mod world_size == rank; together they make the cube
+    seen = np.zeros(6, dtype=int)
+    for r, rk in enumerate(ranks):
+        owned = rk["cube_rot_owned"]
+        assert [int(c0) % world_size for c0, _ in owned] == [r] * len(owned) and len(owned) >= 6 // world_size
+        for c0, c1 in owned:
+            seen[c0:c1] += 1
+            a, b = rk["cube_rot_img"][:, :, c0:c1], ref_img[:, :, c0:c1]
+            assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(ref_img))
+            assert np.max(np.abs(rk["cube_rot_sw"][c0:c1] - sc[c0:c1])) <= 1e-12 * np.max(np.abs(sc))
+    assert np.array_equal(seen, np.ones(6, dtype=int))
