@@ -388,10 +388,11 @@ def cube_record(a, dev, rank, world, dist, time_split, groups):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    sw = None
+    sw, owned = None, None
     for _ in range(a.cube_steps):
         out = one(timer)
-        sw = out[1] if out[1] is not None else sw
+        if out[1] is not None:
+            sw, owned = out[1], out[-1]
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -403,7 +404,10 @@ def cube_record(a, dev, rank, world, dist, time_split, groups):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(ph, op=dist.ReduceOp.MAX)
-    ok = bool(torch.isfinite(sw).all() and (sw > 0).all()) if sw is not None else None
+    ok = None
+    if sw is not None:   # every plane this rank transformed has a finite, positive sum of weights
+        rows = torch.cat([sw[c0:c1] for c0, c1 in owned]) if isinstance(owned, list) else sw
+        ok = bool(torch.isfinite(rows).all() and (rows > 0).all() and rows.numel() > 0)
     del d, vis, wgt
     torch.cuda.empty_cache()
     ms = float(ms.item())

@@ -58,12 +58,14 @@ def _plan_for(n_u, n_v, n_planes, precision, device):
 
 
 def grid_to_image(grid, image_size, sum_weight=None, corr_u=None, corr_v=None, norm_image=None, pb_image=None,
-                  pb_limit=0.0, divide_by_centre=False, single_precision_roundtrip=False):
+                  pb_limit=0.0, divide_by_centre=False, single_precision_roundtrip=False, centre_pixel=None):
     """Kernel-side grid (n_chan, n_pol, n_u, n_v), complex or real -> API-side image (l, m, n_chan, n_pol), real.
 
     image = Re(fftshift(ifft2(ifftshift(grid)))) cropped * (n_u*n_v), / sum_weight (0 -> 1),
             / (corr_u[l]*corr_v[m] * norm_image), zeroed where pb_image < pb_limit.
     norm_image / pb_image are kernel-side (n_chan, n_pol, l, m) or (l, m) (broadcast).
+    divide_by_centre: every plane is divided by its pixel `centre_pixel` (default (l // 2, m // 2); make_psf_with_gcf.py:140
+    uses grid_parms['image_center']); a plane whose centre value is 0 or not finite is left undivided.
     """
     L = _lib.lib()
     like_torch = is_torch(grid)
@@ -90,6 +92,9 @@ def grid_to_image(grid, image_size, sum_weight=None, corr_u=None, corr_v=None, n
             setattr(a, name + "_planes", 1 if t.dim() == 2 else n_c * n_p)
     a.pb_limit = float(pb_limit)
     a.divide_by_centre, a.single_precision_roundtrip = int(bool(divide_by_centre)), int(bool(single_precision_roundtrip))
+    if divide_by_centre and centre_pixel is not None:
+        a.divide_by_centre = 2
+        a.centre_pixel[0], a.centre_pixel[1] = int(centre_pixel[0]), int(centre_pixel[1])
     a.image = ptr(image)
     plan = _plan_for(n_u, n_v, n_c * n_p, precision, dev)
     with torch.cuda.device(dev):

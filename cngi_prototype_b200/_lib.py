@@ -96,7 +96,7 @@ class GridToImageArgs(C.Structure):
         ("pb_image", vp), ("pb_image_planes", i64),
         ("pb_limit", f64),
         ("divide_by_centre", i32), ("single_precision_roundtrip", i32),
-        ("image", vp),
+        ("image", vp), ("centre_pixel", i64 * 2),
     ]
 
 

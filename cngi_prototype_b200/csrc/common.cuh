@@ -69,9 +69,11 @@ __device__ __forceinline__ int oversample_offset(int centre, double pos, int ove
     return __double2int_rd(__dadd_rn(__dmul_rn(off, (double)oversampling), 0.5));
 }
 
+// Written without `centre +- half` so that a saturated centre (uvw = +-inf or huge: __double2int_rz clamps to INT_MAX /
+// INT_MIN) cannot wrap around and pass the test -- such samples are skipped like every other out-of-grid sample.
 __device__ __forceinline__ bool stamp_inside(int uc, int vc, int half, int n_u, int n_v)
 {
-    return (uc + half < n_u) && (vc + half < n_v) && (uc - half >= 0) && (vc - half >= 0);
+    return (uc < n_u - half) && (vc < n_v - half) && (uc >= half) && (vc >= half);
 }
 
 // weighted_data = vis * weight as numba evaluates complex128 * float64 (weight promoted to w + 0j).

@@ -10,7 +10,9 @@
 //   fftshift  on the OUTPUT is an index remap folded, together with the crop, into the one pass of the
 //   post kernel, which reads only the cropped window and writes the real, normalised image.
 #include "common.cuh"
+#include "fft_bluestein.cuh"
 #include <cufft.h>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 
@@ -22,6 +24,11 @@ struct cngi_fft_plan {
     int64_t tail_planes;
     void *work;                // complex [max_planes, n_u, n_v]
     double2 *phase_u, *phase_v;   // exp(-2 pi i h m / n) per axis
+    // complex64 grids whose sides are n1 * (a prime cuFFT has no radix for) -- 4915, 9830, ... from the reference's default
+    // fft_padding of 1.2: shared-memory Bluestein passes (fft_bluestein.cu) instead of cuFFT; [0] inverse, [1] forward
+    bool use_blu;
+    cngi::BluAxis blu_u[2], blu_v[2];
+    bool blu_ready[2];
 };
 
 namespace cngi {
@@ -130,17 +137,18 @@ template <typename T> __global__ void __launch_bounds__(256) fft_pre_kernel(PreP
     ((CT *)p.work)[((long long)pl * p.n_u + j0) * p.n_v + j1] = z;
 }
 
-template <typename T> __global__ void divide_by_centre_kernel(T *image, int n_l, int n_m, long long n_planes)
+template <typename T> __global__ void divide_by_centre_kernel(T *image, int n_l, int n_m, long long n_planes, int c_l, int c_m)
 {
     // each block handles one plane; the centre value is read before any thread overwrites it
     const long long pl = blockIdx.x;
     if (pl >= n_planes) return;
     T *img = image + pl * (long long)n_l * n_m;
     __shared__ double centre;
-    if (threadIdx.x == 0) centre = (double)img[(long long)(n_l / 2) * n_m + n_m / 2];
+    if (threadIdx.x == 0) centre = (double)img[(long long)c_l * n_m + c_m];
     __syncthreads();
     const double c = centre;
     __syncthreads();
+    if (c == 0.0 || !isfinite(c)) return;   // e.g. the centre was masked by pb_limit: leave the plane as it is
     for (long long i = threadIdx.x; i < (long long)n_l * n_m; i += blockDim.x) img[i] = (T)((double)img[i] / c);
 }
 
@@ -160,6 +168,22 @@ static int make_phase(double2 **dev, int64_t n)
     CNGI_CUDA_TRY(cudaMalloc((void **)dev, n * sizeof(double2)));
     CNGI_CUDA_TRY(cudaMemcpy(*dev, h.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
     return CNGI_OK;
+}
+
+// 2-D transform of nb planes with the shared-memory Bluestein kernel: rows (lines along v) src -> work, then columns
+// (lines along u) in place.  dir 0 = unnormalised inverse, 1 = forward.
+static int blu_transform(cngi_fft_plan *pl, int dir, const float2 *src, float2 *dst, int64_t nb, cudaStream_t st)
+{
+    if (!pl->blu_ready[dir]) {
+        int rc = blu_axis_create(&pl->blu_u[dir], pl->n_u, dir == 0 ? +1 : -1);
+        if (rc == CNGI_OK) rc = blu_axis_create(&pl->blu_v[dir], pl->n_v, dir == 0 ? +1 : -1);
+        if (rc != CNGI_OK) return rc;
+        pl->blu_ready[dir] = true;
+    }
+    const long long plane = (long long)pl->n_u * pl->n_v;
+    int rc = blu_lines(pl->blu_v[dir], src, dst, pl->n_v, 1, plane, pl->n_v, 1, plane, (int)pl->n_u, (int)nb, st);
+    if (rc != CNGI_OK) return rc;
+    return blu_lines(pl->blu_u[dir], dst, dst, 1, pl->n_v, plane, 1, pl->n_v, plane, (int)pl->n_v, (int)nb, st);
 }
 
 static int make_cufft(cufftHandle *h, int64_t n_u, int64_t n_v, int64_t batch, int32_t precision)
@@ -185,7 +209,10 @@ extern "C" int cngi_b200_fft_plan_create(cngi_fft_plan **out, int64_t n_u, int64
     cngi_fft_plan *pl = new cngi_fft_plan();
     pl->n_u = n_u, pl->n_v = n_v, pl->max_planes = max_planes, pl->precision = precision;
     pl->plan = 0, pl->plan_tail = 0, pl->tail_planes = 0, pl->work = nullptr, pl->phase_u = pl->phase_v = nullptr;
-    int rc = make_cufft(&pl->plan, n_u, n_v, max_planes, precision);
+    pl->blu_ready[0] = pl->blu_ready[1] = false;
+    const char *knob = getenv("CNGI_FFT_BLUESTEIN");   // "0": cuFFT for every size (A/B measurements, tests)
+    pl->use_blu = precision == CNGI_F32 && blu_supported(n_u) && blu_supported(n_v) && !(knob && knob[0] == '0');
+    int rc = pl->use_blu ? CNGI_OK : make_cufft(&pl->plan, n_u, n_v, max_planes, precision);
     if (rc == CNGI_OK) {
         const size_t cb = precision == CNGI_F32 ? 8 : 16;
         cudaError_t e = cudaMalloc(&pl->work, (size_t)max_planes * n_u * n_v * cb);
@@ -209,6 +236,10 @@ extern "C" int cngi_b200_fft_plan_destroy(cngi_fft_plan *pl)
     if (!pl) return CNGI_OK;
     if (pl->plan) cufftDestroy(pl->plan);
     if (pl->plan_tail) cufftDestroy(pl->plan_tail);
+    for (int d = 0; d < 2; ++d) {
+        cngi::blu_axis_destroy(&pl->blu_u[d]);
+        cngi::blu_axis_destroy(&pl->blu_v[d]);
+    }
     if (pl->work) cudaFree(pl->work);
     if (pl->phase_u) cudaFree(pl->phase_u);
     if (pl->phase_v) cudaFree(pl->phase_v);
@@ -234,41 +265,56 @@ extern "C" int cngi_b200_grid_to_image(cngi_fft_plan *pl, const cngi_grid_to_ima
 
     for (int64_t p0 = 0; p0 < a->n_planes; p0 += pl->max_planes) {
         const int64_t nb = std::min<int64_t>(pl->max_planes, a->n_planes - p0);
-        cufftHandle h = pl->plan;
-        if (nb != pl->max_planes) {
-            if (pl->tail_planes != nb) {
-                if (pl->plan_tail) cufftDestroy(pl->plan_tail);
-                pl->plan_tail = 0, pl->tail_planes = 0;
-                int rc = make_cufft(&pl->plan_tail, pl->n_u, pl->n_v, nb, pl->precision);
-                if (rc != CNGI_OK) return rc;
-                pl->tail_planes = nb;
+        if (pl->use_blu) {   // shared-memory Bluestein passes (complex64, sides n1 * prime)
+            const float2 *bsrc;
+            if (a->grid_is_complex) {
+                bsrc = (const float2 *)((const char *)a->grid + (size_t)p0 * plane_cells * cb);
+            } else {
+                const long long n = nb * plane_cells;
+                const unsigned blocks = (unsigned)std::min<long long>(ceil_div(n, 256), (long long)sm_count() * 16);
+                real_to_complex_kernel<float><<<blocks, 256, 0, st>>>((const float *)a->grid + (size_t)p0 * plane_cells, (float2 *)pl->work, n);
+                CNGI_CUDA_TRY(cudaGetLastError());
+                bsrc = (const float2 *)pl->work;
             }
-            h = pl->plan_tail;
-        }
-        if (cufftSetStream(h, st) != CUFFT_SUCCESS) {
-            set_error("cufftSetStream failed");
-            return CNGI_ERR_CUDA;
-        }
-        cufftResult r;
-        if (a->grid_is_complex) {
-            const char *src = (const char *)a->grid + (size_t)p0 * plane_cells * cb;
-            r = f32 ? cufftExecC2C(h, (cufftComplex *)src, (cufftComplex *)pl->work, CUFFT_INVERSE)
-                    : cufftExecZ2Z(h, (cufftDoubleComplex *)src, (cufftDoubleComplex *)pl->work, CUFFT_INVERSE);
+            int rc = blu_transform(pl, 0, bsrc, (float2 *)pl->work, nb, st);
+            if (rc != CNGI_OK) return rc;
         } else {
-            const char *src = (const char *)a->grid + (size_t)p0 * plane_cells * rb;
-            const long long n = nb * plane_cells;
-            const unsigned blocks = (unsigned)std::min<long long>(ceil_div(n, 256), (long long)sm_count() * 16);
-            if (f32)
-                real_to_complex_kernel<float><<<blocks, 256, 0, st>>>((const float *)src, (float2 *)pl->work, n);
-            else
-                real_to_complex_kernel<double><<<blocks, 256, 0, st>>>((const double *)src, (double2 *)pl->work, n);
-            CNGI_CUDA_TRY(cudaGetLastError());
-            r = f32 ? cufftExecC2C(h, (cufftComplex *)pl->work, (cufftComplex *)pl->work, CUFFT_INVERSE)
-                    : cufftExecZ2Z(h, (cufftDoubleComplex *)pl->work, (cufftDoubleComplex *)pl->work, CUFFT_INVERSE);
-        }
-        if (r != CUFFT_SUCCESS) {
-            set_error("cufftExec failed with %d", (int)r);
-            return CNGI_ERR_CUDA;
+            cufftHandle h = pl->plan;
+            if (nb != pl->max_planes) {
+                if (pl->tail_planes != nb) {
+                    if (pl->plan_tail) cufftDestroy(pl->plan_tail);
+                    pl->plan_tail = 0, pl->tail_planes = 0;
+                    int rc = make_cufft(&pl->plan_tail, pl->n_u, pl->n_v, nb, pl->precision);
+                    if (rc != CNGI_OK) return rc;
+                    pl->tail_planes = nb;
+                }
+                h = pl->plan_tail;
+            }
+            if (cufftSetStream(h, st) != CUFFT_SUCCESS) {
+                set_error("cufftSetStream failed");
+                return CNGI_ERR_CUDA;
+            }
+            cufftResult r;
+            if (a->grid_is_complex) {
+                const char *src = (const char *)a->grid + (size_t)p0 * plane_cells * cb;
+                r = f32 ? cufftExecC2C(h, (cufftComplex *)src, (cufftComplex *)pl->work, CUFFT_INVERSE)
+                        : cufftExecZ2Z(h, (cufftDoubleComplex *)src, (cufftDoubleComplex *)pl->work, CUFFT_INVERSE);
+            } else {
+                const char *src = (const char *)a->grid + (size_t)p0 * plane_cells * rb;
+                const long long n = nb * plane_cells;
+                const unsigned blocks = (unsigned)std::min<long long>(ceil_div(n, 256), (long long)sm_count() * 16);
+                if (f32)
+                    real_to_complex_kernel<float><<<blocks, 256, 0, st>>>((const float *)src, (float2 *)pl->work, n);
+                else
+                    real_to_complex_kernel<double><<<blocks, 256, 0, st>>>((const double *)src, (double2 *)pl->work, n);
+                CNGI_CUDA_TRY(cudaGetLastError());
+                r = f32 ? cufftExecC2C(h, (cufftComplex *)pl->work, (cufftComplex *)pl->work, CUFFT_INVERSE)
+                        : cufftExecZ2Z(h, (cufftDoubleComplex *)pl->work, (cufftDoubleComplex *)pl->work, CUFFT_INVERSE);
+            }
+            if (r != CUFFT_SUCCESS) {
+                set_error("cufftExec failed with %d", (int)r);
+                return CNGI_ERR_CUDA;
+            }
         }
         PostParams pp{};
         pp.spec = pl->work, pp.image = a->image, pp.phase_u = pl->phase_u, pp.phase_v = pl->phase_v;
@@ -287,12 +333,16 @@ extern "C" int cngi_b200_grid_to_image(cngi_fft_plan *pl, const cngi_grid_to_ima
         CNGI_CUDA_TRY(cudaGetLastError());
     }
     if (a->divide_by_centre) {
+        const int c_l = a->divide_by_centre == 2 ? (int)a->centre_pixel[0] : (int)(a->image_size[0] / 2);
+        const int c_m = a->divide_by_centre == 2 ? (int)a->centre_pixel[1] : (int)(a->image_size[1] / 2);
+        CNGI_REQUIRE(c_l >= 0 && c_l < a->image_size[0] && c_m >= 0 && c_m < a->image_size[1],
+                     "grid_to_image: centre pixel (%d, %d) is outside the image", c_l, c_m);
         if (f32)
             divide_by_centre_kernel<float><<<(unsigned)a->n_planes, 256, 0, st>>>((float *)a->image, (int)a->image_size[0],
-                                                                                 (int)a->image_size[1], a->n_planes);
+                                                                                 (int)a->image_size[1], a->n_planes, c_l, c_m);
         else
             divide_by_centre_kernel<double><<<(unsigned)a->n_planes, 256, 0, st>>>((double *)a->image, (int)a->image_size[0],
-                                                                                  (int)a->image_size[1], a->n_planes);
+                                                                                  (int)a->image_size[1], a->n_planes, c_l, c_m);
         CNGI_CUDA_TRY(cudaGetLastError());
     }
     return CNGI_OK;
@@ -317,19 +367,21 @@ extern "C" int cngi_b200_image_to_grid(cngi_fft_plan *pl, const cngi_image_to_gr
         const int64_t nb = std::min<int64_t>(pl->max_planes, a->n_planes - p0);
         CNGI_REQUIRE(nb < 65536, "image_to_grid: too many planes per batch");
         cufftHandle h = pl->plan;
-        if (nb != pl->max_planes) {
-            if (pl->tail_planes != nb) {
-                if (pl->plan_tail) cufftDestroy(pl->plan_tail);
-                pl->plan_tail = 0, pl->tail_planes = 0;
-                int rc = make_cufft(&pl->plan_tail, pl->n_u, pl->n_v, nb, pl->precision);
-                if (rc != CNGI_OK) return rc;
-                pl->tail_planes = nb;
+        if (!pl->use_blu) {
+            if (nb != pl->max_planes) {
+                if (pl->tail_planes != nb) {
+                    if (pl->plan_tail) cufftDestroy(pl->plan_tail);
+                    pl->plan_tail = 0, pl->tail_planes = 0;
+                    int rc = make_cufft(&pl->plan_tail, pl->n_u, pl->n_v, nb, pl->precision);
+                    if (rc != CNGI_OK) return rc;
+                    pl->tail_planes = nb;
+                }
+                h = pl->plan_tail;
             }
-            h = pl->plan_tail;
-        }
-        if (cufftSetStream(h, st) != CUFFT_SUCCESS) {
-            set_error("cufftSetStream failed");
-            return CNGI_ERR_CUDA;
+            if (cufftSetStream(h, st) != CUFFT_SUCCESS) {
+                set_error("cufftSetStream failed");
+                return CNGI_ERR_CUDA;
+            }
         }
         PreParams pp{};
         pp.image = (const char *)a->image + (size_t)p0 * plane_pix * rb;
@@ -343,6 +395,11 @@ extern "C" int cngi_b200_image_to_grid(cngi_fft_plan *pl, const cngi_image_to_gr
             fft_pre_kernel<double><<<grid, 256, 0, st>>>(pp);
         CNGI_CUDA_TRY(cudaGetLastError());
         char *dst = (char *)a->grid + (size_t)p0 * plane_cells * cb;
+        if (pl->use_blu) {
+            int rc = blu_transform(pl, 1, (const float2 *)pl->work, (float2 *)dst, nb, st);
+            if (rc != CNGI_OK) return rc;
+            continue;
+        }
         cufftResult r = f32 ? cufftExecC2C(h, (cufftComplex *)pl->work, (cufftComplex *)dst, CUFFT_FORWARD)
                             : cufftExecZ2Z(h, (cufftDoubleComplex *)pl->work, (cufftDoubleComplex *)dst, CUFFT_FORWARD);
         if (r != CUFFT_SUCCESS) {

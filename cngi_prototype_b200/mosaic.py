@@ -115,6 +115,7 @@ def _normalized(grid, sw, gp, gcf_dataset, img_dataset, norm_parms, divide_by_ce
     return grid_to_image(grid, gp["image_size"], sum_weight=sw, corr_u=_sinc_1d(n_l, int(osamp[0])),
                          corr_v=_sinc_1d(n_m, int(osamp[1])), norm_image=norm, pb_image=pb if use_limit else None,
                          pb_limit=float(_np["pb_limit"]) if use_limit else 0.0, divide_by_centre=divide_by_centre,
+                         centre_pixel=gp.get("image_center"),
                          single_precision_roundtrip=_np["single_precision"])
 
 

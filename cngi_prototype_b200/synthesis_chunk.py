@@ -66,17 +66,24 @@ def _make_pb(n_pol, freq_chan, pb_parms, grid_parms):
 
 
 def synthesis_imaging_chunk(vis_data, uvw, data_weight, flag, freq_chan, grid_parms, imaging_weights_parms, fused=True,
-                            pb_parms=None):
+                            pb_parms=None, grid_with="imaging_weight"):
     """Weights -> [PB] -> PSF -> image for one channel chunk (the shape of _synthesis_imaging_cube_std_chunk :171-220
     without the beam fit, which is image analysis).  Returns image, image_sum_weight, psf, psf_sum_weight
     (images API-side (l, m, chan, pol)), plus pb (l, m, chan, pol, dish) when pb_parms is given."""
+    assert grid_with in ("imaging_weight", "data_weight"), grid_with
     if pb_parms is not None:
-        out = synthesis_imaging_chunk(vis_data, uvw, data_weight, flag, freq_chan, grid_parms, imaging_weights_parms, fused)
+        out = synthesis_imaging_chunk(vis_data, uvw, data_weight, flag, freq_chan, grid_parms, imaging_weights_parms, fused,
+                                      grid_with=grid_with)
         return out + (_make_pb(int(data_weight.shape[3]), freq_chan, pb_parms, grid_parms),)
     gp = dict(grid_parms)
     gp["oversampling"], gp["support"] = 100, 7
     cgk_1D = _create_prolate_spheroidal_kernel_1D(100, 7)
     w = _make_imaging_weight_chunk(uvw, data_weight, freq_chan, gp, imaging_weights_parms)
+    if grid_with == "data_weight":
+        # the reference's chunk function computes the imaging weights and then grids psf and image with data_weight
+        # (synthesis_imaging_cube.py:183,206,210): this switch reproduces its output exactly; the default uses the weights
+        # it computed (what make_imaging_weight + make_psf / make_image do) -- see INTEGRATION.md
+        w = data_weight
     if fused:   # one pass over uvw / weights / vis for both grids (cngi_b200_standard_grid_image_psf)
         grid, img_sw, psf_grid, psf_sw = standard_grid_image_psf(vis_data, uvw, w, freq_chan, cgk_1D, gp, flag=flag)
         return _finish(grid, img_sw, gp, True), img_sw, _finish(psf_grid, psf_sw, gp, True), psf_sw

@@ -276,9 +276,12 @@ typedef struct cngi_grid_to_image_args {
     const void *pb_image;       /* optional real [n_planes or 1, l, m]: pixels with pb < pb_limit -> 0 */
     int64_t pb_image_planes;
     double pb_limit;
-    int32_t divide_by_centre;   /* make_psf_with_gcf.py:140: divide plane by its centre pixel          */
+    int32_t divide_by_centre;   /* make_psf_with_gcf.py:140: divide plane by its centre pixel; 1 = pixel (l/2, m/2),
+                                   2 = pixel centre_pixel[] (grid_parms['image_center']); a plane whose centre value is
+                                   0 or not finite is left undivided (the reference would fill it with inf / NaN)       */
     int32_t single_precision_roundtrip; /* _normalize.py:86-87                                        */
     void *image;                /* real out [n_planes, l, m] (kernel-side plane order)                */
+    int64_t centre_pixel[2];    /* used when divide_by_centre == 2                                      */
 } cngi_grid_to_image_args;
 
 int cngi_b200_grid_to_image(cngi_fft_plan *plan, const cngi_grid_to_image_args *args, void *stream);

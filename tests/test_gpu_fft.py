@@ -151,3 +151,43 @@ def test_predict_modelvis_image(oracle):
         analytic += amp * np.exp(-2j * np.pi * (up * (i - n // 2) + vp * (j - n // 2)) / n_pad)
     ok = v[..., 0] != 0
     assert ok.mean() > 0.9 and np.abs(v[..., 0][ok] - analytic[ok]).max() < 1e-2
+
+
+@pytest.mark.parametrize("n_pad,n_img", [((1228, 1228), (1024, 1024)),     # 4 * 307: what fft_padding 1.2 makes of 1024
+                                         ((614, 921), (512, 700)),         # 2 * 307 x 3 * 307 (generic n1)
+                                         ((983, 1535), (800, 1279)),       # n1 = 1 x 5 * 307
+                                         ((4915, 1228), (4096, 1024)),     # 5 * 983: 4096 padded
+                                         ((1966, 6140), (1638, 5000))])    # 2 * 983 x 20 * 307
+def test_shared_memory_bluestein_sizes_match_numpy_and_cufft(fft, oracle, n_pad, n_img, monkeypatch):
+    """Sides n1 * prime (127 < prime <= 1021, n1 <= 32) of complex64 grids take the shared-memory Bluestein passes
+    (csrc/fft_bluestein.cu) instead of cuFFT: same image as numpy.fft and as cuFFT (CNGI_FFT_BLUESTEIN=0) to fp32
+    rounding, both directions, complex and real (psf) grids."""
+    import torch
+    rng = np.random.default_rng(n_pad[0] + n_pad[1])
+    g = (rng.standard_normal((2,) + tuple(n_pad)) + 1j * rng.standard_normal((2,) + tuple(n_pad))).astype(np.complex64)
+    g = g.reshape((1, 2) + tuple(n_pad))
+    g[0, 1, n_pad[0] // 2, n_pad[1] // 2] += 50.0                 # a bright centre cell: a smooth pedestal under the noise
+    ref = oracle.grid_to_uncorrected_image(g.astype(np.complex128), np.array(n_img))
+    gt = torch.as_tensor(g).cuda()
+    fft._plans.clear()
+    img = fft.grid_to_image(gt, n_img).cpu().numpy()
+    assert rel_err(img, ref) <= 2e-6
+    gr = torch.as_tensor(np.ascontiguousarray(g.real)).cuda()
+    img_r = fft.grid_to_image(gr, n_img).cpu().numpy()
+    ref_r = oracle.grid_to_uncorrected_image(g.real.astype(np.float64), np.array(n_img))
+    assert rel_err(img_r, ref_r) <= 2e-6
+    # forward: image -> grid (config 4's first step) and back
+    model = torch.as_tensor(rng.standard_normal(tuple(n_img) + (1, 2)).astype(np.float32)).cuda()
+    grid_b = fft.image_to_grid(model, n_pad).cpu().numpy()
+    monkeypatch.setenv("CNGI_FFT_BLUESTEIN", "0")
+    fft._plans.clear()
+    img_c = fft.grid_to_image(gt, n_img).cpu().numpy()
+    grid_c = fft.image_to_grid(model, n_pad).cpu().numpy()
+    fft._plans.clear()
+    assert rel_err(img, img_c) <= 2e-6 and rel_err(img_c, ref) <= 2e-6
+    assert rel_err(grid_b, grid_c) <= 2e-6
+    padded = np.zeros(tuple(n_pad))
+    s0, s1 = n_pad[0] // 2 - n_img[0] // 2, n_pad[1] // 2 - n_img[1] // 2
+    padded[s0:s0 + n_img[0], s1:s1 + n_img[1]] = model[:, :, 0, 1].cpu().numpy()
+    ref_g = np.fft.fftshift(np.fft.fft2(np.fft.ifftshift(padded)))
+    assert rel_err(grid_b[0, 1], ref_g) <= 2e-6
