@@ -1,4 +1,4 @@
-// fft_bluestein.cu -- complex64 FFTs of length n = n1 * P (P a prime in (127, 1021], n1 <= 32) done per line in SHARED MEMORY.
+// fft_bluestein.cu -- complex64 FFTs of length n = n1 * P (P a prime in (512, 1021], n1 <= 32) done per line in SHARED MEMORY.
 //
 // Why: the reference pads the uv-grid to int(1.2 * image_size) (_check_imaging_parms.py:36) -- for the power-of-two images
 // people make that is 1228 = 4 * 307, 4915 = 5 * 983, 9830 = 10 * 983 (BASELINE config 5), 19660 = 20 * 983.  cuFFT has no
@@ -24,9 +24,11 @@ namespace {
 
 constexpr int BM = 2048;                      // convolution length (>= 2 P - 1)
 constexpr int BT = 256;                       // threads per block
-constexpr int YLEN = BM + (BM >> 5) * 4;      // re / im planes of the work buffer, skewed by 4 floats per 32 elements
+constexpr int YLEN = BM + (BM >> 5) * 4;      // complex work buffer, skewed by 4 elements per 32
 
-__device__ __forceinline__ int skew(int e) { return e + ((e >> 5) << 2); }   // makes the stride-4 stage bank-conflict free
+// 64-bit shared-memory accesses are served per half warp: the skew makes the 16 elements a half warp touches in the
+// stride-4 stage (4 blocks of 32 x 4 offsets) fall into 16 different 8-byte bank pairs
+__device__ __forceinline__ int skew(int e) { return e + ((e >> 5) << 2); }
 
 __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -88,6 +90,7 @@ struct BluParams {
     float2 *dst;
     long long src_line, src_elem, src_plane, dst_line, dst_elem, dst_plane;   // element strides
     int n_lines, n1, P;
+    int line0, line_mod;       // line handled by block i is (line0 + i) mod line_mod: a cyclic window of lines
     const float2 *tw_n;        // [n]   exp(s 2 pi i j / n)
     const float2 *w_n1;        // [n1]  exp(s 2 pi i j / n1)
     const float2 *chirp;       // [P]   exp(s i pi j^2 / P)
@@ -99,14 +102,11 @@ struct BluParams {
 // One radix-8 stage of the 2048-point network on the skewed re / im planes.  DIF (forward): butterfly, then twiddle;
 // DIT (backward): twiddle, then butterfly.  `first` = element index of leg 0, `sub` = distance between legs, j1 = index of
 // W^{offset} in the W_M table.
-template <bool DIT> __device__ __forceinline__ void radix8_stage(float *yre, float *yim, const float2 *wm, int first, int sub, int j1)
+template <bool DIT> __device__ __forceinline__ void radix8_stage(float2 *y, const float2 *wm, int first, int sub, int j1)
 {
     float2 a[8], w[8];
 #pragma unroll
-    for (int l = 0; l < 8; ++l) {
-        const int e = skew(first + sub * l);
-        a[l] = make_float2(yre[e], yim[e]);
-    }
+    for (int l = 0; l < 8; ++l) a[l] = y[skew(first + sub * l)];
     twiddles<DIT>(wm, j1, w);
     if (DIT) {
 #pragma unroll
@@ -118,10 +118,7 @@ template <bool DIT> __device__ __forceinline__ void radix8_stage(float *yre, flo
         for (int q = 1; q < 8; ++q) a[q] = cmul(a[q], w[q]);
     }
 #pragma unroll
-    for (int l = 0; l < 8; ++l) {
-        const int e = skew(first + sub * l);
-        yre[e] = a[l].x, yim[e] = a[l].y;
-    }
+    for (int l = 0; l < 8; ++l) y[skew(first + sub * l)] = a[l];
 }
 
 // N1 > 0: compile-time n1 (the n1-point DFTs keep a column in registers); N1 == 0: any n1 <= 32 (re-reads shared memory)
@@ -130,12 +127,15 @@ template <int N1> __global__ void __launch_bounds__(BT, 2) bluestein_lines_kerne
     extern __shared__ __align__(16) unsigned char blu_smem[];
     const int n1 = N1 > 0 ? N1 : p.n1, P = p.P, n = n1 * P, t = threadIdx.x;
     float2 *X = reinterpret_cast<float2 *>(blu_smem);              // the line: x[n1' * P + n2]
-    float *yre = reinterpret_cast<float *>(X + ((n + 1) & ~1));     // convolution buffer, 16-byte aligned
-    float *yim = yre + YLEN;
-    const float2 *__restrict__ src = p.src + (long long)blockIdx.y * p.src_plane + (long long)blockIdx.x * p.src_line;
-    float2 *__restrict__ dst = p.dst + (long long)blockIdx.y * p.dst_plane + (long long)blockIdx.x * p.dst_line;
+    float2 *y = X + ((n + 1) & ~1);                                 // convolution buffer, 16-byte aligned
+    int line = p.line0 + (int)blockIdx.x;
+    if (line >= p.line_mod) line -= p.line_mod;
+    const float2 *__restrict__ src = p.src + (long long)blockIdx.y * p.src_plane + (long long)line * p.src_line;
+    float2 *dst = p.dst +   // (may alias src: the column pass runs in place; every read of the line precedes its writes)
+        (long long)blockIdx.y * p.dst_plane + (long long)line * p.dst_line;
 
-    for (int j = t; j < n; j += BT) X[j] = src[(long long)j * p.src_elem];
+#pragma unroll 8
+    for (int j = t; j < n; j += BT) X[j] = __ldg(src + (long long)j * p.src_elem);
     __syncthreads();
 
     // ---- n1-point DFTs down the columns of the (n1, P) view + twiddles: A[k1][n2] = W_n^{n2 k1} sum_l x[l P + n2] W_n1^{l k1}
@@ -182,43 +182,37 @@ template <int N1> __global__ void __launch_bounds__(BT, 2) bluestein_lines_kerne
 #pragma unroll
             for (int q = 1; q < 8; ++q) a[q] = cmul(a[q], w[q]);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int e = skew(t + 256 * q);
-                yre[e] = a[q].x, yim[e] = a[q].y;
-            }
+            for (int q = 0; q < 8; ++q) y[skew(t + 256 * q)] = a[q];
         }
         __syncthreads();
-        radix8_stage<false>(yre, yim, p.w_m, (t >> 5) * 256 + (t & 31), 32, 8 * (t & 31));     // span 256
+        radix8_stage<false>(y, p.w_m, (t >> 5) * 256 + (t & 31), 32, 8 * (t & 31));     // span 256
         __syncthreads();
-        radix8_stage<false>(yre, yim, p.w_m, (t >> 2) * 32 + (t & 3), 4, 64 * (t & 3));         // span 32
+        radix8_stage<false>(y, p.w_m, (t >> 2) * 32 + (t & 3), 4, 64 * (t & 3));         // span 32
         __syncthreads();
         // forward span 4, times the filter spectrum, backward span 4: four consecutive elements, registers only
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int g = t + 256 * h, e = skew(4 * g);   // 4 g .. 4 g + 3 never straddle a skew boundary
-            float4 re = *reinterpret_cast<float4 *>(yre + e), im = *reinterpret_cast<float4 *>(yim + e);
-            float2 a0 = make_float2(re.x, im.x), a1 = make_float2(re.y, im.y), a2 = make_float2(re.z, im.z), a3 = make_float2(re.w, im.w);
+            const float4 v01 = *reinterpret_cast<float4 *>(y + e), v23 = *reinterpret_cast<float4 *>(y + e + 2);
+            float2 a0 = make_float2(v01.x, v01.y), a1 = make_float2(v01.z, v01.w), a2 = make_float2(v23.x, v23.y), a3 = make_float2(v23.z, v23.w);
             dft4<-1>(a0, a1, a2, a3);
             const float4 f01 = __ldg(reinterpret_cast<const float4 *>(p.bf + 4 * g));
             const float4 f23 = __ldg(reinterpret_cast<const float4 *>(p.bf + 4 * g + 2));
             a0 = cmul(a0, make_float2(f01.x, f01.y)), a1 = cmul(a1, make_float2(f01.z, f01.w));
             a2 = cmul(a2, make_float2(f23.x, f23.y)), a3 = cmul(a3, make_float2(f23.z, f23.w));
             dft4<+1>(a0, a1, a2, a3);
-            *reinterpret_cast<float4 *>(yre + e) = make_float4(a0.x, a1.x, a2.x, a3.x);
-            *reinterpret_cast<float4 *>(yim + e) = make_float4(a0.y, a1.y, a2.y, a3.y);
+            *reinterpret_cast<float4 *>(y + e) = make_float4(a0.x, a0.y, a1.x, a1.y);
+            *reinterpret_cast<float4 *>(y + e + 2) = make_float4(a2.x, a2.y, a3.x, a3.y);
         }
         __syncthreads();
-        radix8_stage<true>(yre, yim, p.w_m, (t >> 2) * 32 + (t & 3), 4, 64 * (t & 3));          // span 32
+        radix8_stage<true>(y, p.w_m, (t >> 2) * 32 + (t & 3), 4, 64 * (t & 3));          // span 32
         __syncthreads();
-        radix8_stage<true>(yre, yim, p.w_m, (t >> 5) * 256 + (t & 31), 32, 8 * (t & 31));      // span 256
+        radix8_stage<true>(y, p.w_m, (t >> 5) * 256 + (t & 31), 32, 8 * (t & 31));      // span 256
         __syncthreads();
         {   // backward span 2048 fused with the output chirp; only k2 < P (<= 1024: legs 0..3) is kept, into the dead segment
             float2 a[8], w[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int e = skew(t + 256 * q);
-                a[q] = make_float2(yre[e], yim[e]);
-            }
+            for (int q = 0; q < 8; ++q) a[q] = y[skew(t + 256 * q)];
             twiddles<true>(p.w_m, t, w);
 #pragma unroll
             for (int q = 1; q < 8; ++q) a[q] = cmul(a[q], w[q]);
@@ -272,7 +266,7 @@ bool blu_supported(int64_t n, int *n1_out, int *p_out)
     for (int n1 = 1; n1 <= 32; ++n1) {
         if (n % n1) continue;
         const int64_t P = n / n1;
-        if (P <= 127 || P > 1021) continue;
+        if (P <= 512 || P > 1021) continue;   // the 2048-point convolution is the right size for 512 < P <= 1021 only
         bool prime = true;
         for (int64_t d = 2; d * d <= P; ++d)
             if (P % d == 0) { prime = false; break; }
@@ -331,7 +325,8 @@ void blu_axis_destroy(BluAxis *ax)
 }
 
 int blu_lines(const BluAxis &ax, const float2 *src, float2 *dst, long long src_line, long long src_elem, long long src_plane,
-              long long dst_line, long long dst_elem, long long dst_plane, int n_lines, int n_planes, cudaStream_t st)
+              long long dst_line, long long dst_elem, long long dst_plane, int n_lines, int n_planes, cudaStream_t st,
+              int line0, int line_mod)
 {
     if (n_lines <= 0 || n_planes <= 0) return CNGI_OK;
     BluParams p{};
@@ -339,8 +334,9 @@ int blu_lines(const BluAxis &ax, const float2 *src, float2 *dst, long long src_l
     p.src_line = src_line, p.src_elem = src_elem, p.src_plane = src_plane;
     p.dst_line = dst_line, p.dst_elem = dst_elem, p.dst_plane = dst_plane;
     p.n_lines = n_lines, p.n1 = ax.n1, p.P = ax.P;
+    p.line0 = line0, p.line_mod = line_mod > 0 ? line_mod : n_lines;
     p.tw_n = ax.tw_n, p.w_n1 = ax.w_n1, p.chirp = ax.chirp, p.chirp_out = ax.chirp_out, p.bf = ax.bf, p.w_m = ax.w_m;
-    const size_t smem = (size_t)((ax.n + 1) & ~1) * sizeof(float2) + 2 * YLEN * sizeof(float);
+    const size_t smem = (size_t)((ax.n + 1) & ~1) * sizeof(float2) + YLEN * sizeof(float2);
     CNGI_REQUIRE(smem <= 227 * 1024, "fft: line of %d complex64 does not fit shared memory", ax.n);
     CNGI_REQUIRE(n_planes < 65536, "fft: too many planes per batch");
     const dim3 grid((unsigned)n_lines, (unsigned)n_planes);

@@ -172,7 +172,10 @@ static int make_phase(double2 **dev, int64_t n)
 
 // 2-D transform of nb planes with the shared-memory Bluestein kernel: rows (lines along v) src -> work, then columns
 // (lines along u) in place.  dir 0 = unnormalised inverse, 1 = forward.
-static int blu_transform(cngi_fft_plan *pl, int dir, const float2 *src, float2 *dst, int64_t nb, cudaStream_t st)
+// keep_v0 / keep_vn: the second pass is only needed for the v bins the caller will read -- the cyclic window
+// [keep_v0, keep_v0 + keep_vn) mod n_v (grid_to_image: the cropped image columns); keep_vn <= 0: every bin.
+static int blu_transform(cngi_fft_plan *pl, int dir, const float2 *src, float2 *dst, int64_t nb, cudaStream_t st,
+                         int keep_v0 = 0, int keep_vn = 0)
 {
     if (!pl->blu_ready[dir]) {
         int rc = blu_axis_create(&pl->blu_u[dir], pl->n_u, dir == 0 ? +1 : -1);
@@ -183,7 +186,8 @@ static int blu_transform(cngi_fft_plan *pl, int dir, const float2 *src, float2 *
     const long long plane = (long long)pl->n_u * pl->n_v;
     int rc = blu_lines(pl->blu_v[dir], src, dst, pl->n_v, 1, plane, pl->n_v, 1, plane, (int)pl->n_u, (int)nb, st);
     if (rc != CNGI_OK) return rc;
-    return blu_lines(pl->blu_u[dir], dst, dst, 1, pl->n_v, plane, 1, pl->n_v, plane, (int)pl->n_v, (int)nb, st);
+    if (keep_vn <= 0 || keep_vn >= pl->n_v) keep_v0 = 0, keep_vn = (int)pl->n_v;
+    return blu_lines(pl->blu_u[dir], dst, dst, 1, pl->n_v, plane, 1, pl->n_v, plane, keep_vn, (int)nb, st, keep_v0, (int)pl->n_v);
 }
 
 static int make_cufft(cufftHandle *h, int64_t n_u, int64_t n_v, int64_t batch, int32_t precision)
@@ -276,7 +280,10 @@ extern "C" int cngi_b200_grid_to_image(cngi_fft_plan *pl, const cngi_grid_to_ima
                 CNGI_CUDA_TRY(cudaGetLastError());
                 bsrc = (const float2 *)pl->work;
             }
-            int rc = blu_transform(pl, 0, bsrc, (float2 *)pl->work, nb, st);
+            // image column m is DFT bin (start_v + m - n_v / 2) mod n_v: the other bins are never read by the post pass
+            const int start_v = (int)(a->n_v / 2 - a->image_size[1] / 2);
+            const int v0 = (int)(((start_v - a->n_v / 2) % a->n_v + a->n_v) % a->n_v);
+            int rc = blu_transform(pl, 0, bsrc, (float2 *)pl->work, nb, st, v0, (int)a->image_size[1]);
             if (rc != CNGI_OK) return rc;
         } else {
             cufftHandle h = pl->plan;

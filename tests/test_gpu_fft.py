@@ -153,13 +153,13 @@ def test_predict_modelvis_image(oracle):
     assert ok.mean() > 0.9 and np.abs(v[..., 0][ok] - analytic[ok]).max() < 1e-2
 
 
-@pytest.mark.parametrize("n_pad,n_img", [((1228, 1228), (1024, 1024)),     # 4 * 307: what fft_padding 1.2 makes of 1024
-                                         ((614, 921), (512, 700)),         # 2 * 307 x 3 * 307 (generic n1)
-                                         ((983, 1535), (800, 1279)),       # n1 = 1 x 5 * 307
-                                         ((4915, 1228), (4096, 1024)),     # 5 * 983: 4096 padded
-                                         ((1966, 6140), (1638, 5000))])    # 2 * 983 x 20 * 307
+@pytest.mark.parametrize("n_pad,n_img", [((1774, 1774), (1500, 1400)),     # 2 * 887
+                                         ((1563, 2084), (1300, 1700)),     # 3 * 521 (generic n1) x 4 * 521
+                                         ((983, 2615), (800, 2179)),       # n1 = 1 x 5 * 523
+                                         ((4915, 1046), (4096, 871)),      # 5 * 983: 4096 padded by 1.2
+                                         ((1966, 10460), (1638, 8716))])   # 2 * 983 x 20 * 523
 def test_shared_memory_bluestein_sizes_match_numpy_and_cufft(fft, oracle, n_pad, n_img, monkeypatch):
-    """Sides n1 * prime (127 < prime <= 1021, n1 <= 32) of complex64 grids take the shared-memory Bluestein passes
+    """Sides n1 * prime (512 < prime <= 1021, n1 <= 32) of complex64 grids take the shared-memory Bluestein passes
     (csrc/fft_bluestein.cu) instead of cuFFT: same image as numpy.fft and as cuFFT (CNGI_FFT_BLUESTEIN=0) to fp32
     rounding, both directions, complex and real (psf) grids."""
     import torch
