@@ -280,15 +280,47 @@ template <typename T, int W, int PP> struct ApTrackCfg {
     static constexpr int RAW = OFF_WD + PP * 2 * (int)sizeof(T);
     static constexpr int R16 = (RAW + 15) / 16;
     static constexpr int REC_BYTES = 16 * (R16 % 2 == 0 ? R16 + 1 : R16);   // 16 * odd: conflict-free 128-bit stores
-    static constexpr int WARP_BYTES = 32 * REC_BYTES;
+    // tap-block ring: the W x W taps of a sample are ONE contiguous block of the tap table (2 KB for W = 16, fp32); the block
+    // of the sample DEPTH steps ahead is fetched with cp.async.bulk (one instruction by one lane, completion on an mbarrier)
+    // while the lanes multiply-accumulate the current one out of shared memory
+    static constexpr int DEPTH = sizeof(T) == 4 ? 4 : 2;
+    static constexpr int BLK_BYTES = W * W * 2 * (int)sizeof(T);
+    static constexpr int RING_BYTES = DEPTH * IPW * BLK_BYTES;
+    static constexpr int BAR_BYTES = DEPTH * IPW * 8;
+    static constexpr int REC_TOTAL = 32 * REC_BYTES;
+    static constexpr int WARP_BYTES = REC_TOTAL + RING_BYTES + BAR_BYTES;   // REC_TOTAL is a multiple of 16
 };
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    // arm the barrier with the byte count, then one bulk copy global -> shared that completes on it (UBLKCP)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
 
 // blocks per SM the fp32 16 x 16 instantiation is compiled for: 3 = 168 registers, no spills (2.87 ms on C3);
 // 4 = 128 registers with 36 B of spills inside the tap loop measured 5.31 ms
 #ifndef CNGI_AP_MINB_F32
 #define CNGI_AP_MINB_F32 3
 #endif
-template <typename T, int W, int PP>
+// BULK: taps come from the shared-memory ring filled by cp.async.bulk (see ApTrackCfg) instead of 16 L2 loads per sample
+template <typename T, int W, int PP, bool BULK>
 __global__ void __launch_bounds__(128, (sizeof(T) == 4 && W == 16) ? CNGI_AP_MINB_F32 : 1) aperture_track_kernel(ApParams p)
 {
     using Cfg = ApTrackCfg<T, W, PP>;
@@ -299,7 +331,15 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && W == 16) ? CNGI_AP_MIN
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (task >= p.n_tasks) return;
-    unsigned char *wbuf = smem + warp * Cfg::WARP_BYTES;
+    unsigned char *wbuf = smem + warp * (BULK ? Cfg::WARP_BYTES : Cfg::REC_TOTAL);
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(wbuf + Cfg::REC_TOTAL);
+    const unsigned bar_s = ring_s + Cfg::RING_BYTES;
+    if constexpr (BULK) {
+        if (lane < Cfg::DEPTH * IPW) mbar_init(bar_s + lane * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
+    unsigned ring_parity = 0;   // BULK: bit `slot` = parity to wait for on this item's barrier of that slot
     const int S = p.smax, shalf = p.smax / 2;
     const int n_cf = p.n_cfb * p.n_cfc * p.n_cfp;
 
@@ -434,11 +474,25 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && W == 16) ? CNGI_AP_MIN
         }
         __syncwarp();
         // ---- phase 2 ----
+        auto prefetch = [&](int i) {   // the item's first lane fetches the tap block of step i into ring slot i mod DEPTH
+            if (r2 == 0) {
+                const int4 nx = *reinterpret_cast<const int4 *>(wbuf + (i * IPW + k2) * Cfg::REC_BYTES);
+                if (nx.x != -1) {
+                    const int slot = (i & (Cfg::DEPTH - 1)) * IPW + k2;
+                    bulk_load(ring_s + slot * Cfg::BLK_BYTES, (const CT *)p.taps + (long long)nx.z * (W * W), Cfg::BLK_BYTES,
+                              bar_s + slot * 8);
+                }
+            }
+        };
+        if constexpr (BULK) {
+#pragma unroll
+            for (int i = 0; i < Cfg::DEPTH; ++i) prefetch(i);
+        }
 #pragma unroll 1
         for (int i = 0; i < ITER; ++i) {
             const unsigned char *rec = wbuf + (i * IPW + k2) * Cfg::REC_BYTES;
             const int4 idx = *reinterpret_cast<const int4 *>(rec);
-            if (idx.x == -1) continue;
+            if (idx.x != -1) {
             CT wd[PP];
 #pragma unroll
             for (int ip = 0; ip < PP; ++ip) wd[ip] = reinterpret_cast<const CT *>(rec + Cfg::OFF_WD)[ip];
@@ -481,6 +535,27 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && W == 16) ? CNGI_AP_MIN
                 d0[ip] = wd[ip];
                 d1[ip].x = -wd[ip].y, d1[ip].y = wd[ip].x;
             }
+            if constexpr (BULK) {
+                const int slot = (i & (Cfg::DEPTH - 1)) * IPW + k2;
+                mbar_wait(bar_s + slot * 8, (ring_parity >> (i & (Cfg::DEPTH - 1))) & 1u);
+                ring_parity ^= 1u << (i & (Cfg::DEPTH - 1));
+                const unsigned ts = ring_s + slot * Cfg::BLK_BYTES + ((r2 - bv) & (W - 1)) * (int)sizeof(CT);
+#pragma unroll
+                for (int sl = 0; sl < W; ++sl) {
+                    const int row = ((sl - bu) & (W - 1)) * W;
+                    CT tap;
+                    if constexpr (sizeof(T) == 4)
+                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(tap.x), "=f"(tap.y) : "r"(ts + row * (int)sizeof(CT)));
+                    else
+                        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(tap.x), "=d"(tap.y) : "r"(ts + row * (int)sizeof(CT)));
+#pragma unroll
+                    for (int ip = 0; ip < PP; ++ip) {
+                        if (ip > 0 && !same_cf) tap = tp1[row];   // a second convolution function for this pol: from L2
+                        pair_fma(acc[sl][ip], d0[ip], tap.x);
+                        pair_fma(acc[sl][ip], d1[ip], tap.y);
+                    }
+                }
+            } else {
 #pragma unroll
             for (int sl = 0; sl < W; ++sl) {
                 const int row = ((sl - bu) & (W - 1)) * W;
@@ -491,6 +566,12 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && W == 16) ? CNGI_AP_MIN
                     pair_fma(acc[sl][ip], d0[ip], tap.x);
                     pair_fma(acc[sl][ip], d1[ip], tap.y);
                 }
+            }
+            }
+            }
+            if constexpr (BULK) {
+                __syncwarp();   // every lane has finished reading this step's ring slot: it may be refilled
+                if (i + Cfg::DEPTH < ITER) prefetch(i + Cfg::DEPTH);
             }
         }
         __syncwarp();
@@ -662,8 +743,20 @@ template <typename T, int W, int PP> static int launch_aperture_track(ApParams p
         set_error("aperture_grid: too many work items for one launch");
         return CNGI_ERR_INVALID;
     }
-    aperture_track_kernel<T, W, PP><<<(unsigned)blocks, wpb * 32, wpb * Cfg::WARP_BYTES, st>>>(p);
-    e = cudaGetLastError();
+    {
+        // Taps through the cp.async.bulk + mbarrier ring (CNGI_APERTURE_BULK=1) or straight from L2 (default).  Measured on
+        // C3 (B200, fp32, 23.1 M samples): 3.21 ms with the ring, 3.08 ms without -- the 14.5 MB tap table is L2 resident and
+        // its latency was already hidden; what bounds the kernel is the 64 FFMA2 per lane and sample (two pipe cycles each:
+        // 1.27 ms for C3) on 12 warps per SM, not the tap fetch.  The ring stays selectable for CFs that outgrow L2.
+        static const bool bulk = getenv("CNGI_APERTURE_BULK") != nullptr;
+        const int smem = wpb * (bulk ? Cfg::WARP_BYTES : Cfg::REC_TOTAL);
+        auto kern = bulk ? aperture_track_kernel<T, W, PP, true> : aperture_track_kernel<T, W, PP, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) {
+            kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(p);
+            e = cudaGetLastError();
+        }
+    }
     cudaFreeAsync(taps, st), cudaFreeAsync(tapnorm, st), cudaFreeAsync(scale, st);
     CNGI_CUDA_TRY(e);
     return CNGI_OK;
