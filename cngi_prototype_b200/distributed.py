@@ -116,7 +116,7 @@ class ContinuumPipeline:
         pipe.flush()            # results of the last step: pipe.last (grid, gsw valid on rank 0)
     """
 
-    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs, side_stream=None, fuse_weights=False):
+    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs, side_stream=None, fuse_weights=False, grid_reduce="root0"):
         """side_stream (a high-priority CUDA stream, device tensors only): the whole imaging-weight chain of step k+1
         (density grid, all-reduce, Briggs factors, weight degrid -- memory-latency bound kernels) is issued there and
         runs CONCURRENTLY with the gridding kernel of step k on the current stream (issue bound): whenever a gridder
@@ -124,6 +124,12 @@ class ContinuumPipeline:
         other's stalls."""
         self.ops, self.gp, self.gp_iw, self.iw_parms, self.cgk = ops, gp, gp_iw, iw_parms, cgk
         self.side = side_stream
+        # grid_reduce: where the summed uv-grid of a step ends up.  "root0": rank 0 (reduce); "rotate": rank k mod N for
+        # step k (successive datasets are transformed by successive ranks: the FFTs and the root's share of the reduce are
+        # spread over the GPUs); "allreduce": everywhere; "none": nowhere (measurement only)
+        assert grid_reduce in ("root0", "rotate", "allreduce", "none"), grid_reduce
+        self.grid_reduce = grid_reduce
+        self.last_root = 0
         # fuse_weights: the weight degrid (A4) runs inside the gridder (ops.standard_grid_weighted) when the ops have it and
         # the support is 7 -- the imaging weights are then never written or re-read.  Measured on C2 (B200, fp32): the
         # gridder is issue bound, so the folded-in work costs what the separate pass costs (2.53 vs 2.50 ms per step): off
@@ -133,6 +139,7 @@ class ContinuumPipeline:
         self.pend_density = [[], []]
         self.pend_grid = [[], []]
         self.k = 0
+        self.n_grids = 0
         self.prev = None
         self.last = None
 
@@ -194,10 +201,22 @@ class ContinuumPipeline:
             self.ops.standard_grid(d["vis"], d["uvw"], iw, d["freq_chan"], self.cgk, self.gp, grid=b.grid, sum_weight=b.gsw)
         if grid_hook is not None:
             grid_hook("end")
-        if world()[1] > 1:   # partial uv-grids -> the rank that runs the FFT
-            self.pend_grid[slot] = [dist.reduce(_as_real(b.grid), 0, async_op=True), dist.reduce(b.gsw, 0, async_op=True)]
+        self._reduce_grid(b, slot)
         self.last = b
         return None if fused else iw
+
+    def _reduce_grid(self, b, slot):
+        """partial uv-grids -> the rank that runs the FFT of this step (self.last_root)"""
+        ws = world()[1]
+        if ws <= 1 or self.grid_reduce == "none":
+            return
+        if self.grid_reduce == "allreduce":
+            self.pend_grid[slot] = [dist.all_reduce(_as_real(b.grid), async_op=True), dist.all_reduce(b.gsw, async_op=True)]
+            return
+        root = (self.n_grids % ws) if self.grid_reduce == "rotate" else 0
+        self.n_grids += 1
+        self.last_root = root
+        self.pend_grid[slot] = [dist.reduce(_as_real(b.grid), root, async_op=True), dist.reduce(b.gsw, root, async_op=True)]
 
     def _weights_on_side(self, d, slot):
         """The whole weight chain of a step on the side stream; returns (imaging weights, event that marks them ready)."""
@@ -230,8 +249,7 @@ class ContinuumPipeline:
             self.ops.standard_grid(d["vis"], d["uvw"], iw, d["freq_chan"], self.cgk, self.gp, grid=b.grid, sum_weight=b.gsw)
         if grid_hook is not None:
             grid_hook("end")
-        if world()[1] > 1:   # partial uv-grids -> the rank that runs the FFT
-            self.pend_grid[slot] = [dist.reduce(_as_real(b.grid), 0, async_op=True), dist.reduce(b.gsw, 0, async_op=True)]
+        self._reduce_grid(b, slot)
         self.last = b
         return None if isinstance(iw, dict) else iw
 
