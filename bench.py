@@ -440,7 +440,8 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     _lib.require_device()
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        from cngi_prototype_b200 import distributed as _D
+        _D.init_nccl(dev)   # NCCL collectives on a high-priority stream (they overlap the gridder instead of queueing behind it)
 
     d = synth.config_c2(n_time=a.n_time, n_chan=a.n_chan, dtype="f32", shard=rank)
     n_samples = d["weight"].size

@@ -20,6 +20,28 @@ import torch
 import torch.distributed as dist
 
 
+def init_nccl(device):
+    """torch.distributed over NCCL with the collectives on a HIGH-PRIORITY stream.
+
+    The collectives of a step are issued while the gridder's ~10 000 blocks are being dispatched.  On a default-priority
+    stream the NCCL kernel's blocks queue behind the gridder's pending blocks and the "overlapped" reduce in fact runs
+    after it; on a high-priority stream they take the next free SM slots.  Measured on 8 B200s (tools/probe_collectives.py,
+    weak scaling, C2): 2.96 -> 2.79 ms per step (standalone: all-reduce of the 134 MB density 0.40 ms, reduce of the
+    268 MB grid 0.45 ms; a single GPU takes 2.50 ms)."""
+    if dist.is_initialized():
+        return
+    opts = None
+    try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+    except Exception:   # older / different builds: fall back to the default stream priority
+        opts = None
+    if opts is not None:
+        dist.init_process_group("nccl", device_id=device, pg_options=opts)
+    else:
+        dist.init_process_group("nccl", device_id=device)
+
+
 def world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()

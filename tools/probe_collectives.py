@@ -34,9 +34,13 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if os.environ.get("PROBE_PLAIN_INIT"):
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        D.init_nccl(dev)
     n = 4096
-    out = {"world": world, "NCCL_ALGO": os.environ.get("NCCL_ALGO", "default")}
+    out = {"world": world, "NCCL_ALGO": os.environ.get("NCCL_ALGO", "default"),
+           "knobs": {k: v for k, v in os.environ.items() if k.startswith(("NCCL_", "TORCH_NCCL")) and k != "NCCL_ALGO"}}
     dens = torch.zeros((1, 1, n, n), dtype=torch.float64, device=dev)
     grid = torch.zeros((1, 2, n, n, 2), dtype=torch.float32, device=dev)
     out["allreduce_density_134MB_f64_ms"] = timed(lambda: dist.all_reduce(dens))
@@ -62,7 +66,8 @@ def main():
                                dsw=torch.empty((1, 2), dtype=torch.float64, device=dev),
                                grid=torch.empty((1, 2, n, n), dtype=torch.complex64, device=dev),
                                gsw=torch.empty((1, 2), dtype=torch.float64, device=dev))
-    for mode in ("root0", "rotate", "allreduce", "none"):
+    modes = os.environ.get("PROBE_MODES", "root0,rotate,allreduce,none").split(",")
+    for mode in modes:
         pipe = D.ContinuumPipeline(D.cuda_ops(), gp, gp_iw, dict(weighting="briggs", robust=0.5), cgk, make_bufs, grid_reduce=mode)
 
         def run():
