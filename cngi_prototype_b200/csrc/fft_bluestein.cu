@@ -87,6 +87,7 @@ template <bool CONJ> __device__ __forceinline__ void twiddles(const float2 *__re
 
 struct BluParams {
     const float2 *src;
+    const float *src_real;     // when set, the lines are REAL (psf grids): read as (x, 0), same element strides
     float2 *dst;
     long long src_line, src_elem, src_plane, dst_line, dst_elem, dst_plane;   // element strides
     int n_lines, n1, P;
@@ -134,8 +135,14 @@ template <int N1> __global__ void __launch_bounds__(BT, 2) bluestein_lines_kerne
     float2 *dst = p.dst +   // (may alias src: the column pass runs in place; every read of the line precedes its writes)
         (long long)blockIdx.y * p.dst_plane + (long long)line * p.dst_line;
 
+    if (p.src_real) {
+        const float *__restrict__ sr = p.src_real + (long long)blockIdx.y * p.src_plane + (long long)line * p.src_line;
 #pragma unroll 8
-    for (int j = t; j < n; j += BT) X[j] = __ldg(src + (long long)j * p.src_elem);
+        for (int j = t; j < n; j += BT) X[j] = make_float2(__ldg(sr + (long long)j * p.src_elem), 0.f);
+    } else {
+#pragma unroll 8
+        for (int j = t; j < n; j += BT) X[j] = __ldg(src + (long long)j * p.src_elem);
+    }
     __syncthreads();
 
     // ---- n1-point DFTs down the columns of the (n1, P) view + twiddles: A[k1][n2] = W_n^{n2 k1} sum_l x[l P + n2] W_n1^{l k1}
@@ -326,11 +333,11 @@ void blu_axis_destroy(BluAxis *ax)
 
 int blu_lines(const BluAxis &ax, const float2 *src, float2 *dst, long long src_line, long long src_elem, long long src_plane,
               long long dst_line, long long dst_elem, long long dst_plane, int n_lines, int n_planes, cudaStream_t st,
-              int line0, int line_mod)
+              int line0, int line_mod, const float *src_real)
 {
     if (n_lines <= 0 || n_planes <= 0) return CNGI_OK;
     BluParams p{};
-    p.src = src, p.dst = dst;
+    p.src = src, p.dst = dst, p.src_real = src_real;
     p.src_line = src_line, p.src_elem = src_elem, p.src_plane = src_plane;
     p.dst_line = dst_line, p.dst_elem = dst_elem, p.dst_plane = dst_plane;
     p.n_lines = n_lines, p.n1 = ax.n1, p.P = ax.P;

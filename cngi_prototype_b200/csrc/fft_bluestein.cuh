@@ -16,6 +16,7 @@ void blu_axis_destroy(BluAxis *ax);
 // transforms n_lines x n_planes lines; element j of line i of plane q is at q * plane + i * line + j * elem (in elements)
 int blu_lines(const BluAxis &ax, const float2 *src, float2 *dst, long long src_line, long long src_elem, long long src_plane,
               long long dst_line, long long dst_elem, long long dst_plane, int n_lines, int n_planes, cudaStream_t st,
-              int line0 = 0, int line_mod = 0);   // lines (line0 + i) mod line_mod, i < n_lines (a cyclic window of lines)
+              int line0 = 0, int line_mod = 0,    // lines (line0 + i) mod line_mod, i < n_lines (a cyclic window of lines)
+              const float *src_real = nullptr);   // real input lines (src ignored): same strides, read as (x, 0)
 
 }  // namespace cngi

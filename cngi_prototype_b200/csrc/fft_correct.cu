@@ -56,21 +56,10 @@ struct PostParams {
     int roundtrip;
 };
 
-template <typename T> __global__ void __launch_bounds__(256) fft_post_kernel(PostParams p)
+// everything after the spectrum value z of image pixel (l, m) of global plane gp has been fetched
+template <typename T>
+__device__ __forceinline__ void post_pixel(const PostParams &p, typename Cplx<T>::type z, int l, int m, int mu, int mv, int gp)
 {
-    using CT = typename Cplx<T>::type;
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;   // fastest image axis
-    const int l = blockIdx.y;
-    const int pl = blockIdx.z;                              // plane within the batch
-    if (m >= p.n_m) return;
-    const int gp = p.plane0 + pl;
-    // fftshift + crop: image pixel (l, m) is shifted-spectrum index k = start + l, i.e. DFT bin (k - h) mod n
-    const int hu = p.n_u / 2, hv = p.n_v / 2;
-    int mu = p.start_u + l - hu;
-    if (mu < 0) mu += p.n_u;
-    int mv = p.start_v + m - hv;
-    if (mv < 0) mv += p.n_v;
-    const CT z = ((const CT *)p.spec)[((long long)pl * p.n_u + mu) * p.n_v + mv];
     const double2 pu = p.phase_u[mu], pv = p.phase_v[mv];
     const double pr = pu.x * pv.x - pu.y * pv.y, pi = pu.x * pv.y + pu.y * pv.x;
     double val = (double)z.x * pr - (double)z.y * pi;       // Re(phase * z)
@@ -99,6 +88,51 @@ template <typename T> __global__ void __launch_bounds__(256) fft_post_kernel(Pos
     }
     if (p.roundtrip) val = (double)(float)val;
     ((T *)p.image)[(long long)gp * npix + pix] = (T)val;
+}
+
+// fftshift + crop: image pixel l (m) is shifted-spectrum index k = start + l, i.e. DFT bin (k - h) mod n
+__device__ __forceinline__ int post_bin(int start, int i, int n)
+{
+    int b = start + i - n / 2;
+    return b < 0 ? b + n : b;
+}
+
+template <typename T> __global__ void __launch_bounds__(256) fft_post_kernel(PostParams p)
+{
+    using CT = typename Cplx<T>::type;
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;   // fastest image axis
+    const int l = blockIdx.y;
+    const int pl = blockIdx.z;                              // plane within the batch
+    if (m >= p.n_m) return;
+    const int mu = post_bin(p.start_u, l, p.n_u), mv = post_bin(p.start_v, m, p.n_v);
+    const CT z = ((const CT *)p.spec)[((long long)pl * p.n_u + mu) * p.n_v + mv];
+    post_pixel<T>(p, z, l, m, mu, mv, p.plane0 + pl);
+}
+
+// The same pass over a spectrum stored TRANSPOSED (spec[plane][v bin][u bin], what the shared-memory Bluestein passes
+// leave: rows out transposed, then rows again): 32 x 32 tiles go through shared memory so that both the reads (along u)
+// and the image writes (along m) are coalesced.  blockDim = (32, 8).
+template <typename T> __global__ void __launch_bounds__(256) fft_post_transposed_kernel(PostParams p)
+{
+    using CT = typename Cplx<T>::type;
+    __shared__ CT tile[32][33];
+    const int m0 = blockIdx.x * 32, l0 = blockIdx.y * 32, pl = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int m = m0 + ty + 8 * r, l = l0 + tx;
+        if (m < p.n_m && l < p.n_l) {
+            const int mu = post_bin(p.start_u, l, p.n_u), mv = post_bin(p.start_v, m, p.n_v);
+            tile[ty + 8 * r][tx] = ((const CT *)p.spec)[((long long)pl * p.n_v + mv) * p.n_u + mu];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int l = l0 + ty + 8 * r, m = m0 + tx;
+        if (m < p.n_m && l < p.n_l)
+            post_pixel<T>(p, tile[tx][ty + 8 * r], l, m, post_bin(p.start_u, l, p.n_u), post_bin(p.start_v, m, p.n_v), p.plane0 + pl);
+    }
 }
 
 
@@ -175,7 +209,7 @@ static int make_phase(double2 **dev, int64_t n)
 // keep_v0 / keep_vn: the second pass is only needed for the v bins the caller will read -- the cyclic window
 // [keep_v0, keep_v0 + keep_vn) mod n_v (grid_to_image: the cropped image columns); keep_vn <= 0: every bin.
 static int blu_transform(cngi_fft_plan *pl, int dir, const float2 *src, float2 *dst, int64_t nb, cudaStream_t st,
-                         int keep_v0 = 0, int keep_vn = 0)
+                         int keep_v0 = 0, int keep_vn = 0, bool transposed_out = false, const float *src_real = nullptr)
 {
     if (!pl->blu_ready[dir]) {
         int rc = blu_axis_create(&pl->blu_u[dir], pl->n_u, dir == 0 ? +1 : -1);
@@ -184,9 +218,17 @@ static int blu_transform(cngi_fft_plan *pl, int dir, const float2 *src, float2 *
         pl->blu_ready[dir] = true;
     }
     const long long plane = (long long)pl->n_u * pl->n_v;
+    if (keep_vn <= 0 || keep_vn >= pl->n_v) keep_v0 = 0, keep_vn = (int)pl->n_v;
+    if (transposed_out) {
+        // rows (lines along v) written TRANSPOSED -- strided stores, which nobody waits for, instead of the strided loads a
+        // column pass starts with -- then the lines along u are contiguous rows of dst: dst[plane][v bin][u bin]
+        // (src must not alias dst here; a real grid is read directly, without a widening pass)
+        int rc = blu_lines(pl->blu_v[dir], src, dst, pl->n_v, 1, plane, 1, pl->n_u, plane, (int)pl->n_u, (int)nb, st, 0, 0, src_real);
+        if (rc != CNGI_OK) return rc;
+        return blu_lines(pl->blu_u[dir], dst, dst, pl->n_u, 1, plane, pl->n_u, 1, plane, keep_vn, (int)nb, st, keep_v0, (int)pl->n_v);
+    }
     int rc = blu_lines(pl->blu_v[dir], src, dst, pl->n_v, 1, plane, pl->n_v, 1, plane, (int)pl->n_u, (int)nb, st);
     if (rc != CNGI_OK) return rc;
-    if (keep_vn <= 0 || keep_vn >= pl->n_v) keep_v0 = 0, keep_vn = (int)pl->n_v;
     return blu_lines(pl->blu_u[dir], dst, dst, 1, pl->n_v, plane, 1, pl->n_v, plane, keep_vn, (int)nb, st, keep_v0, (int)pl->n_v);
 }
 
@@ -270,20 +312,16 @@ extern "C" int cngi_b200_grid_to_image(cngi_fft_plan *pl, const cngi_grid_to_ima
     for (int64_t p0 = 0; p0 < a->n_planes; p0 += pl->max_planes) {
         const int64_t nb = std::min<int64_t>(pl->max_planes, a->n_planes - p0);
         if (pl->use_blu) {   // shared-memory Bluestein passes (complex64, sides n1 * prime)
-            const float2 *bsrc;
-            if (a->grid_is_complex) {
+            const float2 *bsrc = nullptr;
+            const float *rsrc = nullptr;
+            if (a->grid_is_complex)
                 bsrc = (const float2 *)((const char *)a->grid + (size_t)p0 * plane_cells * cb);
-            } else {
-                const long long n = nb * plane_cells;
-                const unsigned blocks = (unsigned)std::min<long long>(ceil_div(n, 256), (long long)sm_count() * 16);
-                real_to_complex_kernel<float><<<blocks, 256, 0, st>>>((const float *)a->grid + (size_t)p0 * plane_cells, (float2 *)pl->work, n);
-                CNGI_CUDA_TRY(cudaGetLastError());
-                bsrc = (const float2 *)pl->work;
-            }
+            else
+                rsrc = (const float *)a->grid + (size_t)p0 * plane_cells;   // psf grids: the first pass reads the real cells
             // image column m is DFT bin (start_v + m - n_v / 2) mod n_v: the other bins are never read by the post pass
             const int start_v = (int)(a->n_v / 2 - a->image_size[1] / 2);
             const int v0 = (int)(((start_v - a->n_v / 2) % a->n_v + a->n_v) % a->n_v);
-            int rc = blu_transform(pl, 0, bsrc, (float2 *)pl->work, nb, st, v0, (int)a->image_size[1]);
+            int rc = blu_transform(pl, 0, bsrc, (float2 *)pl->work, nb, st, v0, (int)a->image_size[1], true, rsrc);
             if (rc != CNGI_OK) return rc;
         } else {
             cufftHandle h = pl->plan;
@@ -333,7 +371,10 @@ extern "C" int cngi_b200_grid_to_image(cngi_fft_plan *pl, const cngi_grid_to_ima
         pp.plane0 = (int)p0, pp.roundtrip = a->single_precision_roundtrip;
         dim3 grid((unsigned)ceil_div(pp.n_m, 256), (unsigned)pp.n_l, (unsigned)nb);
         CNGI_REQUIRE(nb < 65536, "grid_to_image: too many planes per batch");
-        if (f32)
+        if (pl->use_blu)   // the Bluestein passes leave the spectrum transposed
+            fft_post_transposed_kernel<float><<<dim3((unsigned)ceil_div(pp.n_m, 32), (unsigned)ceil_div(pp.n_l, 32), (unsigned)nb),
+                                                dim3(32, 8), 0, st>>>(pp);
+        else if (f32)
             fft_post_kernel<float><<<grid, 256, 0, st>>>(pp);
         else
             fft_post_kernel<double><<<grid, 256, 0, st>>>(pp);
