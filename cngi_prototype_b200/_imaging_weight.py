@@ -116,6 +116,9 @@ def _standard_imaging_weight_degrid_numpy_wrap(grid_imaging_weight, uvw, natural
     a.density = ptr(g)
     for i in range(4):
         a.density_stride[i] = int(strides[i])
+    # pol planes / factor columns that are stride-0 views of one plane are identical by construction (first_pol_only)
+    a.pol_shared = int(n_pol == 2 and strides[3] == 0 and is_torch(briggs_factors) and briggs_factors.dim() == 3
+                       and briggs_factors.stride(2) == 0)
     a.briggs_factors = ptr(up(briggs_factors, torch.float64))
     a.imaging_weight = ptr(out)
     cell = grid_parms["cell_size"]

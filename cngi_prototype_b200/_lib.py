@@ -55,7 +55,7 @@ class IwDegridArgs(C.Structure):
         ("natural_weight", vp), ("uvw", vp), ("freq_chan", vp), ("chan_map", vp), ("pol_map", vp),
         ("density", vp), ("density_stride", i64 * 4), ("briggs_factors", vp), ("imaging_weight", vp),
         ("delta_lm", f64 * 2),
-        ("precision", i32), ("chan_mode", i32),
+        ("precision", i32), ("chan_mode", i32), ("pol_shared", i32), ("reserved", i32),
     ]
 
 

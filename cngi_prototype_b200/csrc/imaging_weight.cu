@@ -29,6 +29,7 @@ struct IwParams {
     void *out;
     const double *scale;   // [2, n_chan] uv_scale table
     int n_pol_out;         // pol planes updated by iw_grid (1 when first_pol_only)
+    int pol_shared;        // degrid: density planes and Briggs factors are identical across pol (one gather, one division)
 };
 
 __device__ __forceinline__ int iw_chan_of(const IwParams &p, int c)
@@ -328,10 +329,14 @@ template <typename T, int NP, int R> __global__ void __launch_bounds__(256) iw_d
         for (int ip = 0; ip < NP; ++ip) rho[k][ip] = 0.0;
         if (ok[k]) {
             const long long cell = cp.uc * p.ds_u + cp.vc * p.ds_v + a_chan * p.ds_c;
+            if (NP == 2 && p.pol_shared) {
+                rho[k][0] = p.density[cell];   // every pol sees this value
+            } else {
 #pragma unroll
-            for (int ip = 0; ip < NP; ++ip) {
-                const double w = (double)nat[k][ip];
-                if (!isnan(w) && w != 0.0) rho[k][ip] = p.density[cell + ip * p.ds_p];   // rho is only used in that case
+                for (int ip = 0; ip < NP; ++ip) {
+                    const double w = (double)nat[k][ip];
+                    if (!isnan(w) && w != 0.0) rho[k][ip] = p.density[cell + ip * p.ds_p];   // rho is only used in that case
+                }
             }
         }
     }
@@ -341,6 +346,19 @@ template <typename T, int NP, int R> __global__ void __launch_bounds__(256) iw_d
         const long long tb = row0 + (long long)k * blockDim.y;
         T res[NP];
         const double avg = NP == 2 ? __dmul_rn(__dadd_rn((double)nat[k][0], (double)nat[k][NP - 1]), 0.5) : 0.0;   // == /2.0
+        if (NP == 2 && p.pol_shared) {   // same value and factors for both pols: one division (bit-identical results)
+            double q = avg;
+            const double r = rho[k][0];
+            if (ok[k] && !isnan(r) && r != 0.0) {
+                const double den = __dadd_rn(__dmul_rn(f0[0], r), f1[0]);
+                q = sizeof(T) == 4 ? (double)__fdiv_rn((float)avg, (float)den) : __ddiv_rn(avg, den);
+            }
+#pragma unroll
+            for (int ip = 0; ip < NP; ++ip) {
+                const double w = (double)nat[k][ip];
+                res[ip] = (T)(ok[k] ? ((!isnan(w) && w != 0.0) ? q : avg) : 0.0);
+            }
+        } else
 #pragma unroll
         for (int ip = 0; ip < NP; ++ip) {
             double iw = 0.0;   // off-grid or NaN uv: 0 (:460,493,502)
@@ -476,6 +494,7 @@ extern "C" int cngi_b200_imaging_weight_degrid(const cngi_iw_degrid_args *a, voi
     p.density = const_cast<double *>(a->density), p.dl = a->delta_lm[0], p.dm = a->delta_lm[1], p.chan_mode = a->chan_mode;
     p.bf = a->briggs_factors, p.out = a->imaging_weight;
     p.ds_u = a->density_stride[0], p.ds_v = a->density_stride[1], p.ds_c = a->density_stride[2], p.ds_p = a->density_stride[3];
+    p.pol_shared = a->pol_shared != 0 && p.n_pol == 2;
     int cx = 1;
     while (cx < 128 && cx < p.n_chan) cx <<= 1;   // channels per block (power of two), 256 / cx rows per block
     const dim3 block(cx, 256 / cx);

@@ -186,6 +186,10 @@ typedef struct cngi_iw_degrid_args {
     double delta_lm[2];
     int32_t precision;
     int32_t chan_mode;
+    int32_t pol_shared;         /* n_pol == 2 only: the caller GUARANTEES identical density planes and Briggs factors for
+                                   both pols (pol-averaged weights, _standard_grid.py:328-330): one gather and one
+                                   division per sample, bit-identical results                                          */
+    int32_t reserved;
 } cngi_iw_degrid_args;
 
 int cngi_b200_imaging_weight_degrid(const cngi_iw_degrid_args *args, void *stream);

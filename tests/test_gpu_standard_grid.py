@@ -247,3 +247,38 @@ def test_reduction_microbench_counts(pattern):
     _lib.check(_lib.lib().cngi_b200_microbench_red(ptr(buf), buf.numel(), pattern, 7, 5, stream()), "microbench_red")
     total = buf.sum().cpu().item()
     assert total.real == 7 * 256 * 5 and total.imag == -7 * 256 * 5
+
+
+@pytest.mark.parametrize("algo", [4, 2, 1])
+def test_infinite_and_huge_uvw_rows_are_skipped_not_wrapped(oracle, algo):
+    """+-inf or huge finite uvw saturate the int conversion of the cell index; `centre +- half` must not wrap
+    around and pass the bounds test (window, track and naive kernels, imaging-weight grid / degrid, degrid predict).  Such
+    rows are skipped like any other off-grid sample; the reference (numba) has undefined behaviour there, so the expected
+    result is the grid of the same data with those rows made NaN."""
+    import torch
+    from cngi_prototype_b200 import synth, _standard_grid as sg, _imaging_weight as iw, _standard_degrid as sd
+    d = synth.make_vis_set(7, 12, 4, 2, 1e9, 1.1e9, 300.0, 120.0, seed=3, dtype="f64")
+    bad = d["uvw"].copy()
+    bad[1, 2, 0], bad[3, 4, 1], bad[5, 6, 0], bad[7, 8, 1] = np.inf, -np.inf, 1e300, -1e300
+    ref_uvw = d["uvw"].copy()
+    for (t, b) in ((1, 2), (3, 4), (5, 6), (7, 8)):
+        ref_uvw[t, b, :2] = np.nan
+    cgk = oracle._create_prolate_spheroidal_kernel_1D(100, 7)
+    gp = synth.grid_parms_for(96, d["cell"], chan_mode="cube")
+    g_ref, s_ref = oracle._standard_grid_numpy_wrap(d["vis"], ref_uvw, d["weight"], d["freq_chan"], cgk, gp)
+    g, s = sg._standard_grid_numpy_wrap(d["vis"], bad, d["weight"], d["freq_chan"], cgk, gp, algorithm=algo)
+    assert same_support(g, g_ref) and rel_err(g, g_ref) <= 1e-12 and rel_err(s, s_ref) <= 1e-12
+    if algo == 4:
+        gpw = dict(gp, support=1, oversampling=0, do_psf=True, complex_grid=False, do_imaging_weight=True)
+        rho_ref, sw_ref = oracle._standard_grid_psf_numpy_wrap(ref_uvw, d["weight"], d["freq_chan"], np.ones(1), gpw)
+        rho, sw = iw.imaging_weight_grid(bad, d["weight"], d["freq_chan"], gpw)
+        assert rel_err(rho, rho_ref) <= 1e-12 and rel_err(sw, sw_ref) <= 1e-12
+        bf = oracle._calculate_briggs_parms(rho_ref, sw_ref, {"weighting": "briggs", "robust": 0.5})
+        w_ref = oracle._standard_imaging_weight_degrid_numpy_wrap(np.moveaxis(rho_ref, (0, 1), (2, 3)), ref_uvw, d["weight"], bf,
+                                                                 d["freq_chan"], gpw)
+        w_gpu = iw._standard_imaging_weight_degrid_numpy_wrap(np.moveaxis(rho_ref, (0, 1), (2, 3)), bad, d["weight"], bf,
+                                                              d["freq_chan"], gpw)
+        assert np.array_equal(np.nan_to_num(w_gpu, nan=-1), np.nan_to_num(w_ref, nan=-1))
+        v_ref = oracle._standard_degrid_numpy_wrap(g_ref, ref_uvw, d["freq_chan"], cgk, gp)
+        v = sd._standard_degrid_numpy_wrap(g_ref, bad, d["freq_chan"], cgk, gp)
+        assert np.array_equal(v == 0, v_ref == 0) and rel_err(v, v_ref) <= 1e-12
