@@ -22,6 +22,7 @@ Prints ONE JSON line.  Keys beyond the base contract:
   roofline     the dominant kernel (std_grid_window) against the measured HBM peak; atomic_roofline: its reductions
   sustained    the same step looped for >= 3 s, with its own clock record
   value_f64    the same step at the reference's precision (complex128 / float64)
+  configs      the other BASELINE configs' rows on this GPU: C1 (fp64 image / psf gridding), C3 (aperture gridders), C4 (degrid)
   cube         BASELINE config 5's per-GPU share (8192^2 padded to 9830^2, 128 channels per GPU, channel-sharded):
                time_split = 1 (no exchange) and, for N >= 2, time_split = 2 (NCCL sub-group grid reduce)
   cpu_baseline the reference's own numba loops (oracle/_ref, kind "reference") when staged, else the C port
@@ -64,6 +65,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cube", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 row timings (N = 1 only)")
     ap.add_argument("--no-extras", action="store_true", help="skip sustained / value_f64 / pcie probe")
     ap.add_argument("--cube-chan-per-gpu", type=int, default=128)
     ap.add_argument("--cube-samples-per-gpu", type=float, default=2.5e9)
@@ -427,6 +429,85 @@ def cube_record(a, dev, rank, world, dist, time_split, groups):
     return rec
 
 
+def config_rows(dev):
+    """Device-resident timings of the other BASELINE configs' hot-path rows (each is parity-tested at this size in
+    tests/test_gpu_full_size_parity.py): C1 standard image + psf gridding (fp64, 1024^2, cube and continuum), C3 aperture
+    image and weight gridding (7-pointing mosaic, 2048^2), C4 degridding predict (fp64, 4096^2).  CUDA events around 5
+    back-to-back calls, after 2 warm-up calls; grids are accumulated into (not re-zeroed), which does not change the work."""
+    import torch
+    from cngi_prototype_b200 import synth, _standard_grid as sg, _aperture_grid as apg, _standard_degrid as sdg
+    from cngi_prototype_b200._gridding_convolutional_kernels import _create_prolate_spheroidal_kernel_1D
+    cgk = torch.as_tensor(_create_prolate_spheroidal_kernel_1D(OVERSAMPLING, SUPPORT)).to(dev)
+
+    def ms_of(fn, n=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def row(ms, n_samples):
+        return {"ms": round(ms, 4), "vis_per_s": n_samples / (ms * 1e-3)}
+
+    out = {}
+    d = synth.config_c1()
+    T = {k: torch.as_tensor(d[k]).to(dev) for k in ("vis", "uvw", "weight", "freq_chan")}
+    n = d["weight"].size
+    c1 = {"workload": "C1 VLA-like 351 bl x 1000 t x 64 ch x 2 pol = %.1f M samples, 1024^2, S=7, fp64" % (n / 1e6)}
+    for mode in ("cube", "continuum"):
+        gp = synth.grid_parms_for(1024, d["cell"], chan_mode=mode)
+        n_ic = 64 if mode == "cube" else 1
+        g = torch.zeros((n_ic, 2, 1024, 1024), dtype=torch.complex128, device=dev)
+        pg = torch.zeros((n_ic, 2, 1024, 1024), dtype=torch.float64, device=dev)
+        sw, psw = torch.zeros((n_ic, 2), dtype=torch.float64, device=dev), torch.zeros((n_ic, 2), dtype=torch.float64, device=dev)
+        c1[mode] = {"image": row(ms_of(lambda: sg.standard_grid(T["vis"], T["uvw"], T["weight"], T["freq_chan"], cgk, gp, False, True,
+                                                                grid=g, sum_weight=sw)), n),
+                    "psf": row(ms_of(lambda: sg.standard_grid(None, T["uvw"], T["weight"], T["freq_chan"], cgk, gp, True, False,
+                                                              grid=pg, sum_weight=psw)), n),
+                    "image_and_psf_one_pass": row(ms_of(lambda: sg.standard_grid_image_psf(
+                        T["vis"], T["uvw"], T["weight"], T["freq_chan"], cgk, gp, grid=g, sum_weight=sw, psf_grid=pg,
+                        psf_sum_weight=psw, force_fused=True)), n)}
+        del g, pg
+    out["C1"] = c1
+    del T
+    d = synth.config_c2(n_time=200, n_chan=64, dtype="f32")
+    gcf = synth.make_mosaic_gcf(d["n_baseline"], 64, 2, n_field=7)
+    field = synth.mosaic_field_column(200, d["n_baseline"], gcf["field_id"])
+    gp = synth.grid_parms_for(2048, d["cell"] * 1.1, chan_mode="continuum")
+    gp["oversampling"], gp["field_id"] = gcf["oversampling"], gcf["field_id"]
+    T = {k: torch.as_tensor(d[k]).to(dev) for k in ("vis", "uvw", "weight", "freq_chan")}
+    G = {k: torch.as_tensor(v).to(dev) for k, v in gcf.items()}
+    fld = torch.as_tensor(field).to(dev)
+    common = (T["uvw"], T["weight"], fld, G["cf_baseline_map"], G["cf_chan_map"], G["cf_pol_map"])
+    g = torch.zeros((1, 2, 2048, 2048), dtype=torch.complex64, device=dev)
+    sw = torch.zeros((1, 2), dtype=torch.float64, device=dev)
+    n = d["weight"].size
+    out["C3"] = {"workload": "C3 mosaic: 7 pointings, 903 bl x 200 t x 64 ch x 2 pol = %.1f M samples, CF 160^2 (oversampling 10, "
+                             "supports 9-15), 2048^2, fp32, continuum" % (n / 1e6),
+                 "aperture_image": row(ms_of(lambda: apg._aperture_grid_numpy_wrap(
+                     T["vis"], *common, G["conv_kernel"], gcf["weight_support"], G["phase_gradient"], T["freq_chan"], gp, grid=g,
+                     sum_weight=sw)), n),
+                 "aperture_weight": row(ms_of(lambda: apg._aperture_weight_grid_numpy_wrap(
+                     *common, G["weight_conv_kernel"], gcf["weight_support"], G["phase_gradient"], T["freq_chan"], gp, grid=g,
+                     sum_weight=sw)), n)}
+    del T, G, g
+    d = synth.config_c4()
+    uvw, freq = torch.as_tensor(d["uvw"]).to(dev), torch.as_tensor(d["freq_chan"]).to(dev)
+    gp = synth.grid_parms_for(4096, d["cell"], chan_mode="continuum")
+    model = torch.view_as_complex(torch.randn((1, 2, 4096, 4096, 2), dtype=torch.float64, device=dev))
+    n = d["weight"].size
+    out["C4"] = {"workload": "C4 predict: 351 bl x 1000 t x 64 ch x 2 pol = %.1f M samples from a 4096^2 model grid, S=7, fp64" % (n / 1e6),
+                 "degrid": row(ms_of(lambda: sdg._standard_degrid_numpy_wrap(model, uvw, freq, cgk, gp, normalize=True)), n)}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -640,6 +721,7 @@ def run_b200(a):
             dist.destroy_process_group()
         return
     sampler.stop()
+    configs = config_rows(dev) if (world == 1 and not a.no_configs) else None
 
     # roofline of the dominant kernel (std_grid_window), algorithmic bytes per SURVEY.md section 8d:
     # n_samples * (8 B vis + 4 B weight) + uvw + grid written once
@@ -714,7 +796,7 @@ def run_b200(a):
             "gpu_launches_note": "per step of the timed (device-resident) region: iw_grid, iw_sumsq, iw_briggs_finalize, iw_degrid, "
                                  "std_grid_window; the 128-thread uv_scale table kernel in front of A2 / A4 / A1 and the memsets are not counted",
             "roofline": roofline, "atomic_roofline": atomic, "parity": parity,
-            "sustained": sustained, "value_f64": value_f64, "cube": cube,
+            "sustained": sustained, "value_f64": value_f64, "cube": cube, "configs": configs,
             "cpu_baseline": cb, "cpu_baseline_port": cb_port}
     emit(line)
     if world > 1:

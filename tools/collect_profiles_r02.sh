@@ -4,7 +4,7 @@
 set -x
 O=gpurun_out
 mkdir -p $O
-B="--no-cpu-baseline --no-e2e --no-cube --no-extras --no-parity"
+B="--no-cpu-baseline --no-e2e --no-cube --no-extras --no-parity --no-configs"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/r02_launches.csv \
     python bench.py --steps 2 --warmup 3 $B > $O/r02_launches.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:std_grid_window -c 1 -f -o $O/r02_window \
