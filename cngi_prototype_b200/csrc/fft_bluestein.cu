@@ -76,13 +76,62 @@ template <int SIGN> __device__ __forceinline__ void dft8_low_half(float2 (&a)[8]
     a[0] = b0, a[1] = c0, a[2] = b1, a[3] = c1, a[4] = b2, a[5] = c2, a[6] = b3, a[7] = c3;
 }
 
-// w[q] = W_M^{j1 * q} (q = 1..7) from three table reads: W^{j1}, W^{2 j1}, W^{4 j1} (indices stay below M for every stage)
-template <bool CONJ> __device__ __forceinline__ void twiddles(const float2 *__restrict__ wm, int j1, float2 (&w)[8])
+// the three table values a stage's twiddles are derived from; they depend on the thread and the stage only, so the
+// kernel loads them ONCE per line and keeps them in registers across the n1 Bluestein transforms
+struct TwBase {
+    float2 w1, w2, w4;
+};
+__device__ __forceinline__ TwBase tw_base(const float2 *__restrict__ wm, int j1)
 {
-    float2 w1 = __ldg(wm + j1), w2 = __ldg(wm + 2 * j1), w4 = __ldg(wm + 4 * j1);
+    TwBase b;
+    b.w1 = __ldg(wm + j1), b.w2 = __ldg(wm + 2 * j1), b.w4 = __ldg(wm + 4 * j1);
+    return b;
+}
+template <bool CONJ> __device__ __forceinline__ void twiddles_from(const TwBase &b, float2 (&w)[8])
+{
+    float2 w1 = b.w1, w2 = b.w2, w4 = b.w4;
     if (CONJ) w1 = cconj(w1), w2 = cconj(w2), w4 = cconj(w4);
     w[1] = w1, w[2] = w2, w[4] = w4;
     w[3] = cmul(w1, w2), w[5] = cmul(w4, w1), w[6] = cmul(w4, w2), w[7] = cmul(w4, w[3]);
+}
+
+// N-point DFT of a register array with the table w[j] = W_NW^j (W_N = w[TS]): even sizes split once more into two
+// half-size DFTs + N / 2 twiddle products (10 -> 2 x 5: 55 complex multiply-adds instead of 100), odd sizes directly
+template <int N, int TS, int NW>
+__device__ __forceinline__ void small_dft(const float2 (&in)[N], float2 (&out)[N], const float2 (&w)[NW])
+{
+    if constexpr (N == 1) {
+        out[0] = in[0];
+    } else if constexpr (N == 2) {
+        out[0] = in[0] + in[1], out[1] = in[0] - in[1];
+    } else if constexpr (N % 2 == 0) {
+        float2 e[N / 2], o[N / 2], E[N / 2], O[N / 2];
+#pragma unroll
+        for (int m = 0; m < N / 2; ++m) e[m] = in[2 * m], o[m] = in[2 * m + 1];
+        small_dft<N / 2, 2 * TS, NW>(e, E, w);
+        small_dft<N / 2, 2 * TS, NW>(o, O, w);
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) {
+            const float2 tw = k ? cmul(O[k], w[(k * TS) % NW]) : O[k];
+            out[k] = E[k] + tw, out[k + N / 2] = E[k] - tw;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            float2 acc = in[0];
+#pragma unroll
+            for (int l = 1; l < N; ++l) {
+                const float2 c = w[(l * k * TS) % NW];
+                if ((l * k) % N == 0) {
+                    acc = acc + in[l];
+                } else {
+                    acc.x = fmaf(in[l].x, c.x, fmaf(-in[l].y, c.y, acc.x));
+                    acc.y = fmaf(in[l].x, c.y, fmaf(in[l].y, c.x, acc.y));
+                }
+            }
+            out[k] = acc;
+        }
+    }
 }
 
 struct BluParams {
@@ -103,12 +152,12 @@ struct BluParams {
 // One radix-8 stage of the 2048-point network on the skewed re / im planes.  DIF (forward): butterfly, then twiddle;
 // DIT (backward): twiddle, then butterfly.  `first` = element index of leg 0, `sub` = distance between legs, j1 = index of
 // W^{offset} in the W_M table.
-template <bool DIT> __device__ __forceinline__ void radix8_stage(float2 *y, const float2 *wm, int first, int sub, int j1)
+template <bool DIT> __device__ __forceinline__ void radix8_stage(float2 *y, const TwBase &tb, int first, int sub)
 {
     float2 a[8], w[8];
 #pragma unroll
     for (int l = 0; l < 8; ++l) a[l] = y[skew(first + sub * l)];
-    twiddles<DIT>(wm, j1, w);
+    twiddles_from<DIT>(tb, w);
     if (DIT) {
 #pragma unroll
         for (int q = 1; q < 8; ++q) a[q] = cmul(a[q], w[q]);
@@ -148,20 +197,12 @@ template <int N1> __global__ void __launch_bounds__(BT, 2) bluestein_lines_kerne
     // ---- n1-point DFTs down the columns of the (n1, P) view + twiddles: A[k1][n2] = W_n^{n2 k1} sum_l x[l P + n2] W_n1^{l k1}
     for (int n2 = t; n2 < P; n2 += BT) {
         if constexpr (N1 > 0) {
-            float2 x[N1], w[N1];
+            float2 x[N1], w[N1], o[N1];
 #pragma unroll
             for (int l = 0; l < N1; ++l) x[l] = X[l * P + n2], w[l] = __ldg(p.w_n1 + l);
+            small_dft<N1, 1, N1>(x, o, w);
 #pragma unroll
-            for (int k1 = 0; k1 < N1; ++k1) {
-                float2 acc = x[0];
-#pragma unroll
-                for (int l = 1; l < N1; ++l) {
-                    const float2 c = w[(l * k1) % N1];
-                    acc.x = fmaf(x[l].x, c.x, fmaf(-x[l].y, c.y, acc.x));
-                    acc.y = fmaf(x[l].x, c.y, fmaf(x[l].y, c.x, acc.y));
-                }
-                X[k1 * P + n2] = k1 ? cmul(acc, __ldg(p.tw_n + n2 * k1)) : acc;
-            }
+            for (int k1 = 0; k1 < N1; ++k1) X[k1 * P + n2] = k1 ? cmul(o[k1], __ldg(p.tw_n + n2 * k1)) : o[k1];
         } else {
             float2 out[32];
             for (int k1 = 0; k1 < n1; ++k1) {
@@ -175,6 +216,10 @@ template <int N1> __global__ void __launch_bounds__(BT, 2) bluestein_lines_kerne
     __syncthreads();
 
     // ---- n1 Bluestein transforms of length P: B[k1][k2] = c[k2] * IFFT_M(FFT_M(A[k1] * c, zero padded) * bf)[k2]
+    const TwBase tw2048 = tw_base(p.w_m, t), tw256 = tw_base(p.w_m, 8 * (t & 31)), tw32 = tw_base(p.w_m, 64 * (t & 3));
+    float2 chirp[4];   // this thread's four chirp values (elements t + 256 l): the same for every k1; the output chirp is chirp / M
+#pragma unroll
+    for (int l = 0; l < 4; ++l) chirp[l] = (t + 256 * l < P) ? __ldg(p.chirp + t + 256 * l) : make_float2(0.f, 0.f);
     for (int k1 = 0; k1 < n1; ++k1) {
         const float2 *seg = X + k1 * P;
         {   // forward stage 1 (span 2048) fused with the load: legs 4..7 are the zero padding (P <= 1024)
@@ -182,19 +227,19 @@ template <int N1> __global__ void __launch_bounds__(BT, 2) bluestein_lines_kerne
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
                 const int j = t + 256 * l;
-                a[l] = j < P ? cmul(seg[j], __ldg(p.chirp + j)) : make_float2(0.f, 0.f);
+                a[l] = j < P ? cmul(seg[j], chirp[l]) : make_float2(0.f, 0.f);
             }
             dft8_low_half<-1>(a);
-            twiddles<false>(p.w_m, t, w);
+            twiddles_from<false>(tw2048, w);
 #pragma unroll
             for (int q = 1; q < 8; ++q) a[q] = cmul(a[q], w[q]);
 #pragma unroll
             for (int q = 0; q < 8; ++q) y[skew(t + 256 * q)] = a[q];
         }
         __syncthreads();
-        radix8_stage<false>(y, p.w_m, (t >> 5) * 256 + (t & 31), 32, 8 * (t & 31));     // span 256
+        radix8_stage<false>(y, tw256, (t >> 5) * 256 + (t & 31), 32);     // span 256
         __syncthreads();
-        radix8_stage<false>(y, p.w_m, (t >> 2) * 32 + (t & 3), 4, 64 * (t & 3));         // span 32
+        radix8_stage<false>(y, tw32, (t >> 2) * 32 + (t & 3), 4);         // span 32
         __syncthreads();
         // forward span 4, times the filter spectrum, backward span 4: four consecutive elements, registers only
 #pragma unroll
@@ -212,22 +257,22 @@ template <int N1> __global__ void __launch_bounds__(BT, 2) bluestein_lines_kerne
             *reinterpret_cast<float4 *>(y + e + 2) = make_float4(a2.x, a2.y, a3.x, a3.y);
         }
         __syncthreads();
-        radix8_stage<true>(y, p.w_m, (t >> 2) * 32 + (t & 3), 4, 64 * (t & 3));          // span 32
+        radix8_stage<true>(y, tw32, (t >> 2) * 32 + (t & 3), 4);          // span 32
         __syncthreads();
-        radix8_stage<true>(y, p.w_m, (t >> 5) * 256 + (t & 31), 32, 8 * (t & 31));      // span 256
+        radix8_stage<true>(y, tw256, (t >> 5) * 256 + (t & 31), 32);      // span 256
         __syncthreads();
         {   // backward span 2048 fused with the output chirp; only k2 < P (<= 1024: legs 0..3) is kept, into the dead segment
             float2 a[8], w[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) a[q] = y[skew(t + 256 * q)];
-            twiddles<true>(p.w_m, t, w);
+            twiddles_from<true>(tw2048, w);
 #pragma unroll
             for (int q = 1; q < 8; ++q) a[q] = cmul(a[q], w[q]);
             dft8<+1>(a);
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
                 const int k2 = t + 256 * l;
-                if (k2 < P) X[k1 * P + k2] = cmul(a[l], __ldg(p.chirp_out + k2));
+                if (k2 < P) X[k1 * P + k2] = cmul(a[l], make_float2(chirp[l].x * (1.0f / BM), chirp[l].y * (1.0f / BM)));
             }
         }
         __syncthreads();
