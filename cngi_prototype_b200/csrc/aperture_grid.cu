@@ -746,8 +746,8 @@ template <typename T, int W, int PP> static int launch_aperture_track(ApParams p
     {
         // Taps through the cp.async.bulk + mbarrier ring (CNGI_APERTURE_BULK=1) or straight from L2 (default).  Measured on
         // C3 (B200, fp32, 23.1 M samples): 3.21 ms with the ring, 3.08 ms without -- the 14.5 MB tap table is L2 resident and
-        // its latency was already hidden; what bounds the kernel is the 64 FFMA2 per lane and sample (two pipe cycles each:
-        // 1.27 ms for C3) on 12 warps per SM, not the tap fetch.  The ring stays selectable for CFs that outgrow L2.
+        // its latency was already hidden; the ring's LDS + barrier waits cost more issue slots than the 16 LDGs they replace
+        // (ncu: 54 % vs 46 % issue-active, profiles/r02_aperture_track*.txt).  The ring stays selectable for CFs that outgrow L2.
         static const bool bulk = getenv("CNGI_APERTURE_BULK") != nullptr;
         const int smem = wpb * (bulk ? Cfg::WARP_BYTES : Cfg::REC_TOTAL);
         auto kern = bulk ? aperture_track_kernel<T, W, PP, true> : aperture_track_kernel<T, W, PP, false>;

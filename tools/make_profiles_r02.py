@@ -60,8 +60,8 @@ out = {"std_grid_kernel": "std_grid_window_kernel<float,complex,S=7,PP=2>",
        "std_grid_red_instructions_per_launch": int(get("smsp__inst_executed_op_global_red.sum")),
        "std_grid_issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
        "std_grid_note": "not HBM bound: %.0f %% of the issue slots are active on 16 warps per SM and the shared-memory pipe co-limits "
-                        "it; FP32 floor 0.45 ms per launch counting one slot per FFMA2 (0.9 ms at the two pipe cycles an FFMA2 "
-                        "takes); see DESIGN.md section 4.1" % get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                        "it; FP32 floor 0.45 ms per launch (256 FMAs per sample, 128 FMA lanes per clock and SM); see DESIGN.md "
+                        "section 4.1" % get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
        "source": "ncu --set full --clock-control none, profiles/r02_std_grid_window_f32_continuum.txt, one launch of bench.py's "
                  "gridding kernel (C2, fp32, continuum)"}
 if os.path.exists(os.path.join(G, "r02_window_cube.ncu-rep")):
