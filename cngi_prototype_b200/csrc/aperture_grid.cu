@@ -287,7 +287,10 @@ template <typename T, int W, int PP> struct ApTrackCfg {
     static constexpr int BLK_BYTES = W * W * 2 * (int)sizeof(T);
     static constexpr int RING_BYTES = DEPTH * IPW * BLK_BYTES;
     static constexpr int BAR_BYTES = DEPTH * IPW * 8;
-    static constexpr int REC_TOTAL = 32 * REC_BYTES;
+    // per-lane sum_weight accumulators live in shared memory (updated once per staged sample): registers are what limits
+    // this kernel's occupancy
+    static constexpr int SW_BYTES = 32 * PP * 8;
+    static constexpr int REC_TOTAL = 32 * REC_BYTES + SW_BYTES;
     static constexpr int WARP_BYTES = REC_TOTAL + RING_BYTES + BAR_BYTES;   // REC_TOTAL is a multiple of 16
 };
 
@@ -314,8 +317,11 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
     } while (!done);
 }
 
-// blocks per SM the fp32 16 x 16 instantiation is compiled for: 3 = 168 registers, no spills (2.87 ms on C3);
-// 4 = 128 registers with 36 B of spills inside the tap loop measured 5.31 ms
+// blocks per SM the fp32 16 x 16 instantiation is compiled for: 3 = 168 registers, 12 warps per SM.  At 4 (128 registers, 16
+// warps) round 1's kernel spilled 36 B inside the tap loop (5.31 ms against 2.87 ms on C3); round 2 moved the per-lane
+// sum_weight accumulators to shared memory and re-reads the uv scales / recomputes the plane offsets instead of keeping
+// them, which fits 128 registers without spills -- and is still slower (3.96 vs 3.08 ms through the wrapper): with fewer
+// registers ptxas keeps fewer of the 16 tap loads of a sample in flight, and that costs more than the extra warps give.
 #ifndef CNGI_AP_MINB_F32
 #define CNGI_AP_MINB_F32 3
 #endif
@@ -366,8 +372,7 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && W == 16) ? CNGI_AP_MIN
 #pragma unroll
     for (int ip = 0; ip < PP; ++ip)
         cf1[ip] = (chan_ok && ip < npol) ? (cf_b * p.n_cfc + (int)p.cf_c_map[c1]) * p.n_cfp + (int)p.cf_p_map[p0 + ip] : 0;
-    const double us1 = chan_ok ? p.scale[c1] : 0.0, vs1 = chan_ok ? p.scale[p.n_chan + c1] : 0.0;
-    double sw_acc[PP];
+    double *sw_acc = reinterpret_cast<double *>(wbuf + 32 * Cfg::REC_BYTES) + lane * PP;   // shared memory, this lane's slots
 #pragma unroll
     for (int ip = 0; ip < PP; ++ip) sw_acc[ip] = 0.0;
     long long carry_key = -1;
@@ -385,16 +390,13 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && W == 16) ? CNGI_AP_MIN
 #pragma unroll
         for (int ip = 0; ip < PP; ++ip) acc[j][ip].x = acc[j][ip].y = (T)0;
     int cur_plane = -1, lo_u = 0, lo_v = 0;
-    long long plane_off[PP];
-#pragma unroll
-    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = 0;
 
     auto flush_one = [&](int j, int u, int v) {
         const int cell = u * p.n_v + v;
 #pragma unroll
         for (int ip = 0; ip < PP; ++ip) {
             if (ip < npol && (acc[j][ip].x != (T)0 || acc[j][ip].y != (T)0)) {
-                red_add((CT *)p.grid + plane_off[ip] + cell, acc[j][ip]);
+                red_add((CT *)p.grid + ((long long)cur_plane * p.n_ip + apol[ip]) * plane_cells + cell, acc[j][ip]);
                 acc[j][ip].x = acc[j][ip].y = (T)0;   // clear only what was flushed (see standard_grid.cu)
             }
         }
@@ -419,7 +421,8 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && W == 16) ? CNGI_AP_MIN
                 const long long f = p.field[tb];
                 const int field_indx = f > -1 ? ap_find_field(p, f) : -1;
                 CellPos cp;
-                bool ok = field_indx >= 0 && locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], us1, vs1, p.n_u, p.n_v, cp);
+                bool ok = field_indx >= 0 && locate_centre(p.uvw[tb * 3], p.uvw[tb * 3 + 1], p.scale[c1], p.scale[p.n_chan + c1],
+                                                           p.n_u, p.n_v, cp);   // (uv scales re-read per round: L1 hits, 4 registers saved)
                 if (ok) ok = stamp_inside(cp.uc, cp.vc, p.max_support, p.n_u, p.n_v);
                 if (ok) {
                     const long long s = (tb * p.n_chan + c1) * p.n_pol + p0;
@@ -517,11 +520,7 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && W == 16) ? CNGI_AP_MIN
                         if (u < new_u || u >= new_u + W) flush_one(j, u, v);
                     }
                 }
-                if (new_plane) {
-#pragma unroll
-                    for (int ip = 0; ip < PP; ++ip) plane_off[ip] = ((long long)plane * p.n_ip + apol[ip]) * plane_cells;
-                    cur_plane = plane;
-                }
+                if (new_plane) cur_plane = plane;
                 lo_u = new_u, lo_v = new_v;
             }
             // taps: slot s of this lane's row <-> stamp column qu = (s - bu) mod W, stamp row q = (r2 - bv) mod W
