@@ -153,6 +153,7 @@ EXPORTS = [
     "cngi_b200_microbench_smem_atomics", "cngi_b200_direction_rotate", "cngi_b200_make_gcf",
     "cngi_b200_phase_gradient", "cngi_b200_image_to_grid", "cngi_b200_standard_grid_image_psf", "cngi_b200_make_pb",
     "cngi_b200_apply_flags", "cngi_b200_zarr_read_chunks", "cngi_b200_standard_grid_weighted",
+    "cngi_b200_multimem_reduce_f32", "cngi_b200_multimem_allreduce_f64",
 ]
 
 _lib = None
@@ -199,6 +200,8 @@ def lib():
         L.cngi_b200_phase_gradient.argtypes = [vp, i64, i64, i64, vp, vp]
         L.cngi_b200_zarr_read_chunks.argtypes = [C.POINTER(ZarrChunkJob), i64, vp, C.POINTER(i64), i32, i32, i32, vp, i32]
         L.cngi_b200_apply_flags.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+        L.cngi_b200_multimem_reduce_f32.argtypes = [vp, vp, i64, i32, vp]
+        L.cngi_b200_multimem_allreduce_f64.argtypes = [vp, i64, i32, i32, i32, vp]
         L.cngi_b200_microbench_red.argtypes = [vp, i64, i32, i32, i32, vp]
         L.cngi_b200_microbench_smem_atomics.argtypes = [vp, i32, i32, vp]
         _lib = L

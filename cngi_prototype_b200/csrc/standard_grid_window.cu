@@ -57,7 +57,12 @@ template <typename T, bool CPLX, int S, int PP, bool DUAL = false, bool IWF = fa
     // the density gather of round r + 1 can be ISSUED one round ahead of its use (it lands in registers: a cp.async gather
     // costs one shared-memory wavefront per lane, measured +64 wavefronts per round on the pipe that co-limits this kernel)
     static constexpr int IW_UV_BYTES = IWF ? ITER * 16 : 0;       // per ring slot
-    static constexpr int WARP_BYTES = REC_BYTES + 2 * RAW_BYTES + 2 * IW_UV_BYTES;
+#ifndef CNGI_WIN_SW_SMEM
+#define CNGI_WIN_SW_SMEM 0
+#endif
+    // CNGI_WIN_SW_SMEM: the per-lane sum_weight accumulators (fp64) live in shared memory instead of registers
+    static constexpr int SW_BYTES = CNGI_WIN_SW_SMEM ? 32 * PP * 8 * (DUAL ? 2 : 1) : 0;
+    static constexpr int WARP_BYTES = REC_BYTES + 2 * RAW_BYTES + 2 * IW_UV_BYTES + SW_BYTES;
     static constexpr int ROW_BYTES = W * (int)sizeof(T);
 };
 
@@ -315,7 +320,12 @@ std_grid_window_kernel(StdParams p)
         const bool chan_ok = c1 < c_end;
         const int a_chan1 = chan_ok ? chan_of(p, c1) : 0;
         const int sc1 = chan_ok ? c1 - p.c_lo : 0;   // row of the uv_scale table
+#if CNGI_WIN_SW_SMEM
+        double *sw_acc = reinterpret_cast<double *>(smem + L.wbuf + warp * Cfg::WARP_BYTES + Cfg::REC_BYTES + 2 * Cfg::RAW_BYTES +
+                                                    2 * Cfg::IW_UV_BYTES) + lane * PP;
+#else
         double sw_acc[PP];
+#endif
 #pragma unroll
         for (int ip = 0; ip < PP; ++ip) sw_acc[ip] = 0.0;
 
@@ -345,10 +355,14 @@ std_grid_window_kernel(StdParams p)
             gplane[ip] = (T *)p.grid +
                          ((long long)plane2 * p.n_ip + apol[ip < npol ? ip : 0]) * ((long long)p.n_u * p.n_v) * (CPLX ? 2 : 1);
         T *pplane[PP];   // psf planes of the fused pass (real)
+#if CNGI_WIN_SW_SMEM
+        double *psw_acc = sw_acc + (DUAL ? 32 * PP - 0 : 0);   // second half of the area (other lanes' slots lie in between)
+#else
         double psw_acc[PP];
+#endif
 #pragma unroll
         for (int ip = 0; ip < PP; ++ip) {
-            psw_acc[ip] = 0.0;
+            if (DUAL || !CNGI_WIN_SW_SMEM) psw_acc[ip] = 0.0;
             pplane[ip] = nullptr;
             if constexpr (DUAL)
                 pplane[ip] = (T *)p.psf_grid + ((long long)plane2 * p.n_ip + apol[ip < npol ? ip : 0]) * ((long long)p.n_u * p.n_v);

@@ -42,6 +42,94 @@ def init_nccl(device):
         dist.init_process_group("nccl", device_id=device)
 
 
+class _EventWork:
+    """The `.wait()` of an async collective for work that was queued on a side stream: the current stream waits for it."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class SymmetricCollectives:
+    """The two sums of the continuum step done INSIDE THE NVSWITCH (NVLS) by this library's own kernels instead of NCCL.
+
+    The accumulators are allocated in symmetric memory (`torch.distributed._symmetric_memory`: the same buffer on every
+    rank, mapped through one multicast address).  `reduce_grid` then costs ONE kernel on the root --
+    cngi_b200_multimem_reduce_f32: `multimem.ld_reduce` streams the sum over all ranks out of the switch into the root's
+    buffer -- and nothing at all on the other ranks (their HBM is read over NVLink; NCCL runs 24-32 blocks of 640 threads on
+    every rank).  `allreduce_density` reduces each rank's 1/N slice of pol plane 0 with `multimem.ld_reduce` and broadcasts
+    it with `multimem.st` (cngi_b200_multimem_allreduce_f64).  Ordering across ranks comes from the symmetric-memory barrier
+    (device side, on the collective stream): one before (every rank's partial result is complete) and one after (nobody
+    overwrites a buffer that is still being read).  Everything runs on one high-priority side stream in program order, so
+    the sums overlap the next kernels of the compute stream exactly like the NCCL calls they replace."""
+
+    def __init__(self, device, group=None, n_blocks=16):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem = symm_mem
+        self.device = device
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
+        self.n_blocks = int(n_blocks)
+        self.handles = {}
+
+    @staticmethod
+    def supported(device):
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            return bool(symm_mem._SymmetricMemory.has_multicast_support(torch.device(device).type, torch.device(device).index or 0))
+        except Exception:
+            return False
+
+    def empty(self, shape, dtype):
+        """A symmetric tensor (collective: every rank calls it with the same shape, in the same order)."""
+        t = self.symm_mem.empty(tuple(int(x) for x in shape), dtype=dtype, device=self.device)
+        h = self.symm_mem.rendezvous(t, self.group)
+        assert h.multicast_ptr != 0, "no multicast mapping (NVLS) for this buffer"
+        self.handles[t.data_ptr()] = h
+        return t
+
+    def _bracket(self, t, body):
+        """barrier -> body -> barrier on the collective stream, ordered behind the work queued so far on the current
+        stream; returns the work handle whose .wait() orders the current stream behind it."""
+        from . import _lib
+        h = self.handles[t.data_ptr()]
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            h.barrier(channel=0)
+            body(h, _lib)
+            h.barrier(channel=1)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        t.record_stream(self.stream)
+        return _EventWork(done)
+
+    def reduce_grid(self, grid, root):
+        """grid (symmetric, complex64 or float32, contiguous): the sum over ranks lands in the root's buffer."""
+        n_floats = grid.numel() * (2 if grid.is_complex() else 1)
+        assert grid.is_contiguous() and grid.element_size() * grid.numel() == 4 * n_floats
+
+        def body(h, _lib):
+            if self.rank == root:
+                _lib.check(_lib.lib().cngi_b200_multimem_reduce_f32(h.multicast_ptr, grid.data_ptr(), n_floats, self.n_blocks,
+                                                                    self.stream.cuda_stream), "cngi_b200_multimem_reduce_f32")
+        return self._bracket(grid, body)
+
+    def allreduce_density(self, density, n_doubles):
+        """the first n_doubles of `density` (symmetric, float64: pol plane 0 of a continuum density) summed on every rank"""
+        assert density.dtype == torch.float64 and density.is_contiguous()
+
+        def body(h, _lib):
+            _lib.check(_lib.lib().cngi_b200_multimem_allreduce_f64(h.multicast_ptr, int(n_doubles), self.rank, self.world,
+                                                                   self.n_blocks, self.stream.cuda_stream),
+                       "cngi_b200_multimem_allreduce_f64")
+        return self._bracket(density, body)
+
+
 def world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
@@ -138,7 +226,8 @@ class ContinuumPipeline:
         pipe.flush()            # results of the last step: pipe.last (grid, gsw valid on rank 0)
     """
 
-    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs, side_stream=None, fuse_weights=False, grid_reduce="root0"):
+    def __init__(self, ops, gp, gp_iw, iw_parms, cgk, make_bufs, side_stream=None, fuse_weights=False, grid_reduce="root0",
+                 symmetric=None):
         """side_stream (a high-priority CUDA stream, device tensors only): the whole imaging-weight chain of step k+1
         (density grid, all-reduce, Briggs factors, weight degrid -- memory-latency bound kernels) is issued there and
         runs CONCURRENTLY with the gridding kernel of step k on the current stream (issue bound): whenever a gridder
@@ -152,6 +241,9 @@ class ContinuumPipeline:
         assert grid_reduce in ("root0", "rotate", "allreduce", "none"), grid_reduce
         self.grid_reduce = grid_reduce
         self.last_root = 0
+        # symmetric: a SymmetricCollectives whose .empty() allocated the density / grid accumulators of make_bufs: the two
+        # big sums then go through the NVSwitch (multimem kernels of this library) instead of NCCL
+        self.symmetric = symmetric
         # fuse_weights: the weight degrid (A4) runs inside the gridder (ops.standard_grid_weighted) when the ops have it and
         # the support is 7 -- the imaging weights are then never written or re-read.  Measured on C2 (B200, fp32): the
         # gridder is issue bound, so the folded-in work costs what the separate pass costs (2.53 vs 2.50 ms per step): off
@@ -180,7 +272,11 @@ class ContinuumPipeline:
                                      first_pol_only=n_pol >= 2)
         if world()[1] > 1:   # every rank needs the full density for its own degrid; plane 0 carries all the information
             first = b.density[:, :1] if n_pol >= 2 else b.density
-            self.pend_density[slot] = [dist.all_reduce(first, async_op=True), dist.all_reduce(b.dsw, async_op=True)]
+            if self.symmetric is not None and b.density.shape[0] == 1:   # continuum: plane 0 is the head of the buffer
+                self.pend_density[slot] = [self.symmetric.allreduce_density(b.density, first.numel()),
+                                           dist.all_reduce(b.dsw, async_op=True)]
+            else:
+                self.pend_density[slot] = [dist.all_reduce(first, async_op=True), dist.all_reduce(b.dsw, async_op=True)]
 
     def _weights(self, d, b):
         """Briggs factors + weight degrid from the (all-reduced) density.  With n_pol >= 2 only pol plane 0 was gridded
@@ -238,7 +334,10 @@ class ContinuumPipeline:
         root = (self.n_grids % ws) if self.grid_reduce == "rotate" else 0
         self.n_grids += 1
         self.last_root = root
-        self.pend_grid[slot] = [dist.reduce(_as_real(b.grid), root, async_op=True), dist.reduce(b.gsw, root, async_op=True)]
+        if self.symmetric is not None and b.grid.dtype in (torch.complex64, torch.float32):
+            self.pend_grid[slot] = [self.symmetric.reduce_grid(b.grid, root), dist.reduce(b.gsw, root, async_op=True)]
+        else:
+            self.pend_grid[slot] = [dist.reduce(_as_real(b.grid), root, async_op=True), dist.reduce(b.gsw, root, async_op=True)]
 
     def _weights_on_side(self, d, slot):
         """The whole weight chain of a step on the side stream; returns (imaging weights, event that marks them ready)."""

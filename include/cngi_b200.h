@@ -434,6 +434,19 @@ int cngi_b200_zarr_read_chunks(const cngi_zarr_chunk_job *jobs, int64_t n_jobs, 
  * ---------------------------------------------------------------------------------------------- */
 int cngi_b200_standard_grid_host(const cngi_std_grid_args *args_host, int64_t time_chunk);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU sums of uv-grids through an NVSwitch multicast mapping (NVLS), replacing the reference's
+ * tree sum over chunks (_standard_grid.py:109-120) for partial grids that live on different GPUs.
+ * `multicast_ptr` is the multicast address of a buffer that every rank allocated symmetrically (e.g.
+ * torch.distributed._symmetric_memory); the caller orders the ranks (barrier before: all partial grids
+ * complete; barrier after: nobody overwrites a buffer that is still being read).
+ *   reduce:     dst[i] = sum over ranks of buffer[i]      (run by the root only; 16-byte aligned, n % 4 == 0)
+ *   allreduce:  buffer[i] = sum over ranks, on every rank (each rank handles its 1/world_size slice)
+ * ---------------------------------------------------------------------------------------------- */
+int cngi_b200_multimem_reduce_f32(const void *multicast_ptr, void *dst, int64_t n_floats, int32_t n_blocks, void *stream);
+int cngi_b200_multimem_allreduce_f64(void *multicast_ptr, int64_t n_doubles, int32_t rank, int32_t world_size,
+                                     int32_t n_blocks, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

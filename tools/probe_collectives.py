@@ -67,8 +67,42 @@ def main():
                                grid=torch.empty((1, 2, n, n), dtype=torch.complex64, device=dev),
                                gsw=torch.empty((1, 2), dtype=torch.float64, device=dev))
     modes = os.environ.get("PROBE_MODES", "root0,rotate,allreduce,none").split(",")
+    sym = D.SymmetricCollectives(dev) if D.SymmetricCollectives.supported(dev) else None
+    out["multicast_supported"] = sym is not None
+
+    def make_bufs_sym():
+        return SimpleNamespace(density=sym.empty((1, 2, n, n), torch.float64), dsw=torch.empty((1, 2), dtype=torch.float64, device=dev),
+                               grid=sym.empty((1, 2, n, n), torch.complex64), gsw=torch.empty((1, 2), dtype=torch.float64, device=dev))
+    if sym is not None and "multimem" in modes:
+        # correctness of the two switch-side sums against NCCL, then their stand-alone times
+        a = sym.empty((1, 2, n, n), torch.complex64)
+        ref = torch.empty_like(a)
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        torch.view_as_real(a).normal_(generator=g)
+        ref.copy_(a)
+        dist.reduce(torch.view_as_real(ref), 0)
+        sym.reduce_grid(a, 0).wait()
+        torch.cuda.synchronize()
+        if rank == 0:
+            out["multimem_reduce_max_rel_diff_vs_nccl"] = float((a - ref).abs().max() / ref.abs().max())
+        dd = sym.empty((1, 2, n, n), torch.float64)
+        dd.normal_(generator=g)
+        dref = dd[:, :1].clone()
+        dist.all_reduce(dref)
+        sym.allreduce_density(dd, n * n).wait()
+        torch.cuda.synchronize()
+        out["multimem_allreduce_max_rel_diff_vs_nccl"] = float((dd[:, :1] - dref).abs().max() / dref.abs().max())
+        out["multimem_reduce_grid_268MB_ms"] = timed(lambda: sym.reduce_grid(a, 0).wait())
+        out["multimem_allreduce_density_134MB_ms"] = timed(lambda: sym.allreduce_density(dd, n * n).wait())
+        del a, ref, dd, dref
     for mode in modes:
-        pipe = D.ContinuumPipeline(D.cuda_ops(), gp, gp_iw, dict(weighting="briggs", robust=0.5), cgk, make_bufs, grid_reduce=mode)
+        if mode == "multimem":
+            if sym is None:
+                continue
+            pipe = D.ContinuumPipeline(D.cuda_ops(), gp, gp_iw, dict(weighting="briggs", robust=0.5), cgk, make_bufs_sym,
+                                       symmetric=sym)
+        else:
+            pipe = D.ContinuumPipeline(D.cuda_ops(), gp, gp_iw, dict(weighting="briggs", robust=0.5), cgk, make_bufs, grid_reduce=mode)
 
         def run():
             for _ in range(10):
