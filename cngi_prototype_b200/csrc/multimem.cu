@@ -15,9 +15,26 @@
 
 namespace cngi {
 
+// A multimem.ld_reduce is a round trip through the switch (microseconds): bandwidth comes from bytes in flight, so every
+// thread keeps U independent loads outstanding (32 blocks x 512 threads x 8 x 16 B = 2 MB).
+constexpr int kMmUnroll = 8;
+
 __global__ void __launch_bounds__(512) mm_reduce_f32_kernel(const float *mc, float *dst, long long n4)   // n4 = float4 count
 {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kMmUnroll - 1) * stride < n4; i += kMmUnroll * stride) {
+        float4 v[kMmUnroll];
+#pragma unroll
+        for (int u = 0; u < kMmUnroll; ++u)
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                         : "l"(mc + 4 * (i + u * stride))
+                         : "memory");
+#pragma unroll
+        for (int u = 0; u < kMmUnroll; ++u) reinterpret_cast<float4 *>(dst)[i + u * stride] = v[u];
+    }
+    for (; i < n4; i += stride) {
         float4 v;
         asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
                      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
@@ -30,7 +47,18 @@ __global__ void __launch_bounds__(512) mm_reduce_f32_kernel(const float *mc, flo
 // all-reduce of this rank's slice [lo, hi) (in doubles): sum through the switch, broadcast through the switch
 __global__ void __launch_bounds__(512) mm_allreduce_f64_kernel(double *mc, long long lo, long long hi)
 {
-    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kMmUnroll - 1) * stride < hi; i += kMmUnroll * stride) {
+        double v[kMmUnroll];
+#pragma unroll
+        for (int u = 0; u < kMmUnroll; ++u)
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v[u]) : "l"(mc + i + u * stride) : "memory");
+#pragma unroll
+        for (int u = 0; u < kMmUnroll; ++u)
+            asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i + u * stride), "d"(v[u]) : "memory");
+    }
+    for (; i < hi; i += stride) {
         double v;
         asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(mc + i) : "memory");
         asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v) : "memory");
@@ -46,7 +74,7 @@ extern "C" int cngi_b200_multimem_reduce_f32(const void *multicast_ptr, void *ds
     CNGI_REQUIRE(n_floats >= 0 && n_floats % 4 == 0 && ((uintptr_t)multicast_ptr % 16) == 0 && ((uintptr_t)dst % 16) == 0,
                  "multimem_reduce_f32: the range must be 16-byte aligned and a multiple of 4 floats");
     if (n_floats == 0) return CNGI_OK;
-    if (n_blocks <= 0) n_blocks = 16;
+    if (n_blocks <= 0) n_blocks = 32;
     mm_reduce_f32_kernel<<<(unsigned)n_blocks, 512, 0, (cudaStream_t)stream>>>((const float *)multicast_ptr, (float *)dst, n_floats / 4);
     CNGI_CUDA_TRY(cudaGetLastError());
     return CNGI_OK;
@@ -61,7 +89,7 @@ extern "C" int cngi_b200_multimem_allreduce_f64(void *multicast_ptr, int64_t n_d
     const int64_t per = (n_doubles + world_size - 1) / world_size;
     const int64_t lo = std::min<int64_t>(n_doubles, per * rank), hi = std::min<int64_t>(n_doubles, lo + per);
     if (hi <= lo) return CNGI_OK;
-    if (n_blocks <= 0) n_blocks = 16;
+    if (n_blocks <= 0) n_blocks = 32;
     mm_allreduce_f64_kernel<<<(unsigned)n_blocks, 512, 0, (cudaStream_t)stream>>>((double *)multicast_ptr, lo, hi);
     CNGI_CUDA_TRY(cudaGetLastError());
     return CNGI_OK;

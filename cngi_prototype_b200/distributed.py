@@ -63,9 +63,15 @@ class SymmetricCollectives:
     it with `multimem.st` (cngi_b200_multimem_allreduce_f64).  Ordering across ranks comes from the symmetric-memory barrier
     (device side, on the collective stream): one before (every rank's partial result is complete) and one after (nobody
     overwrites a buffer that is still being read).  Everything runs on one high-priority side stream in program order, so
-    the sums overlap the next kernels of the compute stream exactly like the NCCL calls they replace."""
+    the sums overlap the next kernels of the compute stream exactly like the NCCL calls they replace.
 
-    def __init__(self, device, group=None, n_blocks=16):
+    Measured (tools/probe_collectives.py; results identical to NCCL's to 1e-7 / bit for bit): on 8 B200s the all-reduce of
+    the 134 MB density takes 0.31 ms (NCCL 0.40 ms), the reduce of the 268 MB grid 0.72 ms (NCCL 0.45 ms: the root has to pull
+    the whole grid through its own NVLink port, where NCCL's ring spreads the summation over every rank's SMs and links), and
+    the pipelined step 2.85 ms against 2.76 ms with NCCL on a high-priority stream -- so NCCL stays the default and this is
+    opt-in (ContinuumPipeline(symmetric=...)); on 2 GPUs there is no switch-side advantage at all (2.78 vs 2.68 ms)."""
+
+    def __init__(self, device, group=None, n_blocks=0):
         import torch.distributed._symmetric_memory as symm_mem
         self.symm_mem = symm_mem
         self.device = device
@@ -79,7 +85,8 @@ class SymmetricCollectives:
     def supported(device):
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            return bool(symm_mem._SymmetricMemory.has_multicast_support(torch.device(device).type, torch.device(device).index or 0))
+            from torch._C._autograd import DeviceType
+            return bool(symm_mem._SymmetricMemory.has_multicast_support(DeviceType.CUDA, torch.device(device).index or 0))
         except Exception:
             return False
 

@@ -67,7 +67,7 @@ def main():
                                grid=torch.empty((1, 2, n, n), dtype=torch.complex64, device=dev),
                                gsw=torch.empty((1, 2), dtype=torch.float64, device=dev))
     modes = os.environ.get("PROBE_MODES", "root0,rotate,allreduce,none").split(",")
-    sym = D.SymmetricCollectives(dev) if D.SymmetricCollectives.supported(dev) else None
+    sym = D.SymmetricCollectives(dev, n_blocks=int(os.environ.get("PROBE_MM_BLOCKS", "0"))) if D.SymmetricCollectives.supported(dev) else None
     out["multicast_supported"] = sym is not None
 
     def make_bufs_sym():
