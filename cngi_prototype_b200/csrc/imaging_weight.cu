@@ -97,6 +97,15 @@ template <typename T, int G, int NP> __global__ void __launch_bounds__(256) iw_g
         const double uu = p.uvw[tb * 3], vv = p.uvw[tb * 3 + 1];
         const T *wrow = (const T *)p.weight + (tb * p.n_chan + c0) * n_pol;
         double wd[G];
+        if (NP == 2 && sizeof(T) == 4 && G >= 2 && ng == G && ((reinterpret_cast<uintptr_t>(wrow) & 15) == 0)) {
+            // the thread's G channels x 2 pols are 8 G contiguous bytes: 128-bit loads (two channels each)
+#pragma unroll
+            for (int g = 0; g < G; g += 2) {
+                const float4 w4 = *reinterpret_cast<const float4 *>(wrow + g * 2);
+                wd[g] = __dmul_rn(__dadd_rn((double)w4.x, (double)w4.y), 0.5);
+                wd[g + 1] = __dmul_rn(__dadd_rn((double)w4.z, (double)w4.w), 0.5);
+            }
+        } else
 #pragma unroll
         for (int g = 0; g < G; ++g) {   // issue all loads of the row before the dependent math
             wd[g] = 0.0;
