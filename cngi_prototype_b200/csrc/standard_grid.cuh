@@ -83,5 +83,8 @@ bool window_kernel_supported(const cngi_std_grid_args *a, int table_len);
 int launch_window(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
 int launch_window_dual(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
 int launch_window_iw(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
+// standard_grid_window16_f32.cu / _f64.cu: supports 9 / 11 / 13 / 15
+int launch_window16_f32(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
+int launch_window16_f64(StdParams p, const cngi_std_grid_args *a, cudaStream_t st);
 
 }  // namespace cngi

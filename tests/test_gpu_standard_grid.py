@@ -109,10 +109,11 @@ def test_fused_flag_equals_nan_data(sg, oracle):
         _check(g, s, g_ref, s_ref, TOL["f64"])
 
 
-@pytest.mark.parametrize("support,oversampling", [(3, 20), (5, 50), (9, 100), (11, 30)])
+@pytest.mark.parametrize("support,oversampling", [(3, 20), (5, 50), (9, 100), (11, 30), (13, 40), (15, 25), (17, 10)])
 @pytest.mark.parametrize("n_pol", [1, 2, 3, 4])
 def test_supports_and_pol_counts(sg, oracle, support, oversampling, n_pol):
-    """Track kernel instantiations (3,5,7,9), the naive fallback (11), odd pol counts, ragged channel spans."""
+    """The reference is support-generic (_standard_grid.py:344-360): 8-wide register windows (3, 5), 16-wide ones (9, 11,
+    13, 15), the per-sample fallback (17), odd pol counts, ragged channel spans."""
     from cngi_prototype_b200 import synth
     d = synth.make_vis_set(7, 33, 5, n_pol, 1e9, 1.2e9, 300.0, 200.0, seed=support * 10 + n_pol)
     cgk = oracle._create_prolate_spheroidal_kernel_1D(oversampling, support)
@@ -121,6 +122,30 @@ def test_supports_and_pol_counts(sg, oracle, support, oversampling, n_pol):
         g_ref, s_ref = oracle._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp)
         g, s = sg._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp)
         _check(g, s, g_ref, s_ref, TOL["f64"])
+
+
+@pytest.mark.parametrize("support", [9, 11, 13, 15])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_wide_window_kernel_supports_9_to_15(sg, oracle, support, prec):
+    """16-wide register windows (csrc/standard_grid_window16_*.cu: doubled tap rows + sub-vector rotation copies): image and
+    psf mode, cube and continuum, forced through ALGO_WINDOW, time-chunked accumulation, odd non-square grid, against the
+    oracle; support 9 also against the track kernel it replaces as the default."""
+    from cngi_prototype_b200 import synth
+    d = synth.make_vis_set(9, 41, 19, 2, 1e9, 1.15e9, 300.0, 150.0, seed=100 + support, dtype=prec)
+    cgk = oracle._create_prolate_spheroidal_kernel_1D(100, support)
+    for mode in ("cube", "continuum"):
+        gp = synth.grid_parms_for(96, d["cell"], chan_mode=mode, support=support, oversampling=100)
+        gp["image_size_padded"] = np.array([117, 96])
+        g_ref, s_ref = oracle._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp)
+        g, s = sg._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp, algorithm=ALGOS["window"])
+        _check(g, s, g_ref, s_ref, TOL[prec])
+        if support == 9:
+            g_t, s_t = sg._standard_grid_numpy_wrap(d["vis"], d["uvw"], d["weight"], d["freq_chan"], cgk, gp, algorithm=ALGOS["track"])
+            _check(g_t, s_t, g_ref, s_ref, TOL[prec])
+        gpp = dict(gp, do_psf=True, complex_grid=False)
+        p_ref, ps_ref = oracle._standard_grid_psf_numpy_wrap(d["uvw"], d["weight"], d["freq_chan"], cgk, gpp)
+        pg, ps = sg._standard_grid_psf_numpy_wrap(d["uvw"], d["weight"], d["freq_chan"], cgk, gpp, algorithm=ALGOS["window"])
+        _check(pg, ps, p_ref, ps_ref, TOL[prec])
 
 
 @pytest.mark.parametrize("algo", ["track", "shift", "window"])
