@@ -71,6 +71,8 @@ def parse():
     ap.add_argument("--cube-samples-per-gpu", type=float, default=2.5e9)
     ap.add_argument("--cube-chan-chunk", type=int, default=8)
     ap.add_argument("--cube-steps", type=int, default=2)
+    ap.add_argument("--cube-overlap", type=int, default=0, choices=[0, 1],
+                    help="time_split = 1: grid chunk j + 1 while chunk j is transformed on a side stream (two grid buffers)")
     ap.add_argument("--side-stream", action="store_true",
                     help="issue the imaging-weight chain of step k+1 on a concurrent high-priority stream")
     ap.add_argument("--fuse-weights", action="store_true",
@@ -381,7 +383,8 @@ def cube_record(a, dev, rank, world, dist, time_split, groups):
 
     def one(tm=None):
         return D.cube_imaging(ops, d, gp, cgk, chan_chunk=a.cube_chan_chunk, time_split=time_split, groups=groups,
-                              presharded=True, timer=tm, keep_image=False, rotate_roots=True)
+                              presharded=True, timer=tm, keep_image=False, rotate_roots=True,
+                              overlap=bool(a.cube_overlap) and time_split == 1)
 
     one()                                    # warm-up: cuFFT plan, allocator pools
     torch.cuda.synchronize()
@@ -421,7 +424,7 @@ def cube_record(a, dev, rank, world, dist, time_split, groups):
            "phase_ms_max_over_ranks": {"grid": g_ms, "reduce_incl_wait_for_partner": r_ms, "image_fft_crop_correct": i_ms},
            "fft_share": i_ms / ms if ms else None,
            "gridding_vis_per_s_per_gpu": n_samples / (g_ms * 1e-3) if g_ms else None,
-           "sum_weight_finite_positive": ok}
+           "sum_weight_finite_positive": ok, "overlap": bool(a.cube_overlap) and time_split == 1}
     spp = tj.get("cube_red_sectors_per_sample")
     if spp and g_ms:
         rec["red_sectors_per_s"] = spp * n_samples / (g_ms * 1e-3)

@@ -7,8 +7,17 @@
 // track through time and run-length accumulates while the (cell, conjugate cell) pair is unchanged, so a
 // slowly moving baseline issues one pair of REDG.F64 per cell crossing rather than per sample.
 #include "common.cuh"
+#include <type_traits>
+#include <cstdlib>
 
 namespace cngi {
+
+static inline bool env_flag(const char *name)   // development switches (A/B timing of kernel generations)
+{
+    static_assert(true, "");
+    const char *e = getenv(name);
+    return e && e[0] && e[0] != '0';
+}
 
 struct IwParams {
     int n_time, n_baseline, n_chan, n_pol;
@@ -393,6 +402,119 @@ template <typename T, int NP, int R> __global__ void __launch_bounds__(256) iw_d
     }
 }
 
+
+// Product path of A4 (identity pol_map, 1 or 2 pols, density smaller than 2^31 elements): the mlp kernel above retired 180 warp
+// instructions per sample at 72 % issue utilisation (ncu, profiles/r01_imaging_weight_kernels.txt) -- 64-bit stride
+// arithmetic for every gather, per-sample range predicates on every address, a branch around every step.  Here the cell
+// index is 32-bit, addresses advance by a constant stride, range checks exist only in the launch's last row block, and the
+// three passes (loads / cells + gathers / Briggs division + stores) are straight-line code with selects: a sample that is off
+// the grid gathers cell 0 and discards it.  Results are bit-identical to iw_degrid_kernel's.
+template <typename T, int NP, int R, bool SHARED> __global__ void __launch_bounds__(256) iw_degrid_fast_kernel(IwParams p)
+{
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= p.n_chan) return;
+    const long long rows = (long long)p.n_time * p.n_baseline;
+    const long long row0 = ((long long)blockIdx.x * R) * blockDim.y + threadIdx.y;   // rows row0 + k * blockDim.y
+    const double us = p.scale[c], vs = p.scale[p.n_chan + c];
+    const int a_chan = iw_chan_of(p, c);
+    double f0[NP], f1[NP];
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) {
+        f0[ip] = p.bf[a_chan * p.n_ip + ip];
+        f1[ip] = p.bf[((long long)p.n_ic + a_chan) * p.n_ip + ip];
+    }
+    const double mid_u = (double)(p.n_u / 2), mid_v = (double)(p.n_v / 2);
+    const int ds_u = (int)p.ds_u, ds_v = (int)p.ds_v, ds_p = (int)p.ds_p;
+    const double *dens = p.density + (long long)a_chan * p.ds_c;
+    asm volatile("" : "+l"(dens));   // keep the channel offset folded into the base: ptxas otherwise redoes the 64-bit sum per gather
+    const long long e_stride = (long long)blockDim.y * p.n_chan * NP;
+    const T *const wp = (const T *)p.weight + (row0 * p.n_chan + c) * NP;
+    T *const op = (T *)p.out + (row0 * p.n_chan + c) * NP;
+    const double *const uvp = p.uvw + row0 * 3;
+    const int uv_stride = (int)blockDim.y * 3;
+
+    auto body = [&](auto checked) {
+        constexpr bool CHK = decltype(checked)::value;   // only the last row block of the launch can run past `rows`
+        double uu[R], vv[R];
+        T nat[R][NP];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {   // pass 1: independent loads
+            const bool live = !CHK || (row0 + (long long)k * blockDim.y < rows);
+            uu[k] = vv[k] = 0.0;
+#pragma unroll
+            for (int ip = 0; ip < NP; ++ip) nat[k][ip] = (T)0;
+            if (live) {
+                uu[k] = uvp[k * uv_stride];
+                vv[k] = uvp[k * uv_stride + 1];
+                const T *np_ = wp + k * e_stride;
+                if (NP == 2) {
+                    if (sizeof(T) == 4) {
+                        const float2 w2 = *reinterpret_cast<const float2 *>(np_);
+                        nat[k][0] = (T)w2.x, nat[k][NP - 1] = (T)w2.y;
+                    } else {
+                        const double2 w2 = *reinterpret_cast<const double2 *>(np_);
+                        nat[k][0] = (T)w2.x, nat[k][NP - 1] = (T)w2.y;
+                    }
+                } else {
+                    nat[k][0] = np_[0];
+                }
+            }
+        }
+        double rho[R][SHARED ? 1 : NP];
+        bool ok[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {   // pass 2: cells (locate_centre + stamp_inside, branch-free), then the gathers
+            const double u = __dmul_rn(uu[k], us), v = __dmul_rn(vv[k], vs);
+            const int uc = __double2int_rz(__dadd_rn(__dadd_rn(u, mid_u), 0.5));
+            const int vc = __double2int_rz(__dadd_rn(__dadd_rn(v, mid_v), 0.5));
+            ok[k] = (u == u) && (v == v) && (uc < p.n_u) && (vc < p.n_v) && (uc >= 0) && (vc >= 0);
+            const int cell = ok[k] ? uc * ds_u + vc * ds_v : 0;
+#pragma unroll
+            for (int ip = 0; ip < (SHARED ? 1 : NP); ++ip) rho[k][ip] = dens[cell + ip * ds_p];
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {   // pass 3: Briggs division, stores
+            if (CHK && !(row0 + (long long)k * blockDim.y < rows)) continue;
+            T res[NP];
+            const double avg = NP == 2 ? __dmul_rn(__dadd_rn((double)nat[k][0], (double)nat[k][NP - 1]), 0.5) : 0.0;   // == /2.0
+            if (SHARED) {   // same density value and factors for both pols: one division
+                const double r = rho[k][0];
+                const double den = __dadd_rn(__dmul_rn(f0[0], r), f1[0]);   // :515-516
+                const double quo = sizeof(T) == 4 ? (double)__fdiv_rn((float)avg, (float)den) : __ddiv_rn(avg, den);
+                const double q = (ok[k] && r == r && r != 0.0) ? quo : avg;
+#pragma unroll
+                for (int ip = 0; ip < NP; ++ip) {
+                    const double w = (double)nat[k][ip];
+                    res[ip] = (T)(ok[k] ? ((w == w && w != 0.0) ? q : avg) : 0.0);
+                }
+            } else {
+#pragma unroll
+                for (int ip = 0; ip < NP; ++ip) {
+                    const double w = (double)nat[k][ip], r = rho[k][SHARED ? 0 : ip];
+                    const double num = NP == 2 ? avg : w;   // :508-511
+                    const double den = __dadd_rn(__dmul_rn(f0[ip], r), f1[ip]);
+                    const double quo = sizeof(T) == 4 ? (double)__fdiv_rn((float)num, (float)den) : __ddiv_rn(num, den);
+                    const bool divide = (w == w) && w != 0.0 && (r == r) && r != 0.0;
+                    res[ip] = (T)(ok[k] ? (divide ? quo : num) : 0.0);   // off-grid or NaN uv: 0 (:460,493,502)
+                }
+            }
+            T *out = op + k * e_stride;
+            if (NP == 2) {
+                if (sizeof(T) == 4)
+                    *reinterpret_cast<float2 *>(out) = make_float2((float)res[0], (float)res[NP - 1]);
+                else
+                    *reinterpret_cast<double2 *>(out) = make_double2((double)res[0], (double)res[NP - 1]);
+            } else {
+                out[0] = res[0];
+            }
+        }
+    };
+    if (row0 + (long long)(R - 1) * blockDim.y < rows)
+        body(std::false_type{});
+    else
+        body(std::true_type{});
+}
+
 }  // namespace cngi
 
 extern "C" int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *a, void *stream)
@@ -519,9 +641,16 @@ extern "C" int cngi_b200_imaging_weight_degrid(const cngi_iw_degrid_args *a, voi
     p.scale = scale;
     constexpr int kRows = 4;   // samples per thread in the fast path
     const dim3 grid_mlp((unsigned)ceil_div(rows, (long long)block.y * kRows), (unsigned)gy);
+    // 32-bit cell indices: every (u, v, pol) offset inside one imaging channel's planes must fit an int
+    const long long span = (long long)(p.n_u - 1) * p.ds_u + (long long)(p.n_v - 1) * p.ds_v + (long long)(p.n_pol - 1) * p.ds_p;
+    const bool fast = np && p.ds_u >= 0 && p.ds_v >= 0 && p.ds_p >= 0 && span < (1LL << 31) && p.n_u > 0 && p.n_v > 0 &&
+                      !env_flag("CNGI_IW_DEGRID_MLP");
 #define CNGI_DG_LAUNCH(TT)                                                                      \
     do {                                                                                        \
-        if (np == 2) iw_degrid_mlp_kernel<TT, 2, kRows><<<grid_mlp, block, 0, st>>>(p);         \
+        if (fast && np == 2 && p.pol_shared) iw_degrid_fast_kernel<TT, 2, kRows, true><<<grid_mlp, block, 0, st>>>(p);  \
+        else if (fast && np == 2) iw_degrid_fast_kernel<TT, 2, kRows, false><<<grid_mlp, block, 0, st>>>(p);            \
+        else if (fast) iw_degrid_fast_kernel<TT, 1, kRows, false><<<grid_mlp, block, 0, st>>>(p);                       \
+        else if (np == 2) iw_degrid_mlp_kernel<TT, 2, kRows><<<grid_mlp, block, 0, st>>>(p);    \
         else if (np == 1) iw_degrid_mlp_kernel<TT, 1, kRows><<<grid_mlp, block, 0, st>>>(p);    \
         else iw_degrid_kernel<TT, 0><<<grid, block, 0, st>>>(p);                                \
     } while (0)

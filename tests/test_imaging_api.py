@@ -114,6 +114,13 @@ def test_channel_chunked_cube_equals_unchunked(oracle):
     img, sw, pimg, psw, _ = D.cube_imaging(ops, T, g, cgk, chan_chunk=3, with_psf=True)
     assert rel_err(img.cpu().numpy(), ref["IMAGE"]) <= 1e-12 and rel_err(pimg.cpu().numpy(), psf["PSF"]) <= 1e-12
     assert rel_err(psw.cpu().numpy(), psf["PSF_SUM_WEIGHT"]) <= 1e-12
+    # gridding of chunk j + 1 under the transform of chunk j (two grid buffers, side stream): same cubes
+    for kw in ({}, {"with_psf": True}):
+        res = D.cube_imaging(ops, T, g, cgk, chan_chunk=2, overlap=True, **kw)
+        torch.cuda.synchronize()
+        assert rel_err(res[0].cpu().numpy(), ref["IMAGE"]) <= 1e-12 and rel_err(res[1].cpu().numpy(), ref["SUM_WEIGHT"]) <= 1e-12
+        if kw:
+            assert rel_err(res[2].cpu().numpy(), psf["PSF"]) <= 1e-12
 
 
 @pytest.mark.gpu
