@@ -173,6 +173,166 @@ template <typename T, int G, int NP> __global__ void __launch_bounds__(256) iw_g
     }
 }
 
+// Product path of A2 (identity pol_map, 1 or 2 pols, whole channel groups, 16-byte aligned rows).  ncu on the kernel above
+// (profiles/r01_imaging_weight_kernels.txt): 38 % issue utilisation, 65 % of the stall samples on the long scoreboard -- a
+// time step's weights were loaded right before their use -- and ~85 warp instructions per sample, because every sample ran
+// its own chain of early-outs with the flush inlined behind it.  Here the NEXT time step's weights and (u, v) are loaded
+// before the current one is processed, all G cells of a step are located first in straight-line code (G independent fp64
+// chains), and only then merged into the running (cell, conjugate cell) accumulator with integer compares.
+#ifndef CNGI_IW_GRID_HALF
+#define CNGI_IW_GRID_HALF 4
+#endif
+#ifndef CNGI_IW_GRID_MINB
+#define CNGI_IW_GRID_MINB 2
+#endif
+template <typename T> struct IwPair;
+template <> struct IwPair<float> { using type = float2; };
+template <> struct IwPair<double> { using type = double2; };
+
+template <typename T, int G, int NP> __global__ void __launch_bounds__(256, CNGI_IW_GRID_MINB) iw_grid_fast_kernel(IwParams p)
+{
+    using V2 = typename IwPair<T>::type;
+    const long long plane_cells = (long long)p.n_u * p.n_v;
+    const int n_cg = p.n_chan / G;
+    const long long n_items = (long long)p.n_seg * p.n_baseline * n_cg;
+    long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = item < n_items;   // no early return: the warp reduces sum_weight together at the end
+    if (!in_range) item = 0;
+    const int cg = (int)(item % n_cg);
+    const long long r = item / n_cg;
+    const int b = (int)(r % p.n_baseline);
+    const int seg = (int)(r / p.n_baseline);
+    const int t_lo = seg * p.seg_len, t_hi = in_range ? min(p.n_time, t_lo + p.seg_len) : t_lo;
+    const int c0 = cg * G;
+    const int plane = (G > 1) ? 0 : iw_chan_of(p, c0);   // G > 1 <=> continuum
+    double *const plane_base = p.density + (long long)plane * p.n_ip * plane_cells;
+    const double mid_u = (double)(p.n_u / 2), mid_v = (double)(p.n_v / 2);
+    // uv_scale table, transposed in shared memory to [u | v][g][cg]: the lanes of a warp (consecutive cg) read consecutive
+    // doubles.  Straight from the global table the 16 loads of a time step were strided by G doubles across the lanes --
+    // 8 cache lines per request, 28 % of the stall samples of the first version of this kernel (ncu).
+    extern __shared__ double iw_scale_sm[];
+    for (int i = threadIdx.x; i < 2 * p.n_chan; i += blockDim.x) {
+        const int uv = i / p.n_chan, c = i - uv * p.n_chan;
+        iw_scale_sm[uv * p.n_chan + (c % G) * n_cg + c / G] = p.scale[i];
+    }
+    __syncthreads();
+    const double *us = iw_scale_sm + cg, *vs = iw_scale_sm + p.n_chan + cg;   // channel c0 + g at [g * n_cg]
+
+    const long long row_stride = (long long)p.n_baseline * p.n_chan * NP;
+    const T *wrow = (const T *)p.weight + (((long long)t_lo * p.n_baseline + b) * p.n_chan + c0) * NP;
+    const double *uvp = p.uvw + ((long long)t_lo * p.n_baseline + b) * 3;
+    const long long uv_stride = (long long)p.n_baseline * 3;
+
+    // Running (cell, conjugate cell, sum) of the lane.  (Measured and dropped: holding a retired triple back until some lane of
+    // the warp needs the slot again, so that more lanes share a REDG -- 2.5 M -> 1.0 M reduction instructions, same time:
+    // the kernel is not bound by the reductions; plane 0 + plane 1 instead of plane 0 alone costs 0.03 ms.)
+    int cur = -1, cur_c = -1;     // (-1: none / off the grid)
+    double acc = 0.0, sw = 0.0;
+    const bool both_planes = NP == 2 && p.n_pol_out == 2;
+    auto reduce_out = [&](int cell, int ccell, double v) {   // only reads: the state changes around it are selects
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) {
+            if (ip == 0 || both_planes) {
+                atomicAdd(plane_base + ip * plane_cells + cell, v);
+                if (ccell >= 0) atomicAdd(plane_base + ip * plane_cells + ccell, v);
+            }
+        }
+    };
+
+    T raw[G][NP];          // the NEXT time step's weights
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) raw[g][ip] = (T)0;
+    double nu = 0.0, nv = 0.0;
+    auto load_row = [&]() {
+        nu = uvp[0], nv = uvp[1];
+        if (NP == 2 && sizeof(T) == 4 && G >= 2) {   // two channels x 2 pols per 128-bit load
+#pragma unroll
+            for (int g = 0; g < G; g += 2) {
+                const float4 w4 = *reinterpret_cast<const float4 *>(wrow + g * 2);
+                raw[g][0] = (T)w4.x, raw[g][NP - 1] = (T)w4.y, raw[g + 1 < G ? g + 1 : g][0] = (T)w4.z,
+                raw[g + 1 < G ? g + 1 : g][NP - 1] = (T)w4.w;
+            }
+        } else if (NP == 2) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const V2 w2 = *reinterpret_cast<const V2 *>(wrow + g * 2);
+                raw[g][0] = w2.x, raw[g][NP - 1] = w2.y;
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g) raw[g][0] = wrow[g];
+        }
+        wrow += row_stride;
+        uvp += uv_stride;
+    };
+
+    if (t_lo < t_hi) load_row();
+    for (int t = t_lo; t < t_hi; ++t) {
+        T w_now[G][NP];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int ip = 0; ip < NP; ++ip) w_now[g][ip] = raw[g][ip];
+        const double uu = nu, vv = nv;
+        if (t + 1 < t_hi) load_row();   // in flight while this step is processed
+        // ---- H cells at a time, branch-free (locate_centre + stamp_inside + the conjugate cell, :299-318), then merged into
+        //      the running accumulator; boustrophedon so that consecutive samples stay uv neighbours ----
+        constexpr int H = G < CNGI_IW_GRID_HALF ? G : CNGI_IW_GRID_HALF;
+        const bool back = (t - t_lo) & 1;
+#pragma unroll
+        for (int hh = 0; hh < G / H; ++hh) {
+            int cell[H], ccell[H];
+            double wv[H];
+            auto locate = [&](int k, int g) {   // k, g compile-time constants after unrolling
+                const double w = NP == 2 ? __dmul_rn(__dadd_rn((double)w_now[g][0], (double)w_now[g][NP - 1]), 0.5)   // == /2.0 exactly
+                                         : (double)w_now[g][0];
+                const double u = __dmul_rn(uu, us[g * n_cg]), v = __dmul_rn(vv, vs[g * n_cg]);
+                const int uc = __double2int_rz(__dadd_rn(__dadd_rn(u, mid_u), 0.5));
+                const int vc = __double2int_rz(__dadd_rn(__dadd_rn(v, mid_v), 0.5));
+                const int cu = __double2int_rz(__dadd_rn(__dadd_rn(-u, mid_u), 0.5));   // int(-u + centre + 0.5); -(u) is exact
+                const int cv = __double2int_rz(__dadd_rn(__dadd_rn(-v, mid_v), 0.5));
+                const bool ok = (u == u) && (v == v) && (uc < p.n_u) && (vc < p.n_v) && (uc >= 0) && (vc >= 0) && (w == w) &&
+                                (w != 0.0);
+                const bool cok = (cu >= 0) && (cu < p.n_u) && (cv >= 0) && (cv < p.n_v);
+                cell[k] = ok ? uc * p.n_v + vc : -1;          // n_u * n_v < 2^31 (checked by the launcher)
+                ccell[k] = cok ? cu * p.n_v + cv : -1;
+                wv[k] = ok ? w : 0.0;
+            };
+            auto merge = [&](int k) {
+                const bool moved = cell[k] >= 0 && (cell[k] != cur || ccell[k] != cur_c);
+                const bool retire = moved && acc != 0.0;   // (cur >= 0 whenever acc != 0)
+                if (retire) reduce_out(cur, cur_c, acc);
+                acc = moved ? 0.0 : acc;
+                cur = moved ? cell[k] : cur;
+                cur_c = moved ? ccell[k] : cur_c;
+                acc += wv[k];
+                sw += wv[k];
+            };
+            if (back) {   // the halves are walked downwards on odd steps
+#pragma unroll
+                for (int k = 0; k < H; ++k) locate(k, (G / H - 1 - hh) * H + k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < H; ++k) locate(k, hh * H + k);
+            }
+            if (back) {
+#pragma unroll
+                for (int k = H - 1; k >= 0; --k) merge(k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < H; ++k) merge(k);
+            }
+        }
+    }
+    if (acc != 0.0) reduce_out(cur, cur_c, acc);
+    // sum_weight gets sel_weight * norm twice (:366-369), norm == cgk_1D[0] == 1; one reduction per plane per warp
+    sw += sw;
+    for (int ip = 0; ip < p.n_pol_out; ++ip)   // uniform trip count, so the warp stays converged
+        warp_grouped_add(p.sum_weight, plane * p.n_ip + ip, sw, in_range && sw != 0.0);
+}
+
 // sum of squares per plane -> bf[0][plane] (used as the accumulator, finalised below)
 __global__ void __launch_bounds__(256) iw_sumsq_kernel(const double *density, double *acc, long long n_cells)
 {
@@ -556,9 +716,19 @@ extern "C" int cngi_b200_imaging_weight_grid(const cngi_iw_grid_args *a, void *s
     }
     // compile-time pol count when the pol_map is the identity (the reference's wrappers always pass arange)
     const int np = (!a->pol_map && (p.n_pol == 1 || p.n_pol == 2)) ? p.n_pol : 0;
+    // fast kernel: whole channel groups, and every vector load it issues is aligned (two channels x 2 pols per 128-bit load in
+    // fp32, one pol pair per load otherwise)
+    const size_t elem = a->precision == CNGI_F32 ? 4 : 8;
+    const size_t align = (np == 2) ? ((elem == 4 && G >= 2) ? 16 : 2 * elem) : elem;
+    const bool fast = np && (p.n_chan % G == 0) && (reinterpret_cast<uintptr_t>(p.weight) % align == 0) &&
+                      (((size_t)p.n_chan * np * elem) % align == 0) && (((size_t)G * np * elem) % align == 0) &&
+                      p.n_chan <= 2048 && !env_flag("CNGI_IW_GRID_OLD");
+    const size_t fast_smem = (size_t)2 * p.n_chan * sizeof(double);   // the transposed uv_scale table
 #define CNGI_IW_LAUNCH(TT, GG)                                                      \
     do {                                                                            \
-        if (np == 2) iw_grid_kernel<TT, GG, 2><<<(unsigned)blocks, 256, 0, st>>>(p); \
+        if (fast && np == 2) iw_grid_fast_kernel<TT, GG, 2><<<(unsigned)blocks, 256, fast_smem, st>>>(p); \
+        else if (fast) iw_grid_fast_kernel<TT, GG, 1><<<(unsigned)blocks, 256, fast_smem, st>>>(p); \
+        else if (np == 2) iw_grid_kernel<TT, GG, 2><<<(unsigned)blocks, 256, 0, st>>>(p); \
         else if (np == 1) iw_grid_kernel<TT, GG, 1><<<(unsigned)blocks, 256, 0, st>>>(p); \
         else iw_grid_kernel<TT, GG, 0><<<(unsigned)blocks, 256, 0, st>>>(p);          \
     } while (0)
@@ -639,7 +809,10 @@ extern "C" int cngi_b200_imaging_weight_degrid(const cngi_iw_degrid_args *a, voi
     int rc = make_uv_scale_table(p.freq, p.n_chan, p.dl, p.dm, p.n_u, p.n_v, st, &scale);
     if (rc != CNGI_OK) return rc;
     p.scale = scale;
-    constexpr int kRows = 4;   // samples per thread in the fast path
+#ifndef CNGI_IW_DEGRID_ROWS
+#define CNGI_IW_DEGRID_ROWS 4
+#endif
+    constexpr int kRows = CNGI_IW_DEGRID_ROWS;   // samples per thread in the fast path
     const dim3 grid_mlp((unsigned)ceil_div(rows, (long long)block.y * kRows), (unsigned)gy);
     // 32-bit cell indices: every (u, v, pol) offset inside one imaging channel's planes must fit an int
     const long long span = (long long)(p.n_u - 1) * p.ds_u + (long long)(p.n_v - 1) * p.ds_v + (long long)(p.n_pol - 1) * p.ds_p;
