@@ -813,7 +813,10 @@ template <typename T, bool CPLX, int S, int PP, bool NZ, bool DUAL = false, bool
 static int launch_window_t(StdParams p, const cngi_std_grid_args *a, cudaStream_t st)
 {
     using Cfg = WinCfg<T, CPLX, S, PP, DUAL, IWF>;
-    constexpr int BLK = 128;
+#ifndef CNGI_WIN_BLK
+#define CNGI_WIN_BLK 128
+#endif
+    constexpr int BLK = CNGI_WIN_BLK;
     if (p.n_time == 0 || p.n_baseline == 0 || p.n_chan == 0 || p.n_pol == 0) return CNGI_OK;
     constexpr int kMaxChanWindow = 2048;   // 32 KB of uv-scale table per block at most
     auto kern = std_grid_window_kernel<T, CPLX, S, PP, BLK, NZ, DUAL, IWF>;
@@ -838,6 +841,12 @@ static int launch_window_t(StdParams p, const cngi_std_grid_args *a, cudaStream_
         const size_t smem = (size_t)win_smem_layout<Cfg, T>(p.oversampling, p.c_n, BLK / 32, IWF && p.iw_own_scale).total;
         CNGI_REQUIRE(smem <= 227 * 1024, "standard_grid: tap tables too large for shared memory (%zu bytes)", smem);
         CNGI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // (Measured, round 2: more resident warps do not help this kernel.  96 registers x 5 blocks -- 68 bytes of spills, with
+        // the whole unified array carved out as shared memory so that 5 blocks fit -- 1.96 ms against 1.74 ms; 160-thread
+        // blocks x 4 at 96 registers 2.00 ms; 24 warps per SM at 80 registers 2.47 ms.  CNGI_WIN_CARVEOUT = 0..100 sets the
+        // carve-out preference for such experiments; the default leaves the driver's choice.)
+        static const int carve = env_knob("CNGI_WIN_CARVEOUT", -1);
+        if (carve >= 0) CNGI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         int per_sm = 0;
         CNGI_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLK, smem));
         if (per_sm < 1) per_sm = 1;
