@@ -30,9 +30,66 @@ constexpr int YLEN = BM + (BM >> 5) * 4;      // complex work buffer, skewed by 
 // stride-4 stage (4 blocks of 32 x 4 offsets) fall into 16 different 8-byte bank pairs
 __device__ __forceinline__ int skew(int e) { return e + ((e >> 5) << 2); }
 
+#ifndef CNGI_BLU_PACKED
+#define CNGI_BLU_PACKED 1
+#endif
+#if CNGI_BLU_PACKED
+// complex add / subtract as ONE packed instruction (add.rn.f32x2 / sub.rn.f32x2, sm_100+): the butterflies' additions were
+// 33 % of the kernel's instructions as scalar FADDs (ncu, profiles/r02_bluestein_9830.txt)
+__device__ __forceinline__ float2 operator+(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 operator-(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+#else
 __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
+#if CNGI_BLU_PACKED
+// complex multiply (-accumulate) in TWO packed instructions: a * b = (ax, ay) * bx + (-ay, ax) * by.  ptxas folds the swapped,
+// half-negated copy of `a` into an operand modifier of the second one (SASS: FMUL2 t, a, bx ; FFMA2 d, -a.LO_HI.NP, by, t) --
+// no data movement, against 2 FMUL + 2 FFMA for the scalar form.
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rs, bx, by, t, rd;\n\t.reg .f32 nay;\n\t"
+        "neg.f32 nay, %3;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rs, {nay, %2};\n\t"
+        "mov.b64 bx, {%4, %4};\n\tmov.b64 by, {%5, %5};\n\t"
+        "mul.rn.f32x2 t, ra, bx;\n\tfma.rn.f32x2 rd, rs, by, t;\n\tmov.b64 {%0, %1}, rd;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+// acc + a * b
+__device__ __forceinline__ float2 cmac(float2 acc, float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rs, bx, by, t, rd;\n\t.reg .f32 nay;\n\t"
+        "neg.f32 nay, %3;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rs, {nay, %2};\n\t"
+        "mov.b64 bx, {%4, %4};\n\tmov.b64 by, {%5, %5};\n\tmov.b64 t, {%6, %7};\n\t"
+        "fma.rn.f32x2 t, ra, bx, t;\n\tfma.rn.f32x2 rd, rs, by, t;\n\tmov.b64 {%0, %1}, rd;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(acc.x), "f"(acc.y));
+    return r;
+}
+#else
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cmac(float2 acc, float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, fmaf(-a.y, b.y, acc.x)), fmaf(a.x, b.y, fmaf(a.y, b.x, acc.y)));
+}
+#endif
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // multiplication by SIGN * i
 template <int SIGN> __device__ __forceinline__ float2 rot90(float2 v) { return SIGN < 0 ? make_float2(v.y, -v.x) : make_float2(-v.y, v.x); }
@@ -48,12 +105,20 @@ template <int SIGN> __device__ __forceinline__ void dft4(float2 &a0, float2 &a1,
 template <int SIGN> __device__ __forceinline__ float2 mul_w8_1(float2 v)
 {
     const float r = 0.70710678118654752440f;
+#if CNGI_BLU_PACKED
+    return cmul(v, make_float2(r, SIGN * r));     // two packed instructions
+#else
     return make_float2((v.x - SIGN * v.y) * r, (v.y + SIGN * v.x) * r);
+#endif
 }
 template <int SIGN> __device__ __forceinline__ float2 mul_w8_3(float2 v)
 {
     const float r = 0.70710678118654752440f;
+#if CNGI_BLU_PACKED
+    return cmul(v, make_float2(-r, SIGN * r));
+#else
     return make_float2((-v.x - SIGN * v.y) * r, (-v.y + SIGN * v.x) * r);
+#endif
 }
 
 // 8-point DFT in place, natural order in and out
@@ -125,8 +190,7 @@ __device__ __forceinline__ void small_dft(const float2 (&in)[N], float2 (&out)[N
                 if ((l * k) % N == 0) {
                     acc = acc + in[l];
                 } else {
-                    acc.x = fmaf(in[l].x, c.x, fmaf(-in[l].y, c.y, acc.x));
-                    acc.y = fmaf(in[l].x, c.y, fmaf(in[l].y, c.x, acc.y));
+                    acc = cmac(acc, in[l], c);
                 }
             }
             out[k] = acc;
