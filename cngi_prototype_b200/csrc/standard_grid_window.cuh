@@ -472,11 +472,14 @@ std_grid_window_kernel(StdParams p)
                 } else {
                     for (int pos = lower; pos < upper; ++pos) red_column(lo_b + pos);
                 }
+                // bit j of `gone_mask`: accumulator j (column u == j mod W) leaves -- the run of window positions [lower, upper)
+                // rotated by the window origin; one test per accumulator instead of a subtract / mask / compare each
                 const int m = lo_b & (W - 1);
+                const unsigned run = ((1u << (upper - lower)) - 1u) << lower;
+                const unsigned gone_mask = (run << m) | (run >> (W - m));
 #pragma unroll
                 for (int j = 0; j < W; ++j) {
-                    const int pos = (j - m) & (W - 1);
-                    const bool gone = (unsigned)(pos - lower) < (unsigned)(upper - lower);
+                    const bool gone = (gone_mask >> j) & 1u;
 #pragma unroll
                     for (int n = 0; n < NV; ++n) {
                         acc[j][n].x = gone ? (T)0 : acc[j][n].x;
@@ -688,15 +691,18 @@ std_grid_window_kernel(StdParams p)
                         for (int ip = 0; ip < PP; ++ip) psw_acc[ip] += psel[ip] * norm;
                     }
                     const int need_u = cp.uc - HALF, need_v = cp.vc - HALF;
-                    // {lowest stamp cell packed v<<16|u, address of the v tap row (the lane picks its own tap from it),
-                    //  address of the u tap row rotated into accumulator order, byte offset of the stamp's first row
-                    //  inside a rotated row}
-                    const int rot_u = need_u & (W - 1);
-                    int u_row = (int)tap_s + rot_u * rot_stride + uo * ROW_BYTES;
-                    if constexpr (Cfg::DOUBLED)   // copy rot % TPV, window of 16 entries starting 16 - (rot - rot % TPV) entries in
-                        u_row = (int)tap_s + (rot_u & (Cfg::TPV - 1)) * rot_stride + uo * ROW_BYTES +
-                                ((W - (rot_u & ~(Cfg::TPV - 1))) & (W - 1)) * (int)sizeof(T);
-                    idx = make_int4((need_v << 16) | need_u, (int)tap_s + vo * ROW_BYTES, u_row, (need_v & (W - 1)) * (int)sizeof(T));
+                    // {lowest stamp cell packed v<<16|u, address of the v tap row rotated into lane order, address of the u tap
+                    //  row rotated into accumulator order, unused}
+                    auto rotated_row = [&](int need, int off) -> int {   // address of slot 0 of the row rotated by need mod W
+                        const int rot = need & (W - 1);
+                        if constexpr (Cfg::DOUBLED)   // copy rot % TPV, window of 16 entries starting 16 - (rot - rot % TPV) entries in
+                            return (int)tap_s + (rot & (Cfg::TPV - 1)) * rot_stride + off * ROW_BYTES +
+                                   ((W - (rot & ~(Cfg::TPV - 1))) & (W - 1)) * (int)sizeof(T);
+                        return (int)tap_s + rot * rot_stride + off * ROW_BYTES;
+                    };
+                    // slot j of a rotated row is the tap of the cell == j (mod W): the u row is read whole (accumulator order),
+                    // of the v row a lane reads slot r2 -- its own grid row -- so phase 2 adds only a per-lane constant
+                    idx = make_int4((need_v << 16) | need_u, rotated_row(need_v, vo), rotated_row(need_u, uo), 0);
                 }
             }
             if (sizeof(T) == 4) {
@@ -728,23 +734,27 @@ std_grid_window_kernel(StdParams p)
                 for (int j = 0; j < W; ++j) pk_fma_acc(acc[j][n], t, cv[j]);
             }
         };
+        // the item's records: running addresses instead of index arithmetic in the loop
+        constexpr int WDB = WD * (int)sizeof(T);
+        const unsigned rec0 = idx_s + k2 * (ITER + 1) * 16, wrec0 = wd_s + k2 * (ITER + 1) * WDB;
         auto consume = [&]() {
+            unsigned wrec = wrec0;
             CNGI_WIN_CONSUME_UNROLL
-            for (int i = 0; i < ITER; i += NS) {
+            for (unsigned rec = rec0; rec != rec0 + ITER * 16; rec += NS * 16, wrec += NS * WDB) {
                 int4 idx[NS];
                 T wd[NS][WD], cu[NS], cv[NS][W];
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
-                    idx[s] = lds_idx(idx_s + (k2 * (ITER + 1) + i + s) * 16);
+                    idx[s] = lds_idx(rec + s * 16);
 #pragma unroll
-                    for (int q = 0; q < WD; q += Cfg::TPV)
-                        lds_vec(wd_s + ((k2 * (ITER + 1) + i + s) * WD + q) * (int)sizeof(T), wd[s] + q);
+                    for (int q = 0; q < WD; q += Cfg::TPV)   // (equal strides: the data record sits at a constant distance)
+                        lds_vec((WDB == 16 ? rec + Cfg::IDX_BYTES : wrec) + s * WDB + q * (int)sizeof(T), wd[s] + q);
                 }
                 int misfit = 0;
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     // neither tap address depends on the window position: the table rows are pre-rotated
-                    cu[s] = lds_one(idx[s].y + ((r2 * (int)sizeof(T) - idx[s].w) & (W * (int)sizeof(T) - 1)));
+                    cu[s] = lds_one(idx[s].y + r2 * (int)sizeof(T));
 #pragma unroll
                     for (int q = 0; q < W; q += Cfg::TPV) lds_vec(idx[s].z + q * (int)sizeof(T), cv[s] + q);
                     misfit |= idx[s].x - wkey;   // both 16-bit halves of the difference must be in [0, SPARE]
