@@ -101,7 +101,7 @@ __host__ __device__ inline WinSmem win_smem_layout(int oversampling, int c_n, in
 
 // unroll factor of the phase-2 sample loop (development knob: tools/build_variant.sh ... -DCNGI_WIN_UNROLL=2)
 #ifndef CNGI_WIN_UNROLL
-#define CNGI_WIN_UNROLL 1
+#define CNGI_WIN_UNROLL 2
 #endif
 #define CNGI_STR2(x) #x
 #define CNGI_STR(x) CNGI_STR2(x)
@@ -737,18 +737,37 @@ std_grid_window_kernel(StdParams p)
         // the item's records: running addresses instead of index arithmetic in the loop
         constexpr int WDB = WD * (int)sizeof(T);
         const unsigned rec0 = idx_s + k2 * (ITER + 1) * 16, wrec0 = wd_s + k2 * (ITER + 1) * WDB;
+#ifndef CNGI_WIN_PREFETCH
+#define CNGI_WIN_PREFETCH 1
+#endif
+        // Software pipelining of phase 2 (fp32, one sample per iteration): the NEXT record is loaded before this sample's FMAs,
+        // with the loop unrolled by two so that the rotating registers are renamed instead of moved.  Measured on C2
+        // (continuum / cube, ms): plain 1.660 / 2.874, unrolled by two 1.641 / 2.870, this 1.617 / 2.849; without the unroll
+        // 1.76 (seven moves per sample), unrolled by four 1.64 / 3.73 (code size); also fetching the next sample's TAPS one
+        // sample ahead (a two-deep pipeline) 1.81 / 3.06.  After the item's last sample the load hits its pad record.
+        constexpr bool PREFETCH = CNGI_WIN_PREFETCH && NS == 1 && sizeof(T) == 4;
+        auto load_record = [&](unsigned rec, unsigned wrec, int4 &idx, T *wd) {
+            idx = lds_idx(rec);
+#pragma unroll
+            for (int q = 0; q < WD; q += Cfg::TPV)   // (equal strides: the data record sits at a constant distance)
+                lds_vec((WDB == 16 ? rec + Cfg::IDX_BYTES : wrec) + q * (int)sizeof(T), wd + q);
+        };
         auto consume = [&]() {
             unsigned wrec = wrec0;
+            int4 idx_n;
+            T wd_n[WD];
+            if constexpr (PREFETCH) load_record(rec0, wrec0, idx_n, wd_n);
             CNGI_WIN_CONSUME_UNROLL
             for (unsigned rec = rec0; rec != rec0 + ITER * 16; rec += NS * 16, wrec += NS * WDB) {
                 int4 idx[NS];
                 T wd[NS][WD], cu[NS], cv[NS][W];
+                if constexpr (PREFETCH) {
+                    idx[0] = idx_n;
 #pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    idx[s] = lds_idx(rec + s * 16);
+                    for (int q = 0; q < WD; ++q) wd[0][q] = wd_n[q];
+                } else {
 #pragma unroll
-                    for (int q = 0; q < WD; q += Cfg::TPV)   // (equal strides: the data record sits at a constant distance)
-                        lds_vec((WDB == 16 ? rec + Cfg::IDX_BYTES : wrec) + s * WDB + q * (int)sizeof(T), wd[s] + q);
+                    for (int s = 0; s < NS; ++s) load_record(rec + s * 16, wrec + s * WDB, idx[s], wd[s]);
                 }
                 int misfit = 0;
 #pragma unroll
@@ -759,6 +778,7 @@ std_grid_window_kernel(StdParams p)
                     for (int q = 0; q < W; q += Cfg::TPV) lds_vec(idx[s].z + q * (int)sizeof(T), cv[s] + q);
                     misfit |= idx[s].x - wkey;   // both 16-bit halves of the difference must be in [0, SPARE]
                 }
+                if constexpr (PREFETCH) load_record(rec + 16, wrec + WDB, idx_n, wd_n);
                 if ((misfit & kFitMask) == 0) {
 #pragma unroll
                     for (int s = 0; s < NS; ++s) fma_sample(wd[s], cu[s], cv[s]);
