@@ -15,6 +15,14 @@
 #include <algorithm>
 #include <type_traits>
 
+// unroll factor of the phase-2 sample loop (development knob)
+#ifndef CNGI_DEGRID_UNROLL
+#define CNGI_DEGRID_UNROLL 2
+#endif
+#define CNGI_DG_STR2(x) #x
+#define CNGI_DG_STR(x) CNGI_DG_STR2(x)
+#define CNGI_DEGRID_CONSUME_UNROLL _Pragma(CNGI_DG_STR(unroll CNGI_DEGRID_UNROLL))
+
 namespace cngi {
 
 struct DgwParams {
@@ -248,9 +256,10 @@ __global__ void __launch_bounds__(BLK, (sizeof(T) == 4 ? 4 : 3)) std_degrid_wind
                     const int uo = oversample_offset(cp.uc, cp.u_pos, p.oversampling) + o0;
                     const int vo = oversample_offset(cp.vc, cp.v_pos, p.oversampling) + o0;
                     const int need_u = cp.uc - HALF, need_v = cp.vc - HALF;
-                    idx = make_int4((need_v << 16) | need_u, (int)tap_s + vo * ROW_BYTES,
-                                    (int)tap_s + (need_u & (W - 1)) * rot_stride + uo * ROW_BYTES,
-                                    (need_v & (W - 1)) * (int)sizeof(T));
+                    // both tap rows pre-rotated: slot j is the tap of the cell == j (mod W), so a lane reads slot r2 of the
+                    // v row (its own grid row) with no per-sample address arithmetic, and the u row whole
+                    idx = make_int4((need_v << 16) | need_u, (int)tap_s + (need_v & (W - 1)) * rot_stride + vo * ROW_BYTES,
+                                    (int)tap_s + (need_u & (W - 1)) * rot_stride + uo * ROW_BYTES, 0);
                     if (p.normalize) fac = (T)1 / (tsum[uo] * tsum[vo]);   // 1 / (sum of the S*S taps)
                 }
             }
@@ -260,12 +269,12 @@ __global__ void __launch_bounds__(BLK, (sizeof(T) == 4 ? 4 : 3)) std_degrid_wind
 
         // ---- phase 2: consume ----------------------------------------------------------------------------------------
         auto consume = [&]() {
-#pragma unroll 1
+            CNGI_DEGRID_CONSUME_UNROLL
             for (int i = 0; i < ITER; ++i) {
                 const int slot = k2 * (ITER + 1) + i;
                 const int4 idx = idx_arr[slot];
                 const T fac = fac_arr[slot];
-                const T ca = lds_one(idx.y + ((r2 * (int)sizeof(T) - idx.w) & (ROW_BYTES - 1)));
+                const T ca = lds_one(idx.y + r2 * (int)sizeof(T));
                 T cb[W];
 #pragma unroll
                 for (int q = 0; q < W; q += Cfg::TPV) lds_vec(idx.z + q * (int)sizeof(T), cb + q);
