@@ -15,10 +15,15 @@ ncu --set full --import-source on --clock-control none -k regex:bluestein --laun
     python tools/probe_fft_one.py 9830 8192 > $O/r02_ncu_blu.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:std_grid_window --launch-skip 1 -c 1 -f -o $O/r02_window_cube \
     python tools/probe_cube_chunk.py 2000 > $O/r02_ncu_cube.log 2>&1
+if [ -z "$SKIP_APERTURE" ]; then   # (kernel unchanged since the first collection of the round: SKIP_APERTURE=1 keeps those files)
 ncu --set full --import-source on --clock-control none -k regex:aperture_track -c 1 -f -o $O/r02_aperture \
     python tools/probe_aperture.py > $O/r02_ncu_aperture.log 2>&1
 CNGI_APERTURE_BULK=1 ncu --set full --import-source on --clock-control none -k regex:aperture_track -c 1 -f -o $O/r02_aperture_bulk \
     python tools/probe_aperture.py > $O/r02_ncu_aperture_bulk.log 2>&1
+fi
+# the imaging-weight kernels, both generations (tools/probe_iw_one.py runs the general kernels, then the fast ones)
+ncu --set full --import-source on --clock-control none -k regex:"iw_grid|iw_degrid" -c 4 -f -o $O/r02_iw \
+    python tools/probe_iw_one.py > $O/r02_ncu_iw.log 2>&1
 python tools/probe_fft.py 2> $O/r02_fft.err | tail -1 > $O/r02_fft.json
 python tools/probe_fused_weights.py f32 f64 2> $O/r02_fused_weights.err | tail -1 > $O/r02_fused_weights.json
 python tools/bench_rows.py > $O/r02_rows.json 2> $O/r02_rows.err

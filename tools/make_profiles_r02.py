@@ -41,6 +41,15 @@ summary("r02_window.ncu-rep", "r02_std_grid_window_f32_continuum.txt")
 summary("r02_window_iw.ncu-rep", "r02_std_grid_window_fused_weights_f32.txt")
 summary("r02_bluestein.ncu-rep", "r02_bluestein_9830.txt")
 summary("r02_window_cube.ncu-rep", "r02_std_grid_window_f32_cube_9830.txt")
+summary("r02_iw.ncu-rep", "r02_imaging_weight_kernels.txt")
+if os.path.exists(os.path.join(G, "r02_iw.ncu-rep")):   # per-line tables of every kernel generation in that capture
+    with open(os.path.join(P, "r02_imaging_weight_kernels.txt"), "a") as f:
+        f.write("\n# iw_grid_kernel / iw_degrid_mlp_kernel: the general kernels (round 1); iw_grid_fast_kernel / iw_degrid_fast_kernel: "
+                "the product path (round 2)\n")
+        for k in ("iw_grid_kernel", "iw_grid_fast", "iw_degrid_mlp", "iw_degrid_fast"):
+            f.write("\n### %s\n" % k)
+            f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), os.path.join(G, "r02_iw.ncu-rep"),
+                                    "16", k], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout)
 summary("r02_aperture.ncu-rep", "r02_aperture_track_f32.txt")
 summary("r02_aperture_bulk.ncu-rep", "r02_aperture_track_bulk_ring_f32.txt")
 for f in ("r02_launches.csv", "r02_fft.json", "r02_fused_weights.json", "r02_rows.json"):
