@@ -110,7 +110,6 @@ struct Scratch {
         len = n;
     }
     uint8_t *data() { return p.get(); }
-    size_t size() const { return len; }
 };
 
 enum { CODEC_LZ4 = 1, CODEC_ZLIB = 3, CODEC_ZSTD = 4 };
