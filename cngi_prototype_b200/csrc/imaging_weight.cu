@@ -3,9 +3,14 @@
 //                         called from make_imaging_weight.py:153-161)
 //   A3  briggs factors    calculate_briggs_parms                                 (make_imaging_weight.py:198-213)
 //   A4  weight degrid     _standard_imaging_weight_degrid_jit                    (_standard_grid.py:466-518)
-// All three are HBM / L2-reduction bound (one or two cells per sample).  A2 walks each (baseline, chan)
-// track through time and run-length accumulates while the (cell, conjugate cell) pair is unchanged, so a
-// slowly moving baseline issues one pair of REDG.F64 per cell crossing rather than per sample.
+// One or two cells per sample.  A2 walks each (baseline, chan) track through time and run-length accumulates while the
+// (cell, conjugate cell) pair is unchanged, so a slowly moving baseline issues one pair of REDG.F64 per cell crossing
+// rather than per sample.
+// A2 and A4 exist in two generations: the general kernels (iw_grid_kernel, iw_degrid_kernel / iw_degrid_mlp_kernel: any
+// pol map, ragged channel groups, 64-bit strides) and the product kernels for what the reference's wrappers always hand
+// in (iw_grid_fast_kernel, iw_degrid_fast_kernel: identity pol map, 1 or 2 pols, whole channel groups, aligned rows, a
+// density of fewer than 2^31 cells) -- the launchers pick; CNGI_IW_GRID_OLD=1 / CNGI_IW_DEGRID_MLP=1 force the general
+// ones (tests/test_gpu_imaging_weight.py holds the generations to each other).  DESIGN.md section 4.2 has the measurements.
 #include "common.cuh"
 #include <type_traits>
 #include <cstdlib>
