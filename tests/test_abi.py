@@ -84,6 +84,34 @@ def test_sass_has_native_reductions_and_no_shared_fp_atomics(libpath):
     assert cas and all("smem_atomic_rate_kernel" in name for name in cas), cas
 
 
+def test_sass_packed_fp32_paths(libpath):
+    """What the kernels' FP32 rates rest on: the gridder's FMAs are packed FFMA2; the Bluestein butterflies
+    are packed throughout -- FADD2 for complex add / subtract, complex multiply = FMUL2 + FFMA2 with the swapped, half-negated
+    operand folded into a modifier (no scalar FADD / FMUL left in the line kernels' arithmetic); the imaging-weight product
+    kernels are in the library next to the general ones."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", libpath], stdout=subprocess.PIPE, text=True).stdout
+    funcs = {f.split("\n", 1)[0].strip(): f for f in sass.split("Function : ")[1:]}
+
+    def count(body, op):
+        return len(re.findall(r"\b%s\b" % op, body))
+    win = [b for n, b in funcs.items() if "std_grid_window_kernelIfLb1ELi7ELi2ELi128ELb0ELb0ELb0" in n]
+    assert len(win) == 1 and count(win[0], "FFMA2") >= 32 and count(win[0], "FMUL2") >= 4
+    blu = [b for n, b in funcs.items() if "bluestein_lines_kernelILi10" in n]
+    assert len(blu) == 1
+    assert count(blu[0], "FADD2") > 300 and count(blu[0], "FFMA2") > 200 and count(blu[0], "FMUL2") > 100
+    assert "LO_HI" in blu[0]                                   # the operand swizzle of the packed complex multiply
+    assert count(blu[0], "FADD") + count(blu[0], "FMUL") < 80  # scalar leftovers: address / table arithmetic only
+    for name in ("iw_grid_fast_kernelIfLi8ELi2", "iw_degrid_fast_kernelIfLi2ELi4ELb1", "iw_grid_kernelIfLi8ELi2",
+                 "iw_degrid_mlp_kernelIfLi2ELi4"):
+        assert any(name in n for n in funcs), name
+
+
 def test_no_cpu_fallback_without_gpu(libpath):
     import torch
     if torch.cuda.is_available():
